@@ -1,0 +1,140 @@
+/*
+ * acq_oracle.h -- CPU oracle for the GNSS acquisition search (reference gps/search.cpp).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may build, link or call anything under oracle/.
+ * The product (flydog_sdr_gps_b200/csrc) never includes or links it.
+ *
+ * PARITY STATUS: every stage up to the FFT input (code generators, sample mixing,
+ * half-band decimators) is pinned bit-exactly against the reference's own source
+ * compiled from /root/reference (oracle/_ref, see oracle/Makefile) and against the
+ * reference's three code known-answer tests.  The FFT arithmetic itself lives in
+ * FFTW3f, which is neither vendored nor pinned by the reference and is not
+ * installable here: at that boundary parity is UNPINNED ("parity unpinned") and
+ * is defined against (reference search.cpp + oracle FFT) -- see DESIGN.md.
+ *
+ * With default parameters (orc_params_default) this computes exactly what
+ * Sample() + Correlate() compute (gps/search.cpp:382-499).  The extra parameters
+ * (Doppler span, half-bin spacing, K non-coherent blocks) are the extensions the
+ * BASELINE.json configs ask for; their definitions are in SURVEY.md section 8(d).
+ */
+#ifndef ACQ_ORACLE_H
+#define ACQ_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_FFT_LEN 16384   /* gps/gps.h:72  FFT_LEN  */
+#define ORC_NSAMPLES 65536  /* gps/gps.h:73  NSAMPLES */
+#define ORC_DECIM 4         /* gps/gps.h:62  DECIM    */
+#define ORC_BLOCK_BYTES 8192 /* 16 SPI packets x 512 B, gps/search.cpp:389-406 */
+
+/* sat_e values of the reference (gps/gps.h:98) */
+enum { ORC_NAVSTAR = 0, ORC_SBAS = 1, ORC_QZSS = 2, ORC_E1B = 3 };
+
+/* Mirrors the leading members of SATELLITE (gps/gps.h:101-112):
+ * Navstar {prn, T1, T2}; QZSS {prn, G2_delay, G2_init}; E1B {prn, 0, 0}. */
+typedef struct {
+    int32_t prn, t1, t2, type;
+} orc_sat;
+
+typedef struct {
+    int32_t dop_lo, dop_hi; /* inclusive Doppler range, in bins (half_bin=0) or half-bins (half_bin=1) */
+    int32_t half_bin;       /* 0 = reference behaviour; 1 = extension, index h <-> (h/2) bins */
+    int32_t k_noncoh;       /* 1 = reference behaviour; K>1 sums |r|^2 over K consecutive blocks */
+    float thr_l1;           /* detection threshold for Navstar/QZSS (minimum_sig, search.cpp:70,549) */
+    float thr_e1b;          /* detection threshold for E1B (16, search.cpp:549) */
+    int32_t wrap_mode;      /* ORC_WRAP_REFERENCE (default) or ORC_WRAP_CIRCULAR, see below */
+} orc_params;
+
+/* How code-spectrum bins beyond the end of a satellite's row are fetched for NEGATIVE Doppler.
+ *
+ * The reference stores each code spectrum twice back to back (search.cpp:54,283-284) and calls
+ *     simd_multiply_conjugate_ccc(FFT_LEN, data, code[sat]+FFT_LEN-dop, prod)      (search.cpp:471)
+ * For dop < 0 the last |dop| elements read are code[sat][2*FFT_LEN .. 2*FFT_LEN+|dop|-1], i.e. they
+ * run off the end of the row into the FIRST |dop| bins of the NEXT satellite's spectrum
+ * (code[sat+1][0..|dop|-1]; all-zero rows after the last satellite, since code[] is a zeroed
+ * static with MAX_SATS=64 rows).  The intended behaviour (the #else branch, search.cpp:473-477)
+ * wraps to the satellite's own bins.  Because these bins sit next to DC, where the code spectrum
+ * is strongest, the two differ by several per cent in snr, so parity with the compiled reference
+ * needs the literal behaviour:
+ *   ORC_WRAP_REFERENCE: bins k >= N-|dop| use the next table row (zeros after the last row).
+ *   ORC_WRAP_CIRCULAR : C[(k-dop) mod N] of the same satellite. */
+enum { ORC_WRAP_REFERENCE = 0, ORC_WRAP_CIRCULAR = 1 };
+
+typedef struct {
+    int32_t sat;  /* index into the caller's sat table */
+    int32_t lag;  /* max_snr_i: code phase in /DECIM samples, [0, L) */
+    int32_t dop;  /* max_snr_dop: bins (or half-bins) */
+    float peak;   /* max_pwr at the chosen Doppler */
+    float noise;  /* ave_pwr at the chosen Doppler */
+    float snr;    /* peak / noise */
+} orc_record;
+
+/* per (sat, Doppler) entry of the optional full grid */
+typedef struct {
+    float peak;
+    float noise;
+    float snr;
+    int32_t lag;
+} orc_cell;
+
+void orc_params_default(orc_params *p);
+
+/* --- code generators (gps/cacode.h:23-64, gps/e1bcode.h:63-92) --- */
+/* 1023 chips (0/1) of the C/A code given the SATELLITE T1/T2 pair. */
+void orc_ca_chips(int t1, int t2, uint8_t *chips);
+/* 4092 chips (0/1) of E1B PRN prn (1..50). */
+void orc_e1b_chips(int prn, uint8_t *chips);
+
+/* --- building blocks, exposed so each can be pinned on its own --- */
+/* Half-band decimate-by-2 in place (search.cpp:140-166). buf holds size+31 complex floats. */
+int orc_hb_decimate(int size, float *buf);
+/* 65536 replica samples -> /4 -> 16384 complex (search.cpp:250-276, 315-338). out: 2*16384 floats. */
+void orc_code_baseband(const orc_sat *sat, float *out);
+/* code_baseband + forward FFT (search.cpp:280,342). out: 2*16384 floats. */
+void orc_code_spectrum(const orc_sat *sat, float *out);
+/* 8192 packed bytes -> mixed, /4 decimated baseband (search.cpp:398-442). out: 2*16384 floats.
+ * half_rot=1 additionally multiplies sample n by exp(-j*pi*n/16384) (half-bin extension). */
+void orc_capture_baseband(const uint8_t *packed, int half_rot, float *out);
+/* capture_baseband + forward FFT (search.cpp:447). */
+void orc_capture_spectrum(const uint8_t *packed, int half_rot, float *out);
+/* forward / backward 16384-point FFT, in place (sign -1 / +1). */
+void orc_fft16384(float *buf, int sign);
+
+/* --- the search (Sample + Correlate for every sat, search.cpp:382-499,574) ---
+ * packed: k_noncoh * 8192 bytes (consecutive 65536-sample blocks of one capture).
+ * sats/n_sats: table; sel/n_sel: indices to search (sel==NULL -> all).
+ * out: n_sel records. grid (optional, may be NULL): n_sel * n_dop cells.
+ * nthreads: OpenMP threads over sats (<=0 -> default).
+ * Returns 0, or <0 on bad arguments. */
+int orc_search(const uint8_t *packed, const orc_sat *sats, int n_sats, const int32_t *sel, int n_sel,
+               const orc_params *prm, orc_record *out, orc_cell *grid, int nthreads);
+
+/* Same search with precomputed code spectra (n_sats * 2*16384 floats) -- lets the
+ * caller amortise SearchInit's work (search.cpp:243-346) exactly like the reference. */
+int orc_search_pre(const uint8_t *packed, const orc_sat *sats, int n_sats, const float *spectra,
+                   const int32_t *sel, int n_sel, const orc_params *prm, orc_record *out,
+                   orc_cell *grid, int nthreads);
+
+/* --- deterministic synthetic capture generator (SURVEY.md 8(d) "Value distributions") --- */
+typedef struct {
+    int32_t sat;       /* index into the sat table */
+    int32_t tau;       /* code advance at sample 0, in FS samples */
+    double doppler_hz; /* carrier offset from FC */
+    double cn0_dbhz;
+    double phase;      /* carrier phase at sample 0, radians */
+    int32_t flip_ms;   /* >0: flip the sign every flip_ms milliseconds (data bits); 0: none */
+} orc_signal;
+
+/* Fills n_blocks*8192 bytes. */
+int orc_gen_capture(uint64_t seed, int n_blocks, const orc_sat *sats, int n_sats, const orc_signal *sig,
+                    int n_sig, uint8_t *packed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
