@@ -1,0 +1,66 @@
+"""ctypes binding of the C ABI (include/acq_b200.h).  Fails loudly if the CUDA library is missing:
+there is no CPU fallback anywhere in this package."""
+import ctypes as C
+import os
+
+from . import _build
+
+_lib = None
+
+
+class AcqSat(C.Structure):
+    _fields_ = [("prn", C.c_int32), ("t1", C.c_int32), ("t2", C.c_int32), ("type", C.c_int32)]
+
+
+class AcqParams(C.Structure):
+    _fields_ = [("dop_lo", C.c_int32), ("dop_hi", C.c_int32), ("half_bin", C.c_int32), ("k_noncoh", C.c_int32),
+                ("thr_l1", C.c_float), ("thr_e1b", C.c_float), ("wrap_mode", C.c_int32), ("reserved", C.c_int32)]
+
+
+# every symbol include/acq_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_SIGNATURES = [
+    ("acq_last_error", C.c_char_p, []),
+    ("acq_abi_version", C.c_int, []),
+    ("acq_params_default", C.c_int, [C.POINTER(AcqParams)]),
+    ("acq_create", C.c_int, [C.POINTER(_P), C.POINTER(AcqParams), C.POINTER(AcqSat), C.c_int, C.c_int]),
+    ("acq_destroy", C.c_int, [_P]),
+    ("acq_search", C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
+    ("acq_search_grid", C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P]),
+    ("acq_search_device", C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P]),
+    ("acq_submit", C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
+    ("acq_poll", C.c_int, [_P]),
+    ("acq_wait", C.c_int, [_P]),
+    ("acq_detected", C.c_int, [_P, _P]),
+    ("acq_get_code_spectrum", C.c_int, [_P, C.c_int, _P]),
+    ("acq_get_capture_spectrum", C.c_int, [_P, _P, C.c_int, _P, _P]),
+    ("acq_n_sats", C.c_int, [_P]),
+    ("acq_get_params", C.c_int, [_P, C.POINTER(AcqParams)]),
+    ("acq_launch_count", C.c_int64, [_P]),
+    ("acq_device_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("acq_microbench", C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_int]),
+]
+
+
+def exported_symbols():
+    return [s[0] for s in _SIGNATURES]
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load libacq_b200.so (building it first if sources are newer).  Raises if that is impossible."""
+    global _lib
+    if _lib is None:
+        path = _build.build() if _build.needs_build() else _build.LIB
+        if not os.path.exists(path):
+            raise RuntimeError("libacq_b200.so is missing and could not be built; the engine has no CPU fallback")
+        L = C.CDLL(path)
+        for name, res, args in _SIGNATURES:
+            fn = getattr(L, name)  # AttributeError if the library does not export the header's symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

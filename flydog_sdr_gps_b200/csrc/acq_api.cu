@@ -1,0 +1,621 @@
+// acq_api.cu -- the C ABI of include/acq_b200.h: engine lifetime, device memory, launch sequencing.
+// No CPU fallback exists: every entry point either runs the sm_100a kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <algorithm>
+#include <cstdarg>
+
+#include "acq_geom.h"
+#include "acq_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            return fail(ACQ_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+// Restores the caller's current device on scope exit (the host application may own other GPUs).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Galileo E1-B primary codes, packed (Galileo OS SIS ICD Annex C; see tools/gen_e1b_table.py).
+const uint32_t kE1bWords[50 * 128] = {
+#include "e1b_codes.inc"
+};
+
+// GPS C/A code (IS-GPS-200): G1 = 1 + x^3 + x^10, G2 = 1 + x^2 + x^3 + x^6 + x^8 + x^9 + x^10, both preset
+// to all ones; chip = G1[10] ^ G2[t1] ^ G2[t2].  QZSS/SBAS rows of the satellite table give the G2 preset
+// instead of taps (t1 or t2 > 10): chip = G1[10] ^ G2[10] with bit (i-1) of t2 loaded into stage i.
+// Same conventions as the reference's CACODE (gps/cacode.h:23-64).  Packs 1023 chips LSB-first.
+void ca_code_bits(int t1, int t2, uint32_t *words)
+{
+    const bool preset = (t1 > 10 || t2 > 10);
+    int g1[11], g2[11];
+    for (int i = 1; i <= 10; i++) {
+        g1[i] = 1;
+        g2[i] = preset ? ((t2 >> (i - 1)) & 1) : 1;
+    }
+    memset(words, 0, 128 * sizeof(uint32_t));
+    for (int n = 0; n < 1023; n++) {
+        const int chip = preset ? (g1[10] ^ g2[10]) : (g1[10] ^ g2[t1] ^ g2[t2]);
+        words[n >> 5] |= (uint32_t)chip << (n & 31);
+        const int f1 = g1[3] ^ g1[10];
+        const int f2 = g2[2] ^ g2[3] ^ g2[6] ^ g2[8] ^ g2[9] ^ g2[10];
+        for (int i = 10; i > 1; i--) {
+            g1[i] = g1[i - 1];
+            g2[i] = g2[i - 1];
+        }
+        g1[1] = f1;
+        g2[1] = f2;
+    }
+}
+
+}  // namespace
+
+struct acq_engine {
+    int device = 0, sm_count = 0, sm_clock_khz = 0;
+    acq_params prm{};
+    std::vector<acq_sat> sats;
+    int n_dop = 0, nvar = 1, Q = 0, ext_len = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+    int64_t launches = 0;
+
+    // persistent device data
+    float2 *d_tables = nullptr, *d_rot = nullptr, *d_C = nullptr, *d_Ep = nullptr;
+    // per-call scratch (grown on demand)
+    size_t cap_blocks = 0, cap_cells = 0, cap_rows = 0, cap_packed = 0;
+    uint8_t *d_packed = nullptr;
+    float2 *d_x1 = nullptr, *d_x2 = nullptr, *d_Dp = nullptr;
+    acq_cell *d_cells = nullptr;
+    acq_record *d_records = nullptr;
+    // selection cache
+    std::vector<int32_t> sel_cache;
+    bool sel_valid = false;
+    int n_l1 = 0, n_e1b = 0, n_slots = 0;
+    int2 *d_work = nullptr;   // [n_slots]: L1 entries first, then E1B
+    int *d_slot_sat = nullptr;
+    size_t cap_slots = 0;
+};
+
+namespace {
+
+using namespace acq;
+
+int free_engine(acq_engine *e)
+{
+    if (!e) return ACQ_OK;
+    DeviceGuard g(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_tables);
+    cudaFree(e->d_rot);
+    cudaFree(e->d_C);
+    cudaFree(e->d_Ep);
+    cudaFree(e->d_packed);
+    cudaFree(e->d_x1);
+    cudaFree(e->d_x2);
+    cudaFree(e->d_Dp);
+    cudaFree(e->d_cells);
+    cudaFree(e->d_records);
+    cudaFree(e->d_work);
+    cudaFree(e->d_slot_sat);
+    if (e->done) cudaEventDestroy(e->done);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return ACQ_OK;
+}
+
+template <typename T>
+int grow(T *&ptr, size_t &cap, size_t need_elems)
+{
+    if (need_elems <= cap && ptr) return ACQ_OK;
+    if (ptr) CU(cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    CU(cudaMalloc(&ptr, need_elems * sizeof(T)));
+    cap = need_elems;
+    return ACQ_OK;
+}
+
+int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool own_packed)
+{
+    const size_t blocks = (size_t)n_captures * e->prm.k_noncoh;
+    if (blocks > e->cap_blocks || !e->d_x1) {
+        // changing scratch under an in-flight stream is not allowed: drain first
+        CU(cudaStreamSynchronize(e->stream));
+        if (e->d_x1) CU(cudaFree(e->d_x1));
+        if (e->d_x2) CU(cudaFree(e->d_x2));
+        if (e->d_Dp) CU(cudaFree(e->d_Dp));
+        e->d_x1 = e->d_x2 = e->d_Dp = nullptr;
+        e->cap_blocks = 0;
+        CU(cudaMalloc(&e->d_x1, blocks * 32768 * sizeof(float2)));
+        CU(cudaMalloc(&e->d_x2, blocks * e->nvar * kN * sizeof(float2)));
+        CU(cudaMalloc(&e->d_Dp, blocks * e->nvar * kN * sizeof(float2)));
+        e->cap_blocks = blocks;
+    }
+    if (own_packed) {
+        int rc = grow(e->d_packed, e->cap_packed, blocks * ACQ_BLOCK_BYTES);
+        if (rc) return rc;
+    }
+    const size_t rows = (size_t)n_captures * n_slots;
+    int rc = grow(e->d_cells, e->cap_cells, rows * e->n_dop);
+    if (rc) return rc;
+    return grow(e->d_records, e->cap_rows, rows);
+}
+
+// Split the selection into the 1 ms-window (Navstar/QZSS/SBAS) and E1B work lists.
+int set_selection(acq_engine *e, const int32_t *sel, int n_sel)
+{
+    std::vector<int32_t> s;
+    if (!sel) {
+        s.resize(e->sats.size());
+        for (size_t i = 0; i < s.size(); i++) s[i] = (int32_t)i;
+    } else {
+        if (n_sel <= 0) return fail(ACQ_ERR_ARG, "n_sel must be > 0 when sel is given");
+        s.assign(sel, sel + n_sel);
+    }
+    for (int32_t v : s)
+        if (v < 0 || v >= (int32_t)e->sats.size())
+            return fail(ACQ_ERR_ARG, "satellite index %d outside the table (0..%zu)", v, e->sats.size() - 1);
+    if (e->sel_valid && s == e->sel_cache) return ACQ_OK;
+    std::vector<int2> work;
+    std::vector<int> slot_sat(s.size());
+    int n_l1 = 0;
+    for (int pass = 0; pass < 2; pass++)
+        for (size_t i = 0; i < s.size(); i++) {
+            const bool e1b = (e->sats[s[i]].type == ACQ_E1B);
+            if ((pass == 1) != e1b) continue;
+            work.push_back(make_int2(s[i], (int)i));
+            if (!e1b) n_l1++;
+        }
+    for (size_t i = 0; i < s.size(); i++) slot_sat[i] = s[i];
+    if (s.size() > e->cap_slots) {
+        CU(cudaStreamSynchronize(e->stream));
+        if (e->d_work) CU(cudaFree(e->d_work));
+        if (e->d_slot_sat) CU(cudaFree(e->d_slot_sat));
+        e->d_work = nullptr;
+        e->d_slot_sat = nullptr;
+        e->cap_slots = 0;
+        CU(cudaMalloc(&e->d_work, s.size() * sizeof(int2)));
+        CU(cudaMalloc(&e->d_slot_sat, s.size() * sizeof(int)));
+        e->cap_slots = s.size();
+    }
+    // synchronous copies (pageable source): the vectors die at return
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(e->d_work, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_slot_sat, slot_sat.data(), slot_sat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    e->sel_cache = s;
+    e->sel_valid = true;
+    e->n_l1 = n_l1;
+    e->n_e1b = (int)s.size() - n_l1;
+    e->n_slots = (int)s.size();
+    return ACQ_OK;
+}
+
+// Enqueue front end + search + best-Doppler on `st` for captures already on the device.
+int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq_record *out_dev, cudaStream_t st)
+{
+    const int K = e->prm.k_noncoh;
+    const int blocks = n_captures * K;
+    e->launches += launch_hb1_bits(packed_dev, e->d_x1, blocks, st);
+    e->launches += launch_hb2(e->d_x1, e->d_x2, e->d_rot, blocks, e->nvar, st);
+    e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar, true, e->sm_count, st);
+    SearchArgs a{};
+    a.Dp = e->d_Dp;
+    a.Ep = e->d_Ep;
+    a.tables = e->d_tables;
+    a.cells = e->d_cells;
+    a.n_slots = e->n_slots;
+    a.n_dop = e->n_dop;
+    a.dop_lo = e->prm.dop_lo;
+    a.half_bin = e->prm.half_bin;
+    a.K = K;
+    a.nvar = e->nvar;
+    a.ext_len = e->ext_len;
+    a.Q = e->Q;
+    if (e->n_l1 > 0) {
+        a.work = e->d_work;
+        a.n_work = e->n_l1;
+        a.n_tiles = (long long)n_captures * e->n_l1 * e->n_dop;
+        e->launches += launch_search(a, false, e->sm_count, st);
+    }
+    if (e->n_e1b > 0) {
+        a.work = e->d_work + e->n_l1;
+        a.n_work = e->n_e1b;
+        a.n_tiles = (long long)n_captures * e->n_e1b * e->n_dop;
+        e->launches += launch_search(a, true, e->sm_count, st);
+    }
+    e->launches += launch_best_dop(e->d_cells, e->d_slot_sat, out_dev, n_captures, e->n_slots, e->n_dop,
+                                   e->prm.dop_lo, st);
+    CU(cudaGetLastError());
+    return ACQ_OK;
+}
+
+int check_search_args(acq_engine *e, const void *packed, int n_captures, const void *out)
+{
+    if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");
+    if (!packed || !out) return fail(ACQ_ERR_ARG, "packed/out must not be NULL");
+    if (n_captures <= 0) return fail(ACQ_ERR_ARG, "n_captures must be > 0 (got %d)", n_captures);
+    if ((long long)n_captures * e->prm.k_noncoh > (1 << 24)) return fail(ACQ_ERR_ARG, "too many capture blocks");
+    if (e->pending) return fail(ACQ_ERR_ARG, "a submitted search is still pending: call acq_wait first");
+    return ACQ_OK;
+}
+
+int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel, acq_record *out,
+                acq_cell *grid, bool sync)
+{
+    int rc = check_search_args(e, packed, n_captures, out);
+    if (rc) return rc;
+    DeviceGuard g(e->device);
+    if ((rc = set_selection(e, sel, n_sel))) return rc;
+    if ((rc = ensure_scratch(e, n_captures, e->n_slots, true))) return rc;
+    const size_t bytes = (size_t)n_captures * e->prm.k_noncoh * ACQ_BLOCK_BYTES;
+    CU(cudaMemcpyAsync(e->d_packed, packed, bytes, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = enqueue_search(e, e->d_packed, n_captures, e->d_records, e->stream))) return rc;
+    const size_t rows = (size_t)n_captures * e->n_slots;
+    CU(cudaMemcpyAsync(out, e->d_records, rows * sizeof(acq_record), cudaMemcpyDeviceToHost, e->stream));
+    if (grid)
+        CU(cudaMemcpyAsync(grid, e->d_cells, rows * e->n_dop * sizeof(acq_cell), cudaMemcpyDeviceToHost, e->stream));
+    if (sync) {
+        CU(cudaStreamSynchronize(e->stream));
+    } else {
+        CU(cudaEventRecord(e->done, e->stream));
+        e->pending = true;
+    }
+    return ACQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *acq_last_error(void) { return g_err.c_str(); }
+int acq_abi_version(void) { return ACQ_ABI_VERSION; }
+
+int acq_params_default(acq_params *p)
+{
+    if (!p) return fail(ACQ_ERR_ARG, "params is NULL");
+    p->dop_lo = -20;  // int(-5000/BIN_SIZE), gps/search.cpp:465
+    p->dop_hi = 20;
+    p->half_bin = 0;
+    p->k_noncoh = 1;
+    p->thr_l1 = 16.0f;   // MIN_SIG, gps/gps.h:60
+    p->thr_e1b = 16.0f;  // gps/search.cpp:549
+    p->wrap_mode = ACQ_WRAP_REFERENCE;
+    p->reserved = 0;
+    return ACQ_OK;
+}
+
+int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, int n_sats, int device)
+{
+    if (!out) return fail(ACQ_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!sats || n_sats <= 0 || n_sats > 4096) return fail(ACQ_ERR_ARG, "bad satellite table (n_sats=%d)", n_sats);
+    acq_params prm;
+    if (params) prm = *params;
+    else acq_params_default(&prm);
+    if (prm.dop_hi < prm.dop_lo) return fail(ACQ_ERR_ARG, "dop_hi < dop_lo");
+    if (prm.k_noncoh < 1 || prm.k_noncoh > 255) return fail(ACQ_ERR_ARG, "k_noncoh must be in 1..255");
+    if (prm.half_bin != 0 && prm.half_bin != 1) return fail(ACQ_ERR_ARG, "half_bin must be 0 or 1");
+    if (prm.wrap_mode != ACQ_WRAP_REFERENCE && prm.wrap_mode != ACQ_WRAP_CIRCULAR)
+        return fail(ACQ_ERR_ARG, "bad wrap_mode");
+    const int max_idx = std::max(std::abs(prm.dop_lo), std::abs(prm.dop_hi));
+    const int max_bins = prm.half_bin ? (max_idx + 1) / 2 + 1 : max_idx;
+    if (max_bins > 2048) return fail(ACQ_ERR_ARG, "Doppler span too large (|bins| <= 2048)");
+    for (int i = 0; i < n_sats; i++) {
+        const acq_sat &s = sats[i];
+        if (s.type == ACQ_E1B) {
+            if (s.prn < 1 || s.prn > 50) return fail(ACQ_ERR_ARG, "sat %d: E1B prn %d outside 1..50", i, s.prn);
+            if (prm.k_noncoh > 1)
+                return fail(ACQ_ERR_UNSUPPORTED, "k_noncoh > 1 is implemented for Navstar/QZSS only (sat %d is E1B)", i);
+        } else if (s.type == ACQ_NAVSTAR || s.type == ACQ_QZSS || s.type == ACQ_SBAS) {
+            const bool preset = (s.t1 > 10 || s.t2 > 10);
+            if (!preset && (s.t1 < 1 || s.t2 < 1)) return fail(ACQ_ERR_ARG, "sat %d: G2 taps must be in 1..10", i);
+            if (preset && (s.t2 < 0 || s.t2 > 1023)) return fail(ACQ_ERR_ARG, "sat %d: G2 preset out of range", i);
+        } else {
+            return fail(ACQ_ERR_ARG, "sat %d: unknown type %d", i, s.type);
+        }
+    }
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(ACQ_ERR_NO_DEVICE, "no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= n_dev) return fail(ACQ_ERR_ARG, "device %d out of range (0..%d)", device, n_dev - 1);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ACQ_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+
+    DeviceGuard g(device);
+    acq_engine *e = new acq_engine;
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    e->sm_clock_khz = prop.clockRate;
+    e->prm = prm;
+    e->sats.assign(sats, sats + n_sats);
+    e->n_dop = prm.dop_hi - prm.dop_lo + 1;
+    e->nvar = prm.half_bin ? 2 : 1;
+    e->Q = max_bins / 4 + 2;
+    e->ext_len = kSub + 2 * e->Q;
+
+#define CUE(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            fail(ACQ_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            free_engine(e);                                                                         \
+            return ACQ_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+    CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUE(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
+    CUE(search_kernels_configure());
+
+    // ---- twiddle tables, constants (double precision on the host, rounded once)
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<float2> tables(kT1Elems + kT2Elems);
+    for (int n0 = 1; n0 < 16; n0++)
+        for (int t = 0; t < 256; t++) {
+            const double a = two_pi * (double)((t * n0) % 4096) / 4096.0;
+            tables[(n0 - 1) * 256 + t] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int k2 = 0; k2 < 4; k2++)
+        for (int n1 = 1; n1 < 16; n1++)
+            for (int c = 0; c < 16; c++) {
+                const double a = two_pi * (double)(((4 * c + k2) * n1) % 1024) / 1024.0;
+                tables[kT1Elems + (k2 * 15 + (n1 - 1)) * 16 + c] = make_float2((float)cos(a), (float)sin(a));
+            }
+    float2 cA[64], cC[64];
+    for (int k2 = 0; k2 < 4; k2++)
+        for (int n = 0; n < 16; n++) {
+            const double a = two_pi * (double)(k2 * n) / 16384.0, c = two_pi * (double)(k2 * n) / 64.0;
+            cA[k2 * 16 + n] = make_float2((float)cos(a), (float)sin(a));
+            cC[k2 * 16 + n] = make_float2((float)cos(c), (float)sin(c));
+        }
+    // Half-band taps of the reference (gps/search.cpp:101-136, column 0), narrowed double -> float the
+    // way its initialiser does, in application order: COEF[0], COEF[2..30 step 2], COEF[15].
+    static const double taps_even[16] = {-0.010233, 0.010668, -0.016324, 0.024377, -0.036482, 0.056990,
+                                         -0.101993, 0.316926, 0.316926,  -0.101993, 0.056990, -0.036482,
+                                         0.024377,  -0.016324, 0.010668, -0.010233};
+    float hb[17];
+    for (int i = 0; i < 16; i++) hb[i] = (float)taps_even[i];
+    hb[16] = (float)0.500009;
+    launch_tables_init(cA, cC, hb);
+    CUE(cudaGetLastError());
+    CUE(cudaMalloc(&e->d_tables, tables.size() * sizeof(float2)));
+    CUE(cudaMemcpy(e->d_tables, tables.data(), tables.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    if (e->nvar == 2) {
+        const double pi = 3.14159265358979323846264338327950288;
+        std::vector<float2> rot(kN);
+        for (int n = 0; n < kN; n++) {
+            const double a = pi * (double)n / (double)kN;
+            rot[n] = make_float2((float)cos(a), (float)(-sin(a)));
+        }
+        CUE(cudaMalloc(&e->d_rot, kN * sizeof(float2)));
+        CUE(cudaMemcpy(e->d_rot, rot.data(), kN * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+
+    // ---- code spectra (replaces the loops at gps/search.cpp:243-346)
+    std::vector<uint32_t> chips((size_t)n_sats * 128);
+    std::vector<int> codelen_boc((size_t)n_sats * 2);
+    for (int i = 0; i < n_sats; i++) {
+        if (sats[i].type == ACQ_E1B) {
+            memcpy(&chips[(size_t)i * 128], &kE1bWords[(sats[i].prn - 1) * 128], 128 * sizeof(uint32_t));
+            codelen_boc[2 * i] = 4092;
+            codelen_boc[2 * i + 1] = 1;
+        } else {
+            ca_code_bits(sats[i].t1, sats[i].t2, &chips[(size_t)i * 128]);
+            codelen_boc[2 * i] = 1023;
+            codelen_boc[2 * i + 1] = 0;
+        }
+    }
+    uint32_t *d_chips = nullptr;
+    int *d_clb = nullptr;
+    float2 *d_x1 = nullptr, *d_x2 = nullptr;
+    cudaError_t ce = cudaSuccess;
+    do {
+        if ((ce = cudaMalloc(&d_chips, chips.size() * sizeof(uint32_t)))) break;
+        if ((ce = cudaMalloc(&d_clb, codelen_boc.size() * sizeof(int)))) break;
+        if ((ce = cudaMalloc(&d_x1, (size_t)n_sats * 32768 * sizeof(float2)))) break;
+        if ((ce = cudaMalloc(&d_x2, (size_t)n_sats * kN * sizeof(float2)))) break;
+        if ((ce = cudaMalloc(&e->d_C, (size_t)n_sats * kN * sizeof(float2)))) break;
+        if ((ce = cudaMalloc(&e->d_Ep, (size_t)n_sats * 4 * e->ext_len * sizeof(float2)))) break;
+        if ((ce = cudaMemcpy(d_chips, chips.data(), chips.size() * sizeof(uint32_t), cudaMemcpyHostToDevice))) break;
+        if ((ce = cudaMemcpy(d_clb, codelen_boc.data(), codelen_boc.size() * sizeof(int), cudaMemcpyHostToDevice)))
+            break;
+        e->launches += launch_hb1_code(d_chips, d_clb, d_x1, n_sats, e->stream);
+        e->launches += launch_hb2(d_x1, d_x2, nullptr, n_sats, 1, e->stream);
+        e->launches += launch_fwd_fft(d_x2, e->d_C, e->d_tables, n_sats, false, e->sm_count, e->stream);
+        e->launches += launch_build_ext(e->d_C, e->d_Ep, n_sats, e->Q, e->ext_len, prm.wrap_mode, e->stream);
+        if ((ce = cudaGetLastError())) break;
+        ce = cudaStreamSynchronize(e->stream);
+    } while (0);
+    cudaFree(d_chips);
+    cudaFree(d_clb);
+    cudaFree(d_x1);
+    cudaFree(d_x2);
+    CUE(ce);
+#undef CUE
+    *out = e;
+    return ACQ_OK;
+}
+
+int acq_destroy(acq_engine *e) { return free_engine(e); }
+
+int acq_search(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel, acq_record *out)
+{
+    return search_host(e, packed, n_captures, sel, n_sel, out, nullptr, true);
+}
+
+int acq_search_grid(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel,
+                    acq_record *out, acq_cell *grid)
+{
+    if (!grid) return fail(ACQ_ERR_ARG, "grid is NULL");
+    return search_host(e, packed, n_captures, sel, n_sel, out, grid, true);
+}
+
+int acq_search_device(acq_engine *e, const uint8_t *packed_dev, int n_captures, const int32_t *sel, int n_sel,
+                      acq_record *out_dev, void *stream)
+{
+    int rc = check_search_args(e, packed_dev, n_captures, out_dev);
+    if (rc) return rc;
+    DeviceGuard g(e->device);
+    if ((rc = set_selection(e, sel, n_sel))) return rc;
+    if ((rc = ensure_scratch(e, n_captures, e->n_slots, false))) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    return enqueue_search(e, packed_dev, n_captures, out_dev, st);
+}
+
+int acq_submit(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel, acq_record *out)
+{
+    return search_host(e, packed, n_captures, sel, n_sel, out, nullptr, false);
+}
+
+int acq_poll(acq_engine *e)
+{
+    if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");
+    if (!e->pending) return 1;
+    DeviceGuard g(e->device);
+    cudaError_t q = cudaEventQuery(e->done);
+    if (q == cudaSuccess) {
+        e->pending = false;
+        return 1;
+    }
+    if (q == cudaErrorNotReady) return 0;
+    e->pending = false;
+    return fail(ACQ_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(q));
+}
+
+int acq_wait(acq_engine *e)
+{
+    if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");
+    if (!e->pending) return ACQ_OK;
+    DeviceGuard g(e->device);
+    e->pending = false;
+    CU(cudaEventSynchronize(e->done));
+    return ACQ_OK;
+}
+
+int acq_detected(const acq_engine *e, const acq_record *r)
+{
+    if (!e || !r || r->sat < 0 || r->sat >= (int)e->sats.size()) return 0;
+    const float thr = (e->sats[r->sat].type == ACQ_E1B) ? e->prm.thr_e1b : e->prm.thr_l1;
+    return r->snr >= thr ? 1 : 0;  // search.cpp:591: if (snr < min_sig) continue;
+}
+
+int acq_get_code_spectrum(acq_engine *e, int sat, float *out)
+{
+    if (!e || !out) return fail(ACQ_ERR_ARG, "NULL argument");
+    if (sat < 0 || sat >= (int)e->sats.size()) return fail(ACQ_ERR_ARG, "sat %d outside the table", sat);
+    DeviceGuard g(e->device);
+    CU(cudaMemcpy(out, e->d_C + (size_t)sat * kN, kN * sizeof(float2), cudaMemcpyDeviceToHost));
+    return ACQ_OK;
+}
+
+int acq_get_capture_spectrum(acq_engine *e, const uint8_t *packed, int half_rot, float *x2, float *D)
+{
+    if (!e || !packed) return fail(ACQ_ERR_ARG, "NULL argument");
+    if (half_rot != 0 && half_rot != 1) return fail(ACQ_ERR_ARG, "half_rot must be 0 or 1");
+    if (e->pending) return fail(ACQ_ERR_ARG, "a submitted search is still pending");
+    DeviceGuard g(e->device);
+    uint8_t *d_pk = nullptr;
+    float2 *d_x1 = nullptr, *d_x2 = nullptr, *d_D = nullptr, *d_rot = nullptr;
+    std::vector<float2> rot;
+    int rc = ACQ_OK;
+    cudaError_t ce = cudaSuccess;
+    do {
+        if ((ce = cudaMalloc(&d_pk, ACQ_BLOCK_BYTES))) break;
+        if ((ce = cudaMalloc(&d_x1, 32768 * sizeof(float2)))) break;
+        if ((ce = cudaMalloc(&d_x2, 2 * kN * sizeof(float2)))) break;
+        if ((ce = cudaMalloc(&d_D, kN * sizeof(float2)))) break;
+        if ((ce = cudaMemcpy(d_pk, packed, ACQ_BLOCK_BYTES, cudaMemcpyHostToDevice))) break;
+        const float2 *rotp = e->d_rot;
+        if (half_rot && !rotp) {
+            const double pi = 3.14159265358979323846264338327950288;
+            rot.resize(kN);
+            for (int n = 0; n < kN; n++) {
+                const double a = pi * (double)n / (double)kN;
+                rot[n] = make_float2((float)cos(a), (float)(-sin(a)));
+            }
+            if ((ce = cudaMalloc(&d_rot, kN * sizeof(float2)))) break;
+            if ((ce = cudaMemcpy(d_rot, rot.data(), kN * sizeof(float2), cudaMemcpyHostToDevice))) break;
+            rotp = d_rot;
+        }
+        e->launches += launch_hb1_bits(d_pk, d_x1, 1, e->stream);
+        e->launches += launch_hb2(d_x1, d_x2, rotp, 1, half_rot ? 2 : 1, e->stream);
+        const float2 *sel_x2 = d_x2 + (half_rot ? kN : 0);
+        e->launches += launch_fwd_fft(sel_x2, d_D, e->d_tables, 1, false, e->sm_count, e->stream);
+        if ((ce = cudaGetLastError())) break;
+        if ((ce = cudaStreamSynchronize(e->stream))) break;
+        if (x2 && (ce = cudaMemcpy(x2, sel_x2, kN * sizeof(float2), cudaMemcpyDeviceToHost))) break;
+        if (D && (ce = cudaMemcpy(D, d_D, kN * sizeof(float2), cudaMemcpyDeviceToHost))) break;
+    } while (0);
+    cudaFree(d_pk);
+    cudaFree(d_x1);
+    cudaFree(d_x2);
+    cudaFree(d_D);
+    cudaFree(d_rot);
+    if (ce != cudaSuccess) rc = fail(ACQ_ERR_CUDA, "acq_get_capture_spectrum: %s", cudaGetErrorString(ce));
+    return rc;
+}
+
+int acq_n_sats(const acq_engine *e) { return e ? (int)e->sats.size() : fail(ACQ_ERR_ARG, "engine is NULL"); }
+
+int acq_get_params(const acq_engine *e, acq_params *p)
+{
+    if (!e || !p) return fail(ACQ_ERR_ARG, "NULL argument");
+    *p = e->prm;
+    return ACQ_OK;
+}
+
+int64_t acq_launch_count(const acq_engine *e) { return e ? e->launches : 0; }
+
+int acq_device_info(const acq_engine *e, int *device, int *sm_count, int *sm_clock_khz)
+{
+    if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");
+    if (device) *device = e->device;
+    if (sm_count) *sm_count = e->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = e->sm_clock_khz;
+    return ACQ_OK;
+}
+
+}  // extern "C"

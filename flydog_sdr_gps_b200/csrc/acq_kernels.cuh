@@ -1,0 +1,37 @@
+// acq_kernels.cuh -- launch-side declarations shared by acq_kernels.cu and acq_api.cu.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/acq_b200.h"
+
+namespace acq {
+
+// Arguments of the fused correlate + inverse-FFT + peak-search kernel (one "tile" = one
+// (capture, satellite, Doppler index); a tile runs k_noncoh inverse FFTs).
+struct SearchArgs {
+    const float2 *Dp;      // capture spectra, polyphase: [((cap*K + b)*nvar + v)*4 + k2][4096], D[4*k1 + k2]
+    const float2 *Ep;      // extended code spectra, polyphase: [(sat*4 + r)][ext_len], E[4*(m - Q) + r]
+    const float2 *tables;  // twiddle tables (kT1Elems + kT2Elems float2)
+    const int2 *work;      // [n_work] (sat, output slot)
+    acq_cell *cells;       // [cap][n_slots][n_dop]
+    long long n_tiles;
+    int n_work, n_slots, n_dop, dop_lo, half_bin, K, nvar, ext_len, Q;
+};
+
+// host-side launchers (all asynchronous on `st`; each returns the number of kernels it launched)
+int launch_tables_init(const float2 *h_cA, const float2 *h_cC, const float *h_hb);
+int launch_hb1_bits(const uint8_t *packed, float2 *x1, int n_blocks, cudaStream_t st);
+int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
+int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, cudaStream_t st);
+int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_rows, bool polyphase, int sm_count,
+                   cudaStream_t st);
+int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len, int wrap_mode, cudaStream_t st);
+int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st);
+int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
+                    int dop_lo, cudaStream_t st);
+cudaError_t search_kernels_configure();
+size_t search_smem_bytes(bool e1b);
+
+}  // namespace acq
