@@ -37,6 +37,8 @@ _SIGNATURES = [
     ("acq_n_sats", C.c_int, [_P]),
     ("acq_get_params", C.c_int, [_P, C.POINTER(AcqParams)]),
     ("acq_launch_count", C.c_int64, [_P]),
+    ("acq_set_profiling", C.c_int, [_P, C.c_int]),
+    ("acq_get_kernel_ms", C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     ("acq_device_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("acq_microbench", C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_int]),
 ]

@@ -95,6 +95,8 @@ struct acq_engine {
     cudaEvent_t done = nullptr;
     bool pending = false;
     int64_t launches = 0;
+    bool profiling = false, prof_valid = false;
+    cudaEvent_t prof[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // persistent device data
     float2 *d_tables = nullptr, *d_rot = nullptr, *d_C = nullptr, *d_Ep = nullptr;
@@ -135,6 +137,8 @@ int free_engine(acq_engine *e)
     cudaFree(e->d_work);
     cudaFree(e->d_slot_sat);
     if (e->done) cudaEventDestroy(e->done);
+    for (cudaEvent_t ev : e->prof)
+        if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return ACQ_OK;
@@ -232,9 +236,14 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
 {
     const int K = e->prm.k_noncoh;
     const int blocks = n_captures * K;
+    const bool prof = e->profiling;
+    if (prof) CU(cudaEventRecord(e->prof[0], st));
     e->launches += launch_hb1_bits(packed_dev, e->d_x1, blocks, st);
+    if (prof) CU(cudaEventRecord(e->prof[1], st));
     e->launches += launch_hb2(e->d_x1, e->d_x2, e->d_rot, blocks, e->nvar, st);
+    if (prof) CU(cudaEventRecord(e->prof[2], st));
     e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar, true, e->sm_count, st);
+    if (prof) CU(cudaEventRecord(e->prof[3], st));
     SearchArgs a{};
     a.Dp = e->d_Dp;
     a.Ep = e->d_Ep;
@@ -260,8 +269,13 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         a.n_tiles = (long long)n_captures * e->n_e1b * e->n_dop;
         e->launches += launch_search(a, true, e->sm_count, st);
     }
+    if (prof) CU(cudaEventRecord(e->prof[4], st));
     e->launches += launch_best_dop(e->d_cells, e->d_slot_sat, out_dev, n_captures, e->n_slots, e->n_dop,
                                    e->prm.dop_lo, st);
+    if (prof) {
+        CU(cudaEventRecord(e->prof[5], st));
+        e->prof_valid = true;
+    }
     CU(cudaGetLastError());
     return ACQ_OK;
 }
@@ -608,6 +622,27 @@ int acq_get_params(const acq_engine *e, acq_params *p)
 }
 
 int64_t acq_launch_count(const acq_engine *e) { return e ? e->launches : 0; }
+
+int acq_set_profiling(acq_engine *e, int enable)
+{
+    if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");
+    DeviceGuard g(e->device);
+    if (enable && !e->prof[0])
+        for (cudaEvent_t &ev : e->prof) CU(cudaEventCreate(&ev));
+    e->profiling = enable != 0;
+    if (!enable) e->prof_valid = false;
+    return ACQ_OK;
+}
+
+int acq_get_kernel_ms(acq_engine *e, float *out, int n_out)
+{
+    if (!e || !out || n_out < 5) return fail(ACQ_ERR_ARG, "bad argument");
+    if (!e->prof_valid) return fail(ACQ_ERR_ARG, "no profiled search yet (call acq_set_profiling first)");
+    DeviceGuard g(e->device);
+    CU(cudaEventSynchronize(e->prof[5]));
+    for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(&out[i], e->prof[i], e->prof[i + 1]));
+    return ACQ_OK;
+}
 
 int acq_device_info(const acq_engine *e, int *device, int *sm_count, int *sm_clock_khz)
 {

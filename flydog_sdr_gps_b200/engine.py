@@ -97,6 +97,15 @@ class AcqEngine:
     def launch_count(self):
         return int(self._L.acq_launch_count(self._h))
 
+    def set_profiling(self, on=True):
+        _check(self._L.acq_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_ms(self):
+        """Device time of each kernel of the most recent search (needs set_profiling(True))."""
+        out = (C.c_float * 5)()
+        _check(self._L.acq_get_kernel_ms(self._h, out, 5))
+        return dict(zip(["hb1", "hb2", "fwd_fft", "search", "best_dop"], [float(v) for v in out]))
+
     def device_info(self):
         d, s, c = C.c_int(), C.c_int(), C.c_int()
         _check(self._L.acq_device_info(self._h, C.byref(d), C.byref(s), C.byref(c)))

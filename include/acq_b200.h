@@ -166,6 +166,13 @@ int acq_n_sats(const acq_engine *e);
 int acq_get_params(const acq_engine *e, acq_params *p);
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 int64_t acq_launch_count(const acq_engine *e);
+/* Per-kernel device timing of the most recent search (CUDA events recorded on the launching stream
+ * around each kernel when enabled).  acq_get_kernel_ms waits for that search and fills
+ *   out[0] = unpack+mix+half-band 1, out[1] = half-band 2, out[2] = forward FFT,
+ *   out[3] = fused correlate + inverse FFT + peak search (all constellations), out[4] = best-Doppler pick
+ * in milliseconds; n_out >= 5. */
+int acq_set_profiling(acq_engine *e, int enable);
+int acq_get_kernel_ms(acq_engine *e, float *out, int n_out);
 /* Device ordinal and SM count of the engine's GPU. */
 int acq_device_info(const acq_engine *e, int *device, int *sm_count, int *sm_clock_khz);
 

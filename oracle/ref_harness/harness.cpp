@@ -37,10 +37,11 @@ bool admcfg_bool(const char *, bool *, int) { return true; }
 static unsigned g_fake_time_us;
 unsigned timer_us(void) { return g_fake_time_us += 1000; }
 
-void NextTask(const char *)
+void NextTask(const char *where)
 {
-    /* SearchTask spins on NextTask("busy1") when every sat is busy (search.cpp:551-554) */
-    if (++g_idle_yields > 100000) throw ref_stop_exception{1};
+    /* SearchTask spins on NextTask("busy1") when every sat is busy (search.cpp:551-554):
+     * stop the literal loop once a whole table's worth of sats has been skipped in a row */
+    if (where && strcmp(where, "busy1") == 0 && ++g_idle_yields > 4 * MAX_SATS) throw ref_stop_exception{1};
 }
 void NextTaskP(const char *, int) {}
 void TaskSleepUsec(int) {}

@@ -1,0 +1,79 @@
+"""CPU suite: the C-ABI library builds for sm_100a, loads, and exports every symbol the header declares.
+No compute call is made here (there is no GPU in the development container and no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from flydog_sdr_gps_b200 import _build, _lib, engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "acq_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(acq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    path = _build.build()
+    assert os.path.exists(path)
+    L = C.CDLL(path)
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), "libacq_b200.so does not export %s" % n
+    # the ctypes binding covers the same set
+    assert sorted(_lib.exported_symbols()) == names
+
+
+def test_struct_layouts_match_header():
+    assert engine.RECORD_DTYPE.itemsize == 24  # acq_record
+    assert engine.CELL_DTYPE.itemsize == 16    # acq_cell
+    assert C.sizeof(_lib.AcqSat) == 16
+    assert C.sizeof(_lib.AcqParams) == 32
+
+
+def test_defaults_are_the_reference_constants():
+    p = engine.default_params()
+    assert (p.dop_lo, p.dop_hi, p.half_bin, p.k_noncoh) == (-20, 20, 0, 1)  # gps/search.cpp:465
+    assert p.thr_l1 == 16.0 and p.thr_e1b == 16.0                            # gps/gps.h:60, search.cpp:549
+    assert p.wrap_mode == engine.WRAP_REFERENCE
+    assert _lib.load().acq_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device engine creation must fail loudly, never compute on the host."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from flydog_sdr_gps_b200 import sats
+    with pytest.raises(engine.AcqError) as ei:
+        engine.AcqEngine(sats.navstar())
+    assert ei.value.code == -3  # ACQ_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_argument_errors_without_gpu():
+    L = _lib.load()
+    assert L.acq_params_default(None) == -1
+    h = C.c_void_p()
+    assert L.acq_create(C.byref(h), None, None, 0, 0) == -1
+    assert b"satellite table" in L.acq_last_error()
+    assert L.acq_destroy(None) == 0
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "flydog_sdr_gps_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_py" not in text and "acq_oracle" not in text and "orc_fft" not in text, f

@@ -1,0 +1,286 @@
+"""GPU parity suite (-m gpu): the CUDA engine, called through the C ABI, against the CPU oracle on the
+same bytes, against the golden vectors of the unmodified reference, and through size-independent
+properties at the full BASELINE sizes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import flydog_sdr_gps_b200 as F
+from flydog_sdr_gps_b200 import _lib, scenarios, synth
+from flydog_sdr_gps_b200 import sats as S
+
+from parity import RTOL, compare_records
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref_engine(gpu_required):
+    eng = F.AcqEngine(S.reference_table())
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def nav_engine(gpu_required):
+    eng = F.AcqEngine(S.navstar())
+    yield eng
+    eng.close()
+
+
+def test_native_library_is_loaded(gpu_required):
+    import os
+    maps = open("/proc/self/maps").read()
+    _lib.load()
+    maps = open("/proc/self/maps").read()
+    assert os.path.basename(_lib.lib_path()) in maps
+    info = F.AcqEngine(S.navstar()[:2]).device_info()
+    assert info["sm_count"] >= 100
+
+
+def test_code_spectra_match_oracle(ref_engine, oracle):
+    table = S.reference_table()
+    for k in range(len(table)):
+        c = ref_engine.code_spectrum(k)
+        o = oracle.code_spectrum(table[k])
+        assert np.abs(c - o).max() / np.abs(o).max() < 1e-5, k
+
+
+def test_front_end_bit_exact_and_spectrum(ref_engine, oracle, golden_search, golden_stages):
+    cap = golden_search["captures"][0]
+    x2, D = ref_engine.capture_spectrum(cap)
+    assert np.array_equal(x2, golden_stages["x2"])  # bit-exact vs the unmodified reference
+    assert np.abs(D - golden_stages["D"]).max() / np.abs(golden_stages["D"]).max() < 1e-5
+    for seed in (1, 2):
+        cap = synth.make_capture(seed, 1, S.navstar(), scenarios.signals("cfg1", seed))
+        x2, D = ref_engine.capture_spectrum(cap)
+        assert np.array_equal(x2, oracle.capture_baseband(cap))
+        x2h, Dh = ref_engine.capture_spectrum(cap, 1)
+        assert np.array_equal(x2h, oracle.capture_baseband(cap, 1))
+        oD = oracle.capture_spectrum(cap, 1)
+        assert np.abs(Dh - oD).max() / np.abs(oD).max() < 1e-5
+
+
+def test_golden_reference_vectors(ref_engine, golden_search):
+    """Engine vs the answers of the unmodified reference (all 59 sats, 5 captures): decisions exact."""
+    table = S.reference_table()
+    caps = golden_search["captures"]
+    rec = ref_engine.search(caps.reshape(-1))
+    assert rec.shape == (len(caps), len(table))
+    for i in range(len(caps)):
+        thr = 16.0
+        strong = golden_search["snr"][i] >= thr * (1 + RTOL)
+        assert np.array_equal(rec[i]["dop"][strong], golden_search["dop"][i][strong])
+        assert np.array_equal(rec[i]["lag"][strong], golden_search["lag"][i][strong])
+        np.testing.assert_allclose(rec[i]["snr"], golden_search["snr"][i], rtol=RTOL)
+        # all sats, not only detected ones, agree unless a numerical tie (none expected on these fixtures)
+        assert np.array_equal(rec[i]["dop"], golden_search["dop"][i])
+        assert np.array_equal(rec[i]["lag"], golden_search["lag"][i])
+        assert np.array_equal(ref_engine.detected(rec[i])[np.abs(golden_search["snr"][i] / thr - 1) > RTOL],
+                              (golden_search["snr"][i] >= thr)[np.abs(golden_search["snr"][i] / thr - 1) > RTOL])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_cfg1_cold_start(nav_engine, oracle, seed):
+    table = S.navstar()
+    cap = synth.make_capture(seed, 1, table, scenarios.signals("cfg1", seed))
+    rec, grid = nav_engine.search(cap, want_grid=True)
+    orec, ogrid = oracle.search(cap, table, want_grid=True)
+    compare_records(rec[0], orec, ogrid, -20, 16.0, ggrid=grid[0])
+    assert (orec["snr"] >= 16).sum() >= 5
+
+
+def test_cfg2_weak_signal_half_bin_noncoherent(gpu_required, oracle):
+    table = scenarios.table("cfg2")
+    kw = scenarios.params_kw("cfg2")
+    sig = scenarios.signals("cfg2", 1)
+    cap = synth.make_capture(21, kw["k_noncoh"], table, sig)
+    with F.AcqEngine(table, F.default_params(**kw)) as eng:
+        rec, grid = eng.search(cap, want_grid=True)
+    okw = {k: v for k, v in kw.items()}
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**okw), want_grid=True)
+    compare_records(rec[0], orec, ogrid, kw["dop_lo"], kw["thr_l1"], ggrid=grid[0], max_ties=1)
+    found = {int(r["sat"]) for r in rec[0] if r["snr"] >= kw["thr_l1"]}
+    strong = {s[0] for s in sig if s[3] >= 32.5}
+    assert strong <= found
+
+
+def test_cfg3_galileo_e1b(gpu_required, oracle):
+    table = scenarios.table("cfg3")
+    kw = scenarios.params_kw("cfg3")
+    cap = synth.make_capture(31, 1, table, scenarios.signals("cfg3", 1))
+    with F.AcqEngine(table, F.default_params(**kw)) as eng:
+        rec, grid = eng.search(cap, want_grid=True)
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
+    compare_records(rec[0], orec, ogrid, kw["dop_lo"], 16.0, ggrid=grid[0], max_ties=1)
+    assert (orec["snr"] >= 16).sum() >= 4
+
+
+def test_cfg4_combined_sharded_by_satellite(gpu_required, oracle):
+    """82 PRNs on one capture; sharding the satellite list over 'ranks' gives the same records."""
+    table = scenarios.table("cfg4")
+    cap = synth.make_capture(41, 1, table, scenarios.signals("cfg4", 1))
+    with F.AcqEngine(table) as eng:
+        whole, grid = eng.search(cap, want_grid=True)
+        parts = []
+        for world in (2, 4, 8):
+            recs = []
+            for rank in range(world):
+                lo, hi = scenarios.shard(len(table), rank, world)
+                recs.append(eng.search(cap, sel=np.arange(lo, hi, dtype=np.int32))[0])
+            parts.append(np.concatenate(recs))
+    for p in parts:
+        assert p.tobytes() == whole[0].tobytes()  # bitwise identical however the list is split
+    orec, ogrid = oracle.search(cap, table, want_grid=True)
+    compare_records(whole[0], orec, ogrid, -20, 16.0, ggrid=grid[0], max_ties=1)
+
+
+def test_cfg5_receiver_farm_properties(nav_engine, oracle):
+    """1024 captures x 32 PRNs in one call (5.5e9 cells): checked through properties plus an oracle sample."""
+    import torch
+    table = S.navstar()
+    n_cap = 1024
+    distinct = 16
+    sigs = [scenarios.signals("cfg5", s % distinct) for s in range(n_cap)]
+    base = synth.make_captures_torch(5, distinct, 1, table, sigs[:distinct], "cuda").cpu().numpy()
+    caps = base[np.arange(n_cap) % distinct]  # capture c is a copy of capture c % 16
+    rec = nav_engine.search(caps.reshape(-1))
+    assert rec.shape == (n_cap, 32)
+    # (i) independence: identical captures give bitwise identical records wherever they sit in the batch
+    for c in range(distinct, n_cap):
+        assert rec[c].tobytes() == rec[c % distinct].tobytes()
+    # (ii) batch == one-at-a-time
+    for c in (0, 5, 15):
+        assert nav_engine.search(caps[c])[0].tobytes() == rec[c].tobytes()
+    # (iii) oracle on a sample of the distinct captures
+    for c in (0, 7, 15):
+        orec, ogrid = oracle.search(caps[c], table, want_grid=True)
+        compare_records(rec[c], orec, ogrid, -20, 16.0, max_ties=1)
+    # (iv) every strong injected satellite is detected at its injected lag / Doppler bin
+    for c in range(distinct):
+        for sat, tau, f, cn0, _ in sigs[c]:
+            if cn0 >= 45:
+                r = rec[c][sat]
+                assert r["snr"] >= 16 and abs(((r["lag"] - tau / 4.0 + 2046) % 4092) - 2046) <= 1
+                assert r["dop"] == int(np.round(f / F.BIN_HZ))
+
+
+def test_lag_and_doppler_sweep(nav_engine):
+    """Round trip: inject one strong satellite at many (tau, Doppler); the record returns them."""
+    table = S.navstar()
+    rng = np.random.default_rng(8)
+    caps, want = [], []
+    for k in range(24):
+        sat = int(rng.integers(0, 32))
+        tau = int(rng.integers(0, 4092)) * 4
+        dop = int(rng.integers(-20, 21))
+        caps.append(synth.make_capture(100 + k, 1, table, [(sat, tau, dop * F.BIN_HZ, 50, float(rng.uniform(0, 6)))]))
+        want.append((sat, tau // 4, dop))
+    rec = nav_engine.search(np.concatenate(caps))
+    for k, (sat, lag, dop) in enumerate(want):
+        r = rec[k][sat]
+        assert (r["lag"], r["dop"]) == (lag, dop) and r["snr"] > 50
+
+
+def test_wrap_modes(gpu_required, oracle):
+    """ACQ_WRAP_REFERENCE reproduces the compiled reference's row overrun; ACQ_WRAP_CIRCULAR the intended wrap."""
+    table = S.reference_table()
+    cap = synth.make_capture(77, 1, table, [(3, 777, -4000.0, 47, 0.1), (58, 40000, -2000.0, 47, 0.2)])
+    sel = np.array([3, 31, 35, 36, 58], np.int32)
+    for mode in (F.WRAP_REFERENCE, F.WRAP_CIRCULAR):
+        with F.AcqEngine(table, F.default_params(wrap_mode=mode)) as eng:
+            rec, grid = eng.search(cap, sel=sel, want_grid=True)
+        orec, ogrid = oracle.search(cap, table, sel=sel, params=oracle.default_params(wrap_mode=mode), want_grid=True)
+        compare_records(rec[0], orec, ogrid, -20, 16.0, ggrid=grid[0])
+
+
+def test_selection_order_repeats_and_qzss(ref_engine, oracle):
+    table = S.reference_table()
+    cap = synth.make_capture(55, 1, table, [(33, 1234, 500.0, 48, 0.3), (2, 4444, -1000.0, 48, 0.3), (40, 50000, 0.0, 48, 1.0)])
+    sel = np.array([40, 2, 33, 2, 58, 0], np.int32)  # mixed constellations, a repeat, arbitrary order
+    rec = ref_engine.search(cap, sel=sel)[0]
+    assert np.array_equal(rec["sat"], sel)
+    orec, ogrid = oracle.search(cap, table, sel=sel, want_grid=True)
+    compare_records(rec, orec, ogrid, -20, 16.0)
+    assert rec[1].tobytes() == rec[3].tobytes()
+    one = ref_engine.search(cap, sel=np.array([33], np.int32))[0]
+    assert one[0].tobytes() == rec[2].tobytes()
+
+
+def test_degenerate_captures(nav_engine, oracle):
+    """All-zero and all-one bit captures (a dead front end) follow the reference arithmetic too."""
+    table = S.navstar()
+    for fill in (0x00, 0xFF, 0xAA):
+        cap = np.full(8192, fill, np.uint8)
+        rec, grid = nav_engine.search(cap, sel=np.arange(4, dtype=np.int32), want_grid=True)
+        orec, ogrid = oracle.search(cap, table, sel=np.arange(4), want_grid=True)
+        ok = np.isfinite(ogrid["snr"])
+        assert np.array_equal(np.isfinite(grid[0]["snr"]), ok)
+        if ok.all():
+            compare_records(rec[0], orec, ogrid, -20, 16.0, max_ties=4)
+
+
+def test_asymmetric_doppler_range_and_single_bin(gpu_required, oracle):
+    table = S.navstar()
+    cap = synth.make_capture(66, 1, table, [(9, 2000, 3 * F.BIN_HZ, 48, 0.3)])
+    for lo, hi in ((-3, 7), (3, 3), (-33, -30)):
+        with F.AcqEngine(table, F.default_params(dop_lo=lo, dop_hi=hi)) as eng:
+            rec, grid = eng.search(cap, sel=np.array([9, 10], np.int32), want_grid=True)
+        orec, ogrid = oracle.search(cap, table, sel=[9, 10], params=oracle.default_params(dop_lo=lo, dop_hi=hi), want_grid=True)
+        compare_records(rec[0], orec, ogrid, lo, 16.0, ggrid=grid[0], max_ties=1)
+
+
+def test_async_submit_poll_wait(nav_engine):
+    table = S.navstar()
+    cap = synth.make_capture(3, 1, table, scenarios.signals("cfg1", 3))
+    sync = nav_engine.search(cap)
+    out = np.zeros(32, F.RECORD_DTYPE)
+    nav_engine.submit(cap, out)
+    with pytest.raises(F.AcqError):  # a second call while one is pending is refused, not queued silently
+        nav_engine.search(cap)
+    while not nav_engine.poll():
+        pass
+    nav_engine.wait()
+    assert out.tobytes() == sync[0].tobytes()
+
+
+def test_device_resident_api_on_torch_stream(nav_engine):
+    import torch
+    table = S.navstar()
+    caps = np.concatenate([synth.make_capture(s, 1, table, scenarios.signals("cfg1", s)) for s in (1, 2, 3, 4)])
+    host = nav_engine.search(caps)
+    d_in = torch.from_numpy(caps).cuda()
+    d_out = torch.zeros(4 * 32 * 24, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        nav_engine.search_device(d_in.data_ptr(), d_out.data_ptr(), 4, stream_ptr=st.cuda_stream)
+    st.synchronize()
+    got = d_out.cpu().numpy().view(F.RECORD_DTYPE).reshape(4, 32)
+    assert got.tobytes() == host.tobytes()
+    n0 = nav_engine.launch_count
+    nav_engine.search_device(d_in.data_ptr(), d_out.data_ptr(), 4)
+    torch.cuda.synchronize()
+    assert nav_engine.launch_count - n0 == 5  # hb1, hb2, fwd FFT, search, best-Doppler
+
+
+def test_error_paths(nav_engine):
+    L = _lib.load()
+    cap = np.zeros(8192, np.uint8)
+    with pytest.raises(F.AcqError) as ei:
+        nav_engine.search(cap, sel=np.array([32], np.int32))
+    assert ei.value.code == -1
+    with pytest.raises(ValueError):
+        nav_engine.search(np.zeros(100, np.uint8))
+    out = np.zeros(32, F.RECORD_DTYPE)
+    assert L.acq_search(nav_engine._h, None, 1, None, 0, out.ctypes.data) == -1
+    assert L.acq_search(nav_engine._h, cap.ctypes.data, 0, None, 0, out.ctypes.data) == -1
+    with pytest.raises(F.AcqError) as ei:
+        F.AcqEngine(S.e1b([1, 2]), F.default_params(k_noncoh=4))
+    assert ei.value.code == -4  # ACQ_ERR_UNSUPPORTED, stated not silently degraded
+    with pytest.raises(F.AcqError):
+        F.AcqEngine(S.navstar(), F.default_params(dop_lo=5, dop_hi=-5))
+    with pytest.raises(F.AcqError):
+        F.AcqEngine([(1, 0, 6, 0)])
+    # the engine is still usable after errors
+    assert nav_engine.search(cap).shape == (1, 32)

@@ -1,0 +1,231 @@
+"""CPU suite (-m "not gpu"): the oracle against the reference's known answers, the golden vectors
+produced by the unmodified reference, and numpy; plus host logic."""
+import os
+
+import numpy as np
+import pytest
+
+from flydog_sdr_gps_b200 import sats as S, scenarios, synth
+
+# IS-GPS-200 "first 10 chips, octal" column for PRN 1..32 (the reference's own
+# L1_PRN_TEST / QZSS_PRN_TEST printers, gps/search.cpp:208-237, print exactly these quantities).
+FIRST10_OCTAL = [0o1440, 0o1620, 0o1710, 0o1744, 0o1133, 0o1455, 0o1131, 0o1454, 0o1626, 0o1504, 0o1642, 0o1750,
+                 0o1764, 0o1772, 0o1775, 0o1776, 0o1156, 0o1467, 0o1633, 0o1715, 0o1746, 0o1763, 0o1063, 0o1706,
+                 0o1743, 0o1761, 0o1770, 0o1774, 0o1127, 0o1453, 0o1625, 0o1712]
+QZSS_FIRST10 = {194: 0o0170, 195: 0o0030, 196: 0o0472, 199: 0o1050}
+
+
+def first_bits(chips, n):
+    v = 0
+    for i in range(n):
+        v = (v << 1) | int(chips[i])
+    return v
+
+
+def test_ca_code_known_answers(oracle):
+    for (prn, t1, t2, _), want in zip(S.navstar(), FIRST10_OCTAL):
+        assert first_bits(oracle.ca_chips(t1, t2), 10) == want, prn
+    # gps/search.cpp:209-219 prints the first 16 chips of PRN 9
+    assert first_bits(oracle.ca_chips(3, 10), 16) == 0xE5A9
+    for prn, d, init, _ in S.qzss():
+        chips = oracle.ca_chips(d, init)
+        assert first_bits(chips, 10) == QZSS_FIRST10[prn]
+        assert first_bits(chips, 10) == (0o1777 ^ init)  # G1 starts all ones
+
+
+def test_ca_code_properties(oracle):
+    for prn, t1, t2, _ in S.navstar():
+        c = oracle.ca_chips(t1, t2).astype(np.int32)
+        assert c.sum() in (511, 512)  # balanced Gold code
+        b = 1 - 2 * c
+        ac = np.array([np.dot(b, np.roll(b, k)) for k in (1, 2, 3, 100, 511)])
+        assert set(ac.tolist()) <= {-1, 63, -65}  # three-valued autocorrelation
+
+
+def test_e1b_known_answers(oracle):
+    # expected values are printed by the reference's E1BCODE_TEST (gps/search.cpp:295,302)
+    assert first_bits(oracle.e1b_chips(1), 20) == 0xF5D71
+    assert first_bits(oracle.e1b_chips(2), 20) == 0x96B85
+    for prn in (1, 11, 36, 50):
+        assert np.array_equal(oracle.e1b_chips(prn), synth.e1b_chips(prn))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/gps/e1bcode.h"), reason="reference tree not present")
+def test_e1b_table_matches_reference_strings(oracle):
+    import re
+    strings = re.findall(r'"([0-9A-F]{1023})"', open("/root/reference/gps/e1bcode.h").read())
+    assert len(strings) == 50
+    for prn in range(1, 51):
+        chips = oracle.e1b_chips(prn)
+        bits = "".join(format(int(ch, 16), "04b") for ch in strings[prn - 1])
+        assert "".join(map(str, chips)) == bits
+
+
+def test_host_and_oracle_code_generators_agree(oracle):
+    for prn, t1, t2, _ in S.navstar() + S.qzss():
+        assert np.array_equal(synth.ca_chips(t1, t2), oracle.ca_chips(t1, t2))
+
+
+def test_oracle_fft_against_numpy(oracle):
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(16384) + 1j * rng.standard_normal(16384)).astype(np.complex64)
+    f = oracle.fft16384(x, -1)
+    g = np.fft.fft(x.astype(np.complex128))
+    assert np.abs(f - g).max() / np.abs(g).max() < 1e-6
+    b = oracle.fft16384(x, +1)
+    h = np.fft.ifft(x.astype(np.complex128)) * 16384  # unnormalised like FFTW_BACKWARD
+    assert np.abs(b - h).max() / np.abs(h).max() < 1e-6
+    # impulse at k -> pure complex exponential, exact to rounding
+    imp = np.zeros(16384, np.complex64)
+    imp[5] = 1
+    e = oracle.fft16384(imp, +1)
+    assert np.abs(e - np.exp(2j * np.pi * 5 * np.arange(16384) / 16384)).max() < 1e-6
+    # round trip
+    rt = oracle.fft16384(oracle.fft16384(x, -1), +1) / 16384
+    assert np.abs(rt - x).max() < 1e-5
+
+
+def test_half_band_matches_direct_convolution(oracle):
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    n = 4096
+    buf = np.zeros(2 * (n + 31), np.float32)
+    buf[:2 * n] = rng.standard_normal(2 * n).astype(np.float32)
+    x = buf[:2 * n].copy().view(np.complex64).astype(np.complex128)
+    oracle.lib().orc_hb_decimate(n, buf.ctypes.data_as(C.POINTER(C.c_float)))
+    y = buf[:n].view(np.complex64)
+    taps = np.zeros(31)
+    even = [-0.010233, 0.010668, -0.016324, 0.024377, -0.036482, 0.056990, -0.101993, 0.316926,
+            0.316926, -0.101993, 0.056990, -0.036482, 0.024377, -0.016324, 0.010668, -0.010233]
+    taps[0::2] = even
+    taps[15] = 0.500009
+    xp = np.concatenate([x, np.zeros(31)])
+    want = np.array([np.dot(taps, xp[2 * o:2 * o + 31]) for o in range(n // 2)])
+    assert np.abs(y - want).max() < 1e-5
+
+
+def test_golden_search_vectors(oracle, golden_search):
+    """The oracle reproduces the unmodified reference (Sample + Correlate) on every golden capture:
+    Doppler bin and lag bit-exact, snr to float rounding (same FFT, same operation order)."""
+    table = S.reference_table()
+    for i, cap in enumerate(golden_search["captures"]):
+        rec = oracle.search(cap, table)
+        assert np.array_equal(rec["dop"], golden_search["dop"][i])
+        assert np.array_equal(rec["lag"], golden_search["lag"][i])
+        np.testing.assert_allclose(rec["snr"], golden_search["snr"][i], rtol=2e-6)
+        np.testing.assert_allclose(rec["peak"] / rec["noise"], rec["snr"], rtol=1e-6)
+
+
+def test_golden_injected_signals_are_found(golden_search):
+    """Sanity of the fixtures themselves: strong injected signals come back at lag = tau/4 and the nearest bin."""
+    table = S.reference_table()
+    for i in range(len(golden_search["captures"])):
+        for sat, tau, dop_hz, cn0, _ in golden_search["signals"][i]:
+            if np.isnan(sat):
+                continue
+            sat = int(sat)
+            L = 16368 if table[sat][3] == S.E1B else 4092
+            if cn0 >= 47:
+                assert golden_search["snr"][i, sat] >= 16
+            if golden_search["snr"][i, sat] < 20:
+                continue
+            d = (golden_search["lag"][i, sat] - tau / 4.0) % L  # tau is in FS samples, lag in /4 samples
+            # E1B: the capture holds one 4 ms period + 64 samples, so for tau beyond half a period the
+            # circular correlation peaks on the alignment of the wrapped part, 16 lags later
+            assert min(d, L - d) <= 1.0 or (L == 16368 and abs(d - 16) <= 1.0)
+            assert golden_search["dop"][i, sat] == int(np.round(dop_hz / 249.755859375))
+
+
+def test_golden_stage_vectors(oracle, golden_search, golden_stages):
+    cap = golden_search["captures"][0]
+    assert np.array_equal(oracle.capture_baseband(cap), golden_stages["x2"])       # bit-exact before the FFT
+    np.testing.assert_allclose(oracle.capture_spectrum(cap), golden_stages["D"], rtol=0, atol=1e-3)
+    table = S.reference_table()
+    assert np.array_equal(oracle.code_baseband(table[8]), golden_stages["code_x2_sat8"])
+    assert np.array_equal(oracle.code_baseband(table[40]), golden_stages["code_x2_sat40"])
+    for k in (0, 8, 33, 40, 58):
+        assert abs(np.abs(oracle.code_spectrum(table[k])).astype(np.float64).sum() / golden_stages["code_abs_sum"][k] - 1) < 1e-6
+        assert oracle.code_baseband(table[k]).real.astype(np.float64).sum() == pytest.approx(
+            golden_stages["code_x2_sum"][k], rel=1e-9, abs=1e-6)
+
+
+def test_oracle_against_live_reference(oracle):
+    """Where oracle/_ref exists (development container, or shipped prebuilt), run the unmodified
+    reference side by side on a fresh capture, including the negative-Doppler row overrun."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    table = S.reference_table()
+    assert table == oracle.ref_sats()
+    cap = synth.make_capture(99, 1, table, [(3, 777, -4000.0, 47, 0.1), (40, 40000, 2000.0, 47, 0.2), (33, 9, -250.0, 46, 0.3)])
+    x2, D = oracle.ref_sample(cap)
+    assert np.array_equal(oracle.capture_baseband(cap), x2)
+    assert np.array_equal(oracle.capture_spectrum(cap), D)
+    sel = np.array([0, 3, 31, 32, 33, 35, 36, 40, 58], np.int32)
+    dop, lag, snr = oracle.ref_search(cap, sel)
+    rec = oracle.search(cap, table, sel=sel)
+    assert np.array_equal(rec["dop"], dop) and np.array_equal(rec["lag"], lag) and np.array_equal(rec["snr"], snr)
+    # the intended circular wrap differs measurably for negative Doppler: the quirk matters
+    circ = oracle.search(cap, table, sel=sel, params=oracle.default_params(wrap_mode=oracle.WRAP_CIRCULAR))
+    assert circ["snr"][1] != rec["snr"][1]
+    for k in (0, 20, 35, 36, 58):
+        assert np.array_equal(oracle.code_spectrum(table[k]), oracle.ref_code_spectrum(k))
+
+
+def test_extensions_reduce_to_reference(oracle, golden_search):
+    """Half-bin indexing and K=1 'multi-block' must give the reference answers on the even half-bins."""
+    table = S.navstar()
+    cap = golden_search["captures"][1]
+    base, bgrid = oracle.search(cap, table, want_grid=True)
+    hb, hgrid = oracle.search(cap, table, params=oracle.default_params(dop_lo=-40, dop_hi=40, half_bin=1), want_grid=True)
+    assert np.array_equal(hgrid["lag"][:, 0::2], bgrid["lag"])
+    assert np.array_equal(hgrid["snr"][:, 0::2], bgrid["snr"])
+    # a half-bin Doppler is recovered on the odd index
+    f = 7.5 * 249.755859375
+    cap2 = synth.make_capture(5, 1, table, [(4, 4000, f, 46, 0.3)])
+    r = oracle.search(cap2, table, sel=[4], params=oracle.default_params(dop_lo=-40, dop_hi=40, half_bin=1))
+    assert r["dop"][0] == 15 and r["lag"][0] == 1000
+
+
+def test_noncoherent_accumulation_gain(oracle):
+    """K blocks with the 16-lag-per-block code advance removed: a 33 dB-Hz signal invisible at K=1 is found at K=20."""
+    table = S.navstar()
+    cap = synth.make_capture(11, 20, table, [(7, 8000, 1000.0, 34, 0.5)])
+    one = oracle.search(cap[:8192], table, sel=[7])
+    many, grid = oracle.search(cap, table, sel=[7], params=oracle.default_params(k_noncoh=20), want_grid=True)
+    assert many["lag"][0] == 2000 and many["dop"][0] == 4
+    assert not (one["lag"][0] == 2000 and one["dop"][0] == 4 and one["snr"][0] >= 16)
+    assert many["snr"][0] > 1.5 * np.median(grid["snr"])
+
+
+def test_workload_sizes():
+    """SURVEY.md 8(d) / BASELINE.md cell and tile counts."""
+    def cells(cfg):
+        t = scenarios.table(cfg)
+        kw = scenarios.params_kw(cfg)
+        n_dop = kw.get("dop_hi", 20) - kw.get("dop_lo", -20) + 1
+        c = sum(n_dop * (16368 if r[3] == S.E1B else 4092) for r in t) * scenarios.n_captures(cfg)
+        tiles = len(t) * n_dop * kw.get("k_noncoh", 1) * scenarios.n_captures(cfg)
+        return c, tiles
+    assert cells("cfg1") == (5368704, 1312)
+    assert cells("cfg2") == (21081984, 103040)
+    assert cells("cfg3") == (66290400, 4050)
+    assert cells("cfg4") == (38923104, 3362)
+    assert cells("cfg5") == (5497552896, 1343488)
+
+
+def test_shard_partition():
+    for n in (1, 7, 82, 1024):
+        for w in (1, 2, 3, 4, 8):
+            parts = [scenarios.shard(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synth_capture_format():
+    table = S.navstar()
+    cap = synth.make_capture(1, 2, table, scenarios.signals("cfg1", 1))
+    assert cap.dtype == np.uint8 and cap.size == 2 * 8192
+    assert 0.48 < np.unpackbits(cap).mean() < 0.52
+    assert np.array_equal(cap, synth.make_capture(1, 2, table, scenarios.signals("cfg1", 1)))

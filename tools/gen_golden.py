@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz: synthetic captures plus the answers of the UNMODIFIED reference
+(gps/search.cpp compiled behind stubs, oracle/_ref) for every row of the reference's Sats[] table.
+
+Runs only in the development container (needs /root/reference to build oracle/_ref).  The
+fixtures travel with the repository; the GPU box checks the oracle and the CUDA engine against
+them without the reference tree.
+
+Fixture content (per file):
+  captures  uint8 [n, 8192]   packed 1-bit blocks (the bytes Sample() reads over SPI)
+  signals   float64 [n, m, 5] injected (sat, tau, doppler_hz, cn0, phase), NaN padded
+  dop, lag  int32  [n, 59]    Correlate()'s *max_snr_dop, *max_snr_i   (gps/search.cpp:495)
+  snr       float32 [n, 59]   Correlate()'s return value               (gps/search.cpp:498)
+The FFT under the reference here is the oracle FFT (FFTW is not installable): see DESIGN.md.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from flydog_sdr_gps_b200 import sats as S, synth  # noqa: E402
+from flydog_sdr_gps_b200.engine import BIN_HZ  # noqa: E402
+from oracle import oracle_py as O  # noqa: E402
+
+
+def main():
+    O.build(ref=True)
+    assert O.have_ref(), "oracle/_ref could not be built"
+    table = S.reference_table()
+    assert table == O.ref_sats()
+    rng = np.random.default_rng(20261017)
+    caps, sigs = [], []
+    # three GPS-heavy captures (mix of Navstar, one QZSS, one E1B each), one noise only, one E1B-heavy
+    for n in range(5):
+        sig = []
+        if n < 3:
+            for k, sat in enumerate(rng.choice(32, 7, replace=False)):
+                f = float(rng.integers(-19, 20)) * BIN_HZ + (0.0 if k % 2 == 0 else float(rng.uniform(-60, 60)))
+                sig.append((int(sat), int(rng.integers(0, 16368)), f, float(50 - 1.5 * k), float(rng.uniform(0, 6.28))))
+            sig.append((32 + n, int(rng.integers(0, 16368)), float(rng.integers(-19, 20)) * BIN_HZ, 46.0, 1.0))
+            sig.append((36 + 3 * n, int(rng.integers(0, 65472)), float(rng.integers(-19, 20)) * BIN_HZ, 46.0, 2.0))
+        elif n == 4:
+            for sat in 36 + rng.choice(23, 5, replace=False):
+                sig.append((int(sat), int(rng.integers(0, 65472)), float(rng.integers(-19, 20)) * BIN_HZ,
+                            float(rng.uniform(44, 49)), float(rng.uniform(0, 6.28))))
+        caps.append(synth.make_capture(7000 + n, 1, table, sig))
+        sigs.append(sig)
+    m = max(len(s) for s in sigs)
+    sig_arr = np.full((len(caps), m, 5), np.nan)
+    for i, s in enumerate(sigs):
+        for j, row in enumerate(s):
+            sig_arr[i, j] = row
+    sel = np.arange(len(table), dtype=np.int32)
+    dop = np.zeros((len(caps), len(table)), np.int32)
+    lag = np.zeros_like(dop)
+    snr = np.zeros(dop.shape, np.float32)
+    for i, c in enumerate(caps):
+        dop[i], lag[i], snr[i] = O.ref_search(c, sel)
+        det = [(S.label(table[k]), int(dop[i, k]), int(lag[i, k]), round(float(snr[i, k]), 1)) for k in sel if snr[i, k] >= 16]
+        print("capture", i, "detected", det)
+    out = os.path.join(ROOT, "tests", "golden", "ref_search_59sats.npz")
+    np.savez_compressed(out, captures=np.stack(caps), signals=sig_arr, dop=dop, lag=lag, snr=snr)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+    # stage fixtures: forward-FFT input (x2) and spectrum checksum for capture 0, code replica checksums
+    x2, D = O.ref_sample(caps[0])
+    code_sum = np.array([np.abs(O.ref_code_spectrum(k)).astype(np.float64).sum() for k in sel])
+    code_x2_sum = np.array([O.ref_code_baseband(k).real.astype(np.float64).sum() for k in sel])
+    out2 = os.path.join(ROOT, "tests", "golden", "ref_stages.npz")
+    np.savez_compressed(out2, x2=x2, D=D, code_abs_sum=code_sum, code_x2_sum=code_x2_sum,
+                        code_x2_sat8=O.ref_code_baseband(8), code_x2_sat40=O.ref_code_baseband(40))
+    print("wrote", out2, os.path.getsize(out2), "bytes")
+
+
+if __name__ == "__main__":
+    main()
