@@ -240,7 +240,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     if (prof) CU(cudaEventRecord(e->prof[0], st));
     e->launches += launch_hb1_bits(packed_dev, e->d_x1, blocks, st);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
-    e->launches += launch_hb2(e->d_x1, e->d_x2, e->d_rot, blocks, e->nvar, st);
+    e->launches += launch_hb2(e->d_x1, e->d_x2, e->d_rot, blocks, e->nvar, K, st);
     if (prof) CU(cudaEventRecord(e->prof[2], st));
     e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar, true, e->sm_count, st);
     if (prof) CU(cudaEventRecord(e->prof[3], st));
@@ -477,7 +477,7 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
         if ((ce = cudaMemcpy(d_clb, codelen_boc.data(), codelen_boc.size() * sizeof(int), cudaMemcpyHostToDevice)))
             break;
         e->launches += launch_hb1_code(d_chips, d_clb, d_x1, n_sats, e->stream);
-        e->launches += launch_hb2(d_x1, d_x2, nullptr, n_sats, 1, e->stream);
+        e->launches += launch_hb2(d_x1, d_x2, nullptr, n_sats, 1, 1, e->stream);
         e->launches += launch_fwd_fft(d_x2, e->d_C, e->d_tables, n_sats, false, e->sm_count, e->stream);
         e->launches += launch_build_ext(e->d_C, e->d_Ep, n_sats, e->Q, e->ext_len, prm.wrap_mode, e->stream);
         if ((ce = cudaGetLastError())) break;
@@ -595,7 +595,7 @@ int acq_get_capture_spectrum(acq_engine *e, const uint8_t *packed, int half_rot,
             rotp = d_rot;
         }
         e->launches += launch_hb1_bits(d_pk, d_x1, 1, e->stream);
-        e->launches += launch_hb2(d_x1, d_x2, rotp, 1, half_rot ? 2 : 1, e->stream);
+        e->launches += launch_hb2(d_x1, d_x2, rotp, 1, half_rot ? 2 : 1, 1, e->stream);
         const float2 *sel_x2 = d_x2 + (half_rot ? kN : 0);
         e->launches += launch_fwd_fft(sel_x2, d_D, e->d_tables, 1, false, e->sm_count, e->stream);
         if ((ce = cudaGetLastError())) break;

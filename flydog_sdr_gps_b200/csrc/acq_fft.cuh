@@ -143,18 +143,32 @@ __device__ __forceinline__ void fft_load_tables(const FftSmem &s, const float2 *
 __device__ __forceinline__ void subfft4096_inv(float2 (&x)[16], const int k2, const FftSmem &s, const int t)
 {
     // ---- stage A: DFT over a, twiddle W4096^{t*n0} * W16384^{k2*n0}, scatter by n0
+    // Twiddles are fetched in two batches of registers AHEAD of the stores that use them: the compiler
+    // cannot hoist a shared-memory load above a shared-memory store (possible aliasing), and a
+    // load -> multiply -> store chain per element would expose the LDS latency 15 times per stage.
+    float2 tw[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) tw[i] = s.T1[i * 256 + t];  // n0 = 1..8
     radix16_inv(x);
-    s.S1[t] = x[r16(0)];
-    if (k2 == 0) {
+    if (k2 != 0) {
 #pragma unroll
-        for (int n0 = 1; n0 < 16; n0++) s.S1[n0 * 256 + t] = cmul(x[r16(n0)], s.T1[(n0 - 1) * 256 + t]);
-    } else {
-#pragma unroll
-        for (int n0 = 1; n0 < 16; n0++) {
-            const float2 w = cmul(s.T1[(n0 - 1) * 256 + t], c_cA[k2][n0]);
-            s.S1[n0 * 256 + t] = cmul(x[r16(n0)], w);
-        }
+        for (int i = 0; i < 8; i++) tw[i] = cmul(tw[i], c_cA[k2][i + 1]);
     }
+    s.S1[t] = x[r16(0)];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s.S1[(i + 1) * 256 + t] = cmul(x[r16(i + 1)], tw[i]);
+#pragma unroll
+    for (int i = 0; i < 7; i++) tw[i] = s.T1[(i + 8) * 256 + t];  // n0 = 9..15
+    if (k2 != 0) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) tw[i] = cmul(tw[i], c_cA[k2][i + 9]);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) s.S1[(i + 9) * 256 + t] = cmul(x[r16(i + 9)], tw[i]);
+    // stage-B twiddles W1024^{(4c+k2)*n1} do not depend on the exchange: first batch before the barrier
+    const float2 *twp = s.T2 + k2 * (15 * 16) + (t & 15);
+#pragma unroll
+    for (int i = 0; i < 8; i++) tw[i] = twp[i * 16];  // n1 = 1..8
     __syncthreads();
     // ---- stage B: thread (n0, c) = (t >> 4, t & 15) gathers b = 0..15
     {
@@ -165,10 +179,13 @@ __device__ __forceinline__ void subfft4096_inv(float2 (&x)[16], const int k2, co
     radix16_inv(x);
     {
         float2 *dst = s.S2 + 17 * (t >> 4) + (t & 15);
-        const float2 *tw = s.T2 + k2 * (15 * 16) + (t & 15);
         dst[0] = x[r16(0)];
 #pragma unroll
-        for (int n1 = 1; n1 < 16; n1++) dst[n1 * kS2Stride] = cmul(x[r16(n1)], tw[(n1 - 1) * 16]);
+        for (int i = 0; i < 8; i++) dst[(i + 1) * kS2Stride] = cmul(x[r16(i + 1)], tw[i]);
+#pragma unroll
+        for (int i = 0; i < 7; i++) tw[i] = twp[(i + 8) * 16];  // n1 = 9..15
+#pragma unroll
+        for (int i = 0; i < 7; i++) dst[(i + 9) * kS2Stride] = cmul(x[r16(i + 9)], tw[i]);
     }
     __syncthreads();
     // ---- stage C: thread t = n0 + 16*n1 gathers c = 0..15

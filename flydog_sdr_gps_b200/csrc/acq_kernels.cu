@@ -118,8 +118,12 @@ __global__ void __launch_bounds__(256) k_hb1_code(const uint32_t *__restrict__ c
 // K1b.  Second half-band stage, 32768 -> 16384 per row.  With nvar == 2 also writes the half-bin
 // variant x2[n] * exp(-j*pi*n/N) (rot[] is computed on the host in double precision).
 // x2 layout: [row][v][16384].
+// Non-coherent mode (K > 1): block b = row % K of a capture is stored circularly delayed by 16*b samples,
+// x2'[(n + 16 b) mod N] = x2[n], which makes its correlation r'_b[n] = r_b[(n + 16 b) mod N]: the
+// 16-lag-per-block code advance (65536 = 4 x 16368 + 64 samples) is removed before the FFT, so the
+// search kernel can add block powers lag by lag in registers.
 __global__ void __launch_bounds__(256) k_hb2(const float2 *__restrict__ x1, float2 *__restrict__ x2,
-                                             const float2 *__restrict__ rot, int nvar)
+                                             const float2 *__restrict__ rot, int nvar, int K, int row0)
 {
     const int o = blockIdx.x * 256 + threadIdx.x;
     const float2 *in = x1 + (size_t)blockIdx.y * 32768;
@@ -139,10 +143,11 @@ __global__ void __launch_bounds__(256) k_hb2(const float2 *__restrict__ x1, floa
     v = sample(15);
     acc.add(v.x, v.y, c_hb[16]);
     float2 *out = x2 + (size_t)blockIdx.y * nvar * kN;
-    out[o] = make_float2(acc.re, acc.im);
+    const int oo = (o + 16 * (int)((row0 + blockIdx.y) % K)) & (kN - 1);
+    out[oo] = make_float2(acc.re, acc.im);
     if (nvar == 2) {
         const float2 w = rot[o];
-        out[kN + o] = make_float2(__fsub_rn(__fmul_rn(acc.re, w.x), __fmul_rn(acc.im, w.y)),
+        out[kN + oo] = make_float2(__fsub_rn(__fmul_rn(acc.re, w.x), __fmul_rn(acc.im, w.y)),
                                   __fadd_rn(__fmul_rn(acc.re, w.y), __fmul_rn(acc.im, w.x)));
     }
 }
@@ -230,8 +235,8 @@ __global__ void __launch_bounds__(256) k_build_ext(const float2 *__restrict__ C,
 // K3-5.  The search kernel.  Persistent CTAs stride over tiles.
 //   M = 1: Navstar / QZSS, lags 0..4091 (only m = 0 of the radix-4 combine is formed)
 //   M = 4: Galileo E1B,    lags 0..16367
-//   MULTI: k_noncoh > 1 (M = 1 only): power summed over blocks with the 16-lag-per-block code
-//          advance removed, P[n] += |r_b[(n + 16 b) mod L]|^2.
+//   MULTI: k_noncoh > 1 (M = 1 only): power summed over blocks, P[n] += |r_b[(n + 16 b) mod N]|^2; the
+//          16-lag-per-block code advance is removed in the front end by delaying block b (see k_hb2).
 // ---------------------------------------------------------------------------------------------
 struct Peak {
     float p;
@@ -349,21 +354,12 @@ __global__ void __launch_bounds__(256, (M == 1) ? 2 : 1) k_search(const SearchAr
                     }
                 }
             } else if (M == 1 && MULTI) {
-                float *Sp = reinterpret_cast<float *>(s.S1);  // free: every S1 read precedes the last barrier
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++)
-                    Sp[t + 256 * n2] = acc[n2].x * acc[n2].x + acc[n2].y * acc[n2].y;
-                __syncthreads();
+                // block b was delayed by 16*b samples in the front end (k_hb2), so lag n lines up across blocks
 #pragma unroll
                 for (int n2 = 0; n2 < 16; n2++) {
-                    const int n = t + 256 * n2;
-                    if (n < L) {
-                        const int mm = (n + 16 * b) % L;
-                        const float pw = Sp[mm];
-                        P[n2] = (b == 0) ? pw : P[n2] + pw;
-                    }
+                    const float pw = acc[n2].x * acc[n2].x + acc[n2].y * acc[n2].y;
+                    P[n2] = (b == 0) ? pw : P[n2] + pw;
                 }
-                __syncthreads();  // Sp is overwritten by stage A of the next block
             } else {
                 // E1B: radix-4 combine over k2, lags n = t + 256*n2 + 4096*m < 16368
                 // (lags are not visited in increasing order here, so ties compare the index explicitly)
@@ -410,34 +406,47 @@ __global__ void __launch_bounds__(256, (M == 1) ? 2 : 1) k_search(const SearchAr
 }
 
 // K5b.  max_snr = 0; for dop ascending: if (snr > max_snr) take it   (search.cpp:455,495).
+// One warp per (capture, sat) row: lanes stride over the Doppler cells, then a shuffle reduction that
+// prefers the larger snr and, on equal snr, the lower Doppler index (what the sequential scan keeps).
 // A row whose snr never exceeds 0 (or is NaN) keeps {lag 0, dop 0, zeros}.
 __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ cells, const int *__restrict__ slot_sat,
                                                   acq_record *__restrict__ out, int n_rows, int n_slots, int n_dop,
                                                   int dop_lo)
 {
-    const int row = blockIdx.x * 128 + threadIdx.x;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
     const acq_cell *c = cells + (size_t)row * n_dop;
-    acq_record r;
-    r.sat = slot_sat[row % n_slots];
-    r.lag = 0;
-    r.dop = 0;
-    r.peak = 0.0f;
-    r.noise = 0.0f;
-    r.snr = 0.0f;
-    float max_snr = 0.0f;
-    for (int d = 0; d < n_dop; d++) {
-        const acq_cell cc = c[d];
-        if (cc.snr > max_snr) {
-            max_snr = cc.snr;
+    float best = 0.0f;
+    int best_d = 0x7fffffff;
+    for (int d = lane; d < n_dop; d += 32) {
+        const float snr = c[d].snr;
+        if (snr > best) best = snr, best_d = d;  // ascending d within a lane: first maximum kept
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, best, off);
+        const int d2 = __shfl_xor_sync(0xffffffffu, best_d, off);
+        if (s2 > best || (s2 == best && d2 < best_d)) best = s2, best_d = d2;
+    }
+    if (lane == 0) {
+        acq_record r;
+        r.sat = slot_sat[row % n_slots];
+        r.lag = 0;
+        r.dop = 0;
+        r.peak = 0.0f;
+        r.noise = 0.0f;
+        r.snr = 0.0f;
+        if (best > 0.0f) {
+            const acq_cell cc = c[best_d];
             r.lag = cc.lag;
-            r.dop = dop_lo + d;
+            r.dop = dop_lo + best_d;
             r.peak = cc.peak;
             r.noise = cc.noise;
             r.snr = cc.snr;
         }
+        out[row] = r;
     }
-    out[row] = r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,12 +484,12 @@ int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, i
     return 1;
 }
 
-int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, cudaStream_t st)
+int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st)
 {
     int launched = 0;
     for (int r0 = 0; r0 < n_rows; r0 += 32768) {
         const int nr = (n_rows - r0 < 32768) ? (n_rows - r0) : 32768;
-        k_hb2<<<dim3(64, nr), 256, 0, st>>>(x1 + (size_t)r0 * 32768, x2 + (size_t)r0 * nvar * kN, rot, nvar);
+        k_hb2<<<dim3(64, nr), 256, 0, st>>>(x1 + (size_t)r0 * 32768, x2 + (size_t)r0 * nvar * kN, rot, nvar, K, r0);
         launched++;
     }
     return launched;
@@ -517,7 +526,7 @@ int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out,
                     int dop_lo, cudaStream_t st)
 {
     const int n_rows = n_cap * n_slots;
-    k_best_dop<<<(n_rows + 127) / 128, 128, 0, st>>>(cells, slot_sat, out, n_rows, n_slots, n_dop, dop_lo);
+    k_best_dop<<<(n_rows + 3) / 4, 128, 0, st>>>(cells, slot_sat, out, n_rows, n_slots, n_dop, dop_lo);
     return 1;
 }
 

@@ -24,7 +24,7 @@ struct SearchArgs {
 int launch_tables_init(const float2 *h_cA, const float2 *h_cC, const float *h_hb);
 int launch_hb1_bits(const uint8_t *packed, float2 *x1, int n_blocks, cudaStream_t st);
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
-int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, cudaStream_t st);
+int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st);
 int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_rows, bool polyphase, int sm_count,
                    cudaStream_t st);
 int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len, int wrap_mode, cudaStream_t st);

@@ -271,9 +271,13 @@ static void correlate_one(const float *Dall, int nvar, int K, const float *C, co
                     tot_pwr += pwr;
                 }
             } else {
-                /* extension: block b starts 16 /4-samples later in code phase */
+                /* extension: block b starts 16 /4-samples later in code phase, so
+                 * lag n of block 0 is lag n + 16 b of block b.  The index wraps modulo the FFT length
+                 * (the transform's own circular lag axis), not modulo L: for the 1 ms codes lags
+                 * L..L+16b-1 are the same code phases one period later, and this form is a plain
+                 * circular time shift of the block (no scatter) -- see DESIGN.md "non-coherent sum". */
                 for (i = 0; i < L; i++) {
-                    const int m = (i + 16 * b) % L;
+                    const int m = (i + 16 * b) % N;
                     const float pwr = prod[2 * m] * prod[2 * m] + prod[2 * m + 1] * prod[2 * m + 1];
                     if (b == 0) P[i] = pwr; else P[i] += pwr;
                 }

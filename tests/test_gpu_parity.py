@@ -284,3 +284,65 @@ def test_error_paths(nav_engine):
         F.AcqEngine([(1, 0, 6, 0)])
     # the engine is still usable after errors
     assert nav_engine.search(cap).shape == (1, 32)
+
+
+def test_dropin_search_task_matches_literal_reference(gpu_required, golden_search):
+    """The host shim replays the reference's SearchTask loop (search.cpp:512-604) against a mock receiver:
+    same ChanReset / GPSstat / ChanStart calls, same order, same integer arguments as the unmodified
+    reference produced on these captures (tests/golden/ref_search_task_events.npz)."""
+    import os
+    from conftest import GOLDEN
+    from flydog_sdr_gps_b200 import dropin
+    want = np.load(os.path.join(GOLDEN, "ref_search_task_events.npz"))["events"]
+    rx = dropin.MockReceiver(golden_search["captures"], free_chans=12)
+    d = dropin.Dropin(S.reference_table(), rx)
+    started = d.search_pass(dropin.LITERAL) + d.search_pass(dropin.LITERAL)
+    got = rx.events
+    assert started == int((want["kind"] == 2).sum()) == 12
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        if w["kind"] == 1:
+            assert g == ("chan_reset", w["a"], w["b"], w["c"])
+        elif w["kind"] == 2:   # ChanStart(ch, sat, t_sample, lo_shift, ca_shift, (int) snr)
+            assert g[:5] == ("chan_start", w["a"], w["b"], w["c"], w["d"])
+            assert abs(g[5] - w["e"]) <= 1 and abs(g[5] - w["e"]) <= RTOL * w["e"] + 1
+        elif w["kind"] == 3:   # GPSstat(STAT_SAT, snr, ch, sat, weak)
+            assert g[0] == "stat_sat" and g[1:3] == (w["a"], w["b"])
+            if abs(w["x"] / 16.0 - 1) > RTOL:
+                assert g[3] == w["c"]
+            assert abs(g[4] - w["x"]) <= RTOL * max(w["x"], 1e-9)
+        elif w["kind"] == 4:   # GPSstat(STAT_DOP, ch, (int)(lo_shift*BIN_SIZE), ca_shift)
+            assert g == ("stat_dop", w["a"], w["b"], w["c"])
+    # SearchEnable re-arms a tracked satellite
+    busy = [s for s in range(59) if d.is_busy(s)]
+    assert len(busy) == 12
+    d.enable(busy[0])
+    assert not d.is_busy(busy[0])
+    d.close()
+
+
+def test_dropin_batch_mode_and_gsig(gpu_required, golden_search):
+    """Capture-reuse mode (one capture, all idle sats in one GPU call) starts the same satellites the
+    per-satellite search finds on that capture; -gsig raises the L1 threshold like SearchParams."""
+    from flydog_sdr_gps_b200 import dropin
+    cap = golden_search["captures"][0]
+    rx = dropin.MockReceiver(cap, free_chans=12)
+    d = dropin.Dropin(S.reference_table(), rx)
+    n = d.search_pass(dropin.BATCH)
+    started = sorted(e[2] for e in rx.events if e[0] == "chan_start")
+    want = sorted(np.nonzero(golden_search["snr"][0] >= 16 * (1 + RTOL))[0].tolist())
+    assert n == len(started) and set(want) <= set(started) and len(started) <= len(want) + 2
+    for e in rx.events:
+        if e[0] == "chan_start":
+            assert e[3] == golden_search["dop"][0][e[2]] and e[4] == 4 * golden_search["lag"][0][e[2]]
+    assert rx.samples == 1
+    d.close()
+    rx2 = dropin.MockReceiver(cap, free_chans=12)
+    d2 = dropin.Dropin(S.reference_table(), rx2)
+    d2.params("-gsig", "60")
+    d2.set_acq(1, 0, 0)
+    d2.search_pass(dropin.LITERAL)
+    started2 = sorted(e[2] for e in rx2.events if e[0] == "chan_start")
+    assert started2 == sorted(np.nonzero(golden_search["snr"][0][:32] >= 60)[0].tolist())
+    assert all(e[1] < 32 for e in rx2.events if e[0] == "chan_reset")
+    d2.close()

@@ -73,6 +73,15 @@ def main():
                         code_x2_sat8=O.ref_code_baseband(8), code_x2_sat40=O.ref_code_baseband(40))
     print("wrote", out2, os.path.getsize(out2), "bytes")
 
+    # literal SearchTask loop (gps/search.cpp:512-604): two passes over Sats[] with 12 free tracking
+    # channels; Sample() call k reads capture k % 5.  Event kinds: 1 ChanReset(sat, codegen_init) -> ch,
+    # 2 ChanStart(ch, sat, lo_shift, ca_shift, snr), 3 GPSstat(STAT_SAT, snr, ch, sat, weak), 4 GPSstat(STAT_DOP, ch, hz, ca_shift)
+    ev = O.ref_search_task(np.stack(caps), passes=2, free_chans=12, min_sig=16)
+    ev = ev[ev["kind"] != 5]
+    out3 = os.path.join(ROOT, "tests", "golden", "ref_search_task_events.npz")
+    np.savez_compressed(out3, events=ev)
+    print("wrote", out3, len(ev), "events;", int((ev["kind"] == 2).sum()), "ChanStart calls")
+
 
 if __name__ == "__main__":
     main()
