@@ -42,8 +42,20 @@ __constant__ float2 c_cC[4][16];
 // ---------------------------------------------------------------------------------------------
 // complex helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex add/sub as ONE packed f32x2 instruction (sm_100 FADD2 / FFMA2): the FMA pipe does the same work
+// as two scalar adds, but the instruction occupies a single issue slot, which is what the add-dominated
+// butterflies are short of.  (SASS: FADD2, FFMA2 with a broadcast -1 immediate.)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+// a + j*b and a - j*b: j*b = (-b.y, b.x) is a lane swap (free operand modifier) times the sign pair (-1,+1)
+__device__ __forceinline__ float2 cadd_jb(float2 a, float2 b)
+{
+    return __ffma2_rn(make_float2(b.y, b.x), make_float2(-1.0f, 1.0f), a);
+}
+__device__ __forceinline__ float2 csub_jb(float2 a, float2 b)
+{
+    return __ffma2_rn(make_float2(b.y, b.x), make_float2(1.0f, -1.0f), a);
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 w)
 {
     return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
@@ -60,11 +72,11 @@ __device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.
 __device__ __forceinline__ void radix4_inv(float2 &a, float2 &b, float2 &c, float2 &d)
 {
     const float2 apc = cadd(a, c), amc = csub(a, c);
-    const float2 bpd = cadd(b, d), jbmd = mul_pj(csub(b, d));
+    const float2 bpd = cadd(b, d), bmd = csub(b, d);
     a = cadd(apc, bpd);
-    b = cadd(amc, jbmd);
+    b = cadd_jb(amc, bmd);
     c = csub(apc, bpd);
-    d = csub(amc, jbmd);
+    d = csub_jb(amc, bmd);
 }
 
 // Inverse 16-point DFT in registers: X[n] = sum_a x[a] e^{+2*pi*j*a*n/16}.

@@ -12,6 +12,7 @@
 // The half-band stages use explicit round-to-nearest mul/add in the reference's summation order
 // (no FMA contraction), so the FFT inputs are bit-identical to the reference's x86 build.
 #include "acq_fft.cuh"
+#include "acq_search2.cuh"
 #include "acq_kernels.cuh"
 
 namespace acq {
@@ -405,6 +406,149 @@ __global__ void __launch_bounds__(256, (M == 1) ? 2 : 1) k_search(const SearchAr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3-5, packed variant for the 1 ms lag window (Navstar / QZSS): two Doppler indices per thread in the two
+// lanes of f32x2 instructions (see acq_search2.cuh).  One persistent 256-thread CTA per SM strides over
+// (capture, satellite, Doppler pair).  Lane A = index d0, lane B = index d1 = d0 + 1 bin (d1 == d0 for the
+// unpaired last index, whose lane-B result is dropped).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_split_planar(const float2 *__restrict__ Ep, float *__restrict__ ERp,
+                                                      float *__restrict__ EIp, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) {
+        const float2 v = Ep[i];
+        ERp[i] = v.x;
+        EIp[i] = v.y;
+    }
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(256, 1) k_search2(const SearchArgs p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const FftSmem2 s = fft_smem2_carve(smem);
+    float *red_f = reinterpret_cast<float *>(smem + fft_smem2_bytes());
+    int *red_i = reinterpret_cast<int *>(red_f + 32);
+    const int t = threadIdx.x;
+    constexpr int L = ACQ_LAGS_L1;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
+        float4 *dst = reinterpret_cast<float4 *>(s.T1);
+        for (int i = t; i < (kT1Elems + kT2Elems) / 2; i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    const long long n_pairs = (long long)p.n_cap * p.n_work * p.ppr;
+    for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+        const int j = (int)(pr % p.ppr);
+        const long long cw = pr / p.ppr;
+        const int wi = (int)(cw % p.n_work);
+        const int cap = (int)(cw / p.n_work);
+        const int2 wk = p.work[wi];
+        const int sat = wk.x, slot = wk.y;
+        const int2 dd = p.pairs[j];
+        const int h0 = p.dop_lo + dd.x;
+        const int v = p.half_bin ? (h0 & 1) : 0;
+        const int dopA = p.half_bin ? ((h0 - v) >> 1) : h0;
+        const int dopB = (dd.y != dd.x) ? dopA + 1 : dopA;
+
+        CP acc[16];
+        float2 P[MULTI ? 16 : 1];
+        for (int b = 0; b < p.K; b++) {
+            const float2 *Dblk = p.Dp + ((size_t)((size_t)cap * p.K + b) * p.nvar + v) * kN + t;
+            CP x[16];
+            for (int k2 = 0; k2 < 4; k2++) {
+                const int rA = (k2 - dopA) & 3, qA = (k2 - dopA - rA) >> 2;
+                const int rB = (k2 - dopB) & 3, qB = (k2 - dopB - rB) >> 2;
+                const size_t oA = (size_t)(sat * 4 + rA) * p.ext_len + p.Q + qA + t;
+                const size_t oB = (size_t)(sat * 4 + rB) * p.ext_len + p.Q + qB + t;
+                const float2 *Dk = Dblk + k2 * kSub;
+                const float *erA = p.ERp + oA, *eiA = p.EIp + oA, *erB = p.ERp + oB, *eiB = p.EIp + oB;
+                // prod = conj(D) * E for both lanes; D enters as a broadcast scalar operand
+#pragma unroll
+                for (int a = 0; a < 16; a++) {
+                    const float2 dv = __ldg(Dk + 256 * a);
+                    const float2 ER = make_float2(__ldg(erA + 256 * a), __ldg(erB + 256 * a));
+                    const float2 EI = make_float2(__ldg(eiA + 256 * a), __ldg(eiB + 256 * a));
+                    x[a].re = p_fma(EI, p_bc(dv.y), p_mul(ER, p_bc(dv.x)));
+                    x[a].im = p_fma(ER, p_bc(-dv.y), p_mul(EI, p_bc(dv.x)));
+                }
+                subfft4096_inv2(x, k2, s, t);
+                if (k2 == 0) {
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
+                } else {
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) {
+                        const float2 w = c_cC[k2][n2];
+                        const CP z = x[r16(n2)];
+                        acc[n2].re = p_fma(z.im, p_bc(-w.y), p_fma(z.re, p_bc(w.x), acc[n2].re));
+                        acc[n2].im = p_fma(z.im, p_bc(w.x), p_fma(z.re, p_bc(w.y), acc[n2].im));
+                    }
+                }
+            }
+            if (MULTI) {
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) {
+                    const float2 pw = p_fma(acc[n2].im, acc[n2].im, p_mul(acc[n2].re, acc[n2].re));
+                    P[n2] = (b == 0) ? pw : p_add(P[n2], pw);
+                }
+            }
+        }
+
+        Peak bA, bB;
+        bA.p = bB.p = 0.0f;
+        bA.n = bB.n = 0x7fffffff;
+        float2 sum = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) {
+            const int n = t + 256 * n2;
+            float2 pw = MULTI ? P[n2] : p_fma(acc[n2].im, acc[n2].im, p_mul(acc[n2].re, acc[n2].re));
+            if (n2 == 15 && n >= L) pw = make_float2(0.0f, 0.0f);  // lags 4092..4095 are not scanned (search.cpp:486)
+            if (pw.x > bA.p) bA.p = pw.x, bA.n = n;
+            if (pw.y > bB.p) bB.p = pw.y, bB.n = n;
+            sum = p_add(sum, pw);
+        }
+        bA.sum = sum.x;
+        bB.sum = sum.y;
+        // block reduction of both lanes (shuffles, then one partial per warp)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            peak_merge(bA, __shfl_xor_sync(0xffffffffu, bA.p, off), __shfl_xor_sync(0xffffffffu, bA.n, off),
+                       __shfl_xor_sync(0xffffffffu, bA.sum, off));
+            peak_merge(bB, __shfl_xor_sync(0xffffffffu, bB.p, off), __shfl_xor_sync(0xffffffffu, bB.n, off),
+                       __shfl_xor_sync(0xffffffffu, bB.sum, off));
+        }
+        const int w = t >> 5;
+        if ((t & 31) == 0) {
+            red_f[w] = bA.p;
+            red_f[8 + w] = bA.sum;
+            red_f[16 + w] = bB.p;
+            red_f[24 + w] = bB.sum;
+            red_i[w] = bA.n;
+            red_i[8 + w] = bB.n;
+        }
+        __syncthreads();
+        if (t < 2 && (t == 0 || dd.y != dd.x)) {
+            Peak tot;
+            const int o = t * 16, oi = t * 8;
+            tot.p = red_f[o];
+            tot.n = red_i[oi];
+            tot.sum = red_f[o + 8];
+#pragma unroll
+            for (int k = 1; k < 8; k++) peak_merge(tot, red_f[o + k], red_i[oi + k], red_f[o + 8 + k]);
+            acq_cell c;
+            c.peak = tot.p;
+            c.noise = __fdiv_rn(tot.sum, (float)L);
+            c.snr = __fdiv_rn(tot.p, c.noise);
+            c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
+            p.cells[((size_t)cap * p.n_slots + slot) * p.n_dop + (t == 0 ? dd.x : dd.y)] = c;
+        }
+        // red_* are rewritten only after the >= 8 barriers of the next pair
+    }
+}
+
 // K5b.  max_snr = 0; for dop ascending: if (snr > max_snr) take it   (search.cpp:455,495).
 // One warp per (capture, sat) row: lanes stride over the Doppler cells, then a shuffle reduction that
 // prefers the larger snr and, on equal snr, the lower Doppler index (what the sequential scan keeps).
@@ -452,6 +596,7 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+static size_t search2_smem_bytes() { return fft_smem2_bytes() + 64 * sizeof(float); }
 size_t search_smem_bytes(bool e1b) { return fft_smem_bytes() + (e1b ? kZBytes : 0) + 64 * sizeof(float); }
 static size_t fwd_smem_bytes() { return fft_smem_bytes() + kZBytes; }
 
@@ -462,6 +607,9 @@ cudaError_t search_kernels_configure()
     if ((e = cudaFuncSetAttribute(k_search<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
+    const int s2 = (int)search2_smem_bytes();
+    if ((e = cudaFuncSetAttribute(k_search2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2))) return e;
+    if ((e = cudaFuncSetAttribute(k_search2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     return cudaSuccess;
@@ -519,6 +667,22 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st)
     if (e1b) k_search<4, false><<<grid, 256, smem, st>>>(a);
     else if (a.K > 1) k_search<1, true><<<grid, 256, smem, st>>>(a);
     else k_search<1, false><<<grid, 256, smem, st>>>(a);
+    return 1;
+}
+
+int launch_search2(const SearchArgs &a, int sm_count, cudaStream_t st)
+{
+    const long long n_pairs = (long long)a.n_cap * a.n_work * a.ppr;
+    if (n_pairs <= 0) return 0;
+    const int grid = (int)(n_pairs < sm_count ? n_pairs : sm_count);
+    if (a.K > 1) k_search2<true><<<grid, 256, search2_smem_bytes(), st>>>(a);
+    else k_search2<false><<<grid, 256, search2_smem_bytes(), st>>>(a);
+    return 1;
+}
+
+int launch_build_ext_planar(const float2 *Ep, float *ERp, float *EIp, size_t n, cudaStream_t st)
+{
+    k_split_planar<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Ep, ERp, EIp, n);
     return 1;
 }
 

@@ -18,6 +18,12 @@ struct SearchArgs {
     acq_cell *cells;       // [cap][n_slots][n_dop]
     long long n_tiles;
     int n_work, n_slots, n_dop, dop_lo, half_bin, K, nvar, ext_len, Q;
+    // two-bins-per-thread kernel (k_search2): planar extended code rows and the Doppler pairing
+    const float *ERp;      // [(sat*4 + r)][ext_len] real parts
+    const float *EIp;      // [(sat*4 + r)][ext_len] imaginary parts
+    const int2 *pairs;     // [ppr] (d0, d1): Doppler indices sharing a thread; d1 == d0 marks an unpaired index
+    int ppr;               // pairs per (capture, satellite) row
+    int n_cap;
 };
 
 // host-side launchers (all asynchronous on `st`; each returns the number of kernels it launched)
@@ -29,6 +35,8 @@ int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_ro
                    cudaStream_t st);
 int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len, int wrap_mode, cudaStream_t st);
 int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st);
+int launch_search2(const SearchArgs &a, int sm_count, cudaStream_t st);
+int launch_build_ext_planar(const float2 *Ep, float *ERp, float *EIp, size_t n, cudaStream_t st);
 int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
                     int dop_lo, cudaStream_t st);
 cudaError_t search_kernels_configure();
