@@ -100,10 +100,6 @@ struct acq_engine {
 
     // persistent device data
     float2 *d_tables = nullptr, *d_rot = nullptr, *d_C = nullptr, *d_Ep = nullptr;
-    float *d_ERp = nullptr, *d_EIp = nullptr;  // planar copy of d_Ep for the packed kernel
-    int2 *d_pairs = nullptr;                   // Doppler index pairs (d0, d1)
-    int ppr = 0;
-    bool use_packed = true;                    // ACQ_SEARCH_KERNEL=scalar selects the one-bin-per-thread kernel
     // per-call scratch (grown on demand)
     size_t cap_blocks = 0, cap_cells = 0, cap_rows = 0, cap_packed = 0;
     uint8_t *d_packed = nullptr;
@@ -132,9 +128,6 @@ int free_engine(acq_engine *e)
     cudaFree(e->d_rot);
     cudaFree(e->d_C);
     cudaFree(e->d_Ep);
-    cudaFree(e->d_ERp);
-    cudaFree(e->d_EIp);
-    cudaFree(e->d_pairs);
     cudaFree(e->d_packed);
     cudaFree(e->d_x1);
     cudaFree(e->d_x2);
@@ -264,17 +257,11 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     a.nvar = e->nvar;
     a.ext_len = e->ext_len;
     a.Q = e->Q;
-    a.ERp = e->d_ERp;
-    a.EIp = e->d_EIp;
-    a.pairs = e->d_pairs;
-    a.ppr = e->ppr;
-    a.n_cap = n_captures;
     if (e->n_l1 > 0) {
         a.work = e->d_work;
         a.n_work = e->n_l1;
         a.n_tiles = (long long)n_captures * e->n_l1 * e->n_dop;
-        if (e->use_packed) e->launches += launch_search2(a, e->sm_count, st);
-        else e->launches += launch_search(a, false, e->sm_count, st);
+        e->launches += launch_search(a, false, e->sm_count, st);
     }
     if (e->n_e1b > 0) {
         a.work = e->d_work + e->n_l1;
@@ -413,30 +400,28 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
         }                                                                                           \
     } while (0)
 
-    if (const char *kv = getenv("ACQ_SEARCH_KERNEL")) e->use_packed = (strcmp(kv, "scalar") != 0);
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUE(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
     CUE(search_kernels_configure());
 
     // ---- twiddle tables, constants (double precision on the host, rounded once)
     const double two_pi = 6.283185307179586476925286766559;
-    std::vector<float2> tables(kT1Elems + kT2Elems);
-    for (int n0 = 1; n0 < 16; n0++)
-        for (int t = 0; t < 256; t++) {
-            const double a = two_pi * (double)((t * n0) % 4096) / 4096.0;
-            tables[(n0 - 1) * 256 + t] = make_float2((float)cos(a), (float)sin(a));
-        }
+    std::vector<float2> tables(kT2Elems + kBaseElems);
     for (int k2 = 0; k2 < 4; k2++)
         for (int n1 = 1; n1 < 16; n1++)
             for (int c = 0; c < 16; c++) {
                 const double a = two_pi * (double)(((4 * c + k2) * n1) % 1024) / 1024.0;
-                tables[kT1Elems + (k2 * 15 + (n1 - 1)) * 16 + c] = make_float2((float)cos(a), (float)sin(a));
+                tables[(k2 * 15 + (n1 - 1)) * 16 + c] = make_float2((float)cos(a), (float)sin(a));
             }
-    float2 cA[64], cC[64];
+    for (int k2 = 0; k2 < 4; k2++)
+        for (int t = 0; t < 256; t++) {
+            const double a = two_pi * (double)(4 * t + k2) / 16384.0;
+            tables[kT2Elems + k2 * 256 + t] = make_float2((float)cos(a), (float)sin(a));
+        }
+    float2 cC[64];
     for (int k2 = 0; k2 < 4; k2++)
         for (int n = 0; n < 16; n++) {
-            const double a = two_pi * (double)(k2 * n) / 16384.0, c = two_pi * (double)(k2 * n) / 64.0;
-            cA[k2 * 16 + n] = make_float2((float)cos(a), (float)sin(a));
+            const double c = two_pi * (double)(k2 * n) / 64.0;
             cC[k2 * 16 + n] = make_float2((float)cos(c), (float)sin(c));
         }
     // Half-band taps of the reference (gps/search.cpp:101-136, column 0), narrowed double -> float the
@@ -447,7 +432,7 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     float hb[17];
     for (int i = 0; i < 16; i++) hb[i] = (float)taps_even[i];
     hb[16] = (float)0.500009;
-    launch_tables_init(cA, cC, hb);
+    launch_tables_init(cC, hb);
     CUE(cudaGetLastError());
     CUE(cudaMalloc(&e->d_tables, tables.size() * sizeof(float2)));
     CUE(cudaMemcpy(e->d_tables, tables.data(), tables.size() * sizeof(float2), cudaMemcpyHostToDevice));
@@ -494,31 +479,6 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
         e->launches += launch_hb2(d_x1, d_x2, nullptr, n_sats, 1, 1, e->stream);
         e->launches += launch_fwd_fft(d_x2, e->d_C, e->d_tables, n_sats, false, e->sm_count, e->stream);
         e->launches += launch_build_ext(e->d_C, e->d_Ep, n_sats, e->Q, e->ext_len, prm.wrap_mode, e->stream);
-        {
-            const size_t n_ext = (size_t)n_sats * 4 * e->ext_len;
-            if ((ce = cudaMalloc(&e->d_ERp, n_ext * sizeof(float)))) break;
-            if ((ce = cudaMalloc(&e->d_EIp, n_ext * sizeof(float)))) break;
-            e->launches += launch_build_ext_planar(e->d_Ep, e->d_ERp, e->d_EIp, n_ext, e->stream);
-            // Doppler pairing: indices that differ by exactly one bin share a thread.  With half-bin
-            // spacing one bin is two indices, so even and odd indices pair among themselves.
-            std::vector<int2> pairs;
-            const int stride = prm.half_bin ? 2 : 1;
-            std::vector<char> used(e->n_dop, 0);
-            for (int d = 0; d < e->n_dop; d++) {
-                if (used[d]) continue;
-                used[d] = 1;
-                const int d1 = d + stride;
-                if (d1 < e->n_dop && !used[d1]) {
-                    used[d1] = 1;
-                    pairs.push_back(make_int2(d, d1));
-                } else {
-                    pairs.push_back(make_int2(d, d));
-                }
-            }
-            e->ppr = (int)pairs.size();
-            if ((ce = cudaMalloc(&e->d_pairs, pairs.size() * sizeof(int2)))) break;
-            if ((ce = cudaMemcpy(e->d_pairs, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice))) break;
-        }
         if ((ce = cudaGetLastError())) break;
         ce = cudaStreamSynchronize(e->stream);
     } while (0);

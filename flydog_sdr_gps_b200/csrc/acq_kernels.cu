@@ -5,14 +5,13 @@
 //   K1b k_hb2        : second half-band /2 (+ optional half-bin pre-rotation)       (search.cpp:439-441)
 //   K2  k_fwd_fft    : 16384-point forward FFT of data or code                       (search.cpp:280,342,447)
 //   K6b k_build_ext  : polyphase, margin-extended code-spectrum rows                 (search.cpp:283-284,471)
-//   K3-5 k_search<M> : conj(D).C product, 16384-point inverse FFT, |.|^2, non-coherent
+//   K3-5 k_search_l1 / k_search_e1b : conj(D).C product, 16384-point inverse FFT, |.|^2, non-coherent
 //                      sum, max / first-argmax / mean per (capture, sat, Doppler)    (search.cpp:465-494)
 //   K5b k_best_dop   : best-snr Doppler per (capture, sat), lowest index on ties    (search.cpp:495)
 //
 // The half-band stages use explicit round-to-nearest mul/add in the reference's summation order
 // (no FMA contraction), so the FFT inputs are bit-identical to the reference's x86 build.
 #include "acq_fft.cuh"
-#include "acq_search2.cuh"
 #include "acq_kernels.cuh"
 
 namespace acq {
@@ -21,9 +20,8 @@ namespace acq {
 //   [0] = COEF[0], [1..15] = COEF[2], COEF[4] .. COEF[30], [16] = COEF[15]
 __constant__ float c_hb[17];
 
-int launch_tables_init(const float2 *h_cA, const float2 *h_cC, const float *h_hb)
+int launch_tables_init(const float2 *h_cC, const float *h_hb)
 {
-    cudaMemcpyToSymbol(c_cA, h_cA, sizeof(float2) * 64);
     cudaMemcpyToSymbol(c_cC, h_cC, sizeof(float2) * 64);
     cudaMemcpyToSymbol(c_hb, h_hb, sizeof(float) * 17);
     return 0;
@@ -161,26 +159,38 @@ __global__ void __launch_bounds__(256) k_hb2(const float2 *__restrict__ x1, floa
 // ---------------------------------------------------------------------------------------------
 constexpr size_t kZBytes = sizeof(float2) * 3 * 16 * 256;
 
+__device__ __forceinline__ void load_t2(const FftSmem3 &s, const float2 *__restrict__ tables, int t)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(tables);
+    float4 *dst = reinterpret_cast<float4 *>(s.T2);
+    for (int i = t; i < kT2Elems / 2; i += 256) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
 template <bool POLY>
 __global__ void __launch_bounds__(256, 1) k_fwd_fft(const float2 *__restrict__ x2, float2 *__restrict__ out,
                                                     const float2 *__restrict__ tables, int n_rows)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const FftSmem s = fft_smem_carve(smem);
-    float2 *Z = reinterpret_cast<float2 *>(smem + fft_smem_bytes());
+    const FftSmem3 s = fft_smem3_carve(smem);
+    float2 *Z = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());
     const int t = threadIdx.x;
-    fft_load_tables(s, tables, t, 256);
+    load_t2(s, tables, t);
+    const float2 *base = tables + kT2Elems + t;
+    int buf = 0;
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
         const float2 *in = x2 + (size_t)row * kN;
         float2 *o = out + (size_t)row * kN;
         float2 x[16];
+#pragma unroll 1
         for (int k2 = 0; k2 < 4; k2++) {
 #pragma unroll
             for (int a = 0; a < 16; a++) {
                 const float2 v = in[1024 * a + 4 * t + k2];
                 x[a] = make_float2(v.x, -v.y);
             }
-            subfft4096_inv(x, k2, s, t);
+            subfft4096_inv3(x, k2, __ldg(base + k2 * 256), buf, s, t);
+            buf ^= 1;
             if (k2 < 3) {
 #pragma unroll
                 for (int n2 = 0; n2 < 16; n2++) {
@@ -199,13 +209,13 @@ __global__ void __launch_bounds__(256, 1) k_fwd_fft(const float2 *__restrict__ x
             const float2 zz[4] = {z0, z1, z2, z3};
 #pragma unroll
             for (int m = 0; m < 4; m++) {
-                const int n = t + 256 * n2 + 4096 * m;
+                const int n = lag_of3(t, n2) + 4096 * m;
                 const float2 y = make_float2(zz[m].x, -zz[m].y);
                 if (POLY) o[(n & 3) * 4096 + (n >> 2)] = y;
                 else o[n] = y;
             }
         }
-        // Z is thread-private and S1/S2 hazards are covered inside subfft4096_inv: no barrier needed.
+        // Z is thread-private and the S1/S2 hazards are covered inside subfft4096_inv3: no barrier needed.
     }
 }
 
@@ -233,11 +243,15 @@ __global__ void __launch_bounds__(256) k_build_ext(const float2 *__restrict__ C,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3-5.  The search kernel.  Persistent CTAs stride over tiles.
-//   M = 1: Navstar / QZSS, lags 0..4091 (only m = 0 of the radix-4 combine is formed)
-//   M = 4: Galileo E1B,    lags 0..16367
-//   MULTI: k_noncoh > 1 (M = 1 only): power summed over blocks, P[n] += |r_b[(n + 16 b) mod N]|^2; the
-//          16-lag-per-block code advance is removed in the front end by delaying block b (see k_hb2).
+// K3-5.  The search kernels.  Persistent CTAs stride over tiles = (capture, satellite, Doppler index); a tile
+// runs K inverse FFTs of 16384 points as four 4096-point sub-FFTs (one per input residue k2).
+//   k_search_l1<MULTI> : Navstar / QZSS / SBAS, lags 0..4091 -- only m = 0 of the radix-4 combine is formed,
+//                        so the combine is an accumulation in registers.  Two 256-thread CTAs per SM.
+//                        MULTI (k_noncoh > 1): block powers summed in registers,
+//                        P[n] += |r_b[(n + 16 b) mod N]|^2; the 16-lag-per-block code advance is removed
+//                        in the front end by delaying block b (see k_hb2).
+//   k_search_e1b       : Galileo E1B, lags 0..16367 -- three residues are parked in a thread-private shared
+//                        scratch and all four m are formed.  One CTA per SM.
 // ---------------------------------------------------------------------------------------------
 struct Peak {
     float p;
@@ -280,272 +294,162 @@ __device__ __forceinline__ Peak block_reduce_peak(Peak v, float *red_f, int *red
     return v;  // valid in thread 0
 }
 
-template <int M, bool MULTI>
-__global__ void __launch_bounds__(256, (M == 1) ? 2 : 1) k_search(const SearchArgs p)
-{
-    static_assert(!(MULTI && M != 1), "non-coherent accumulation is implemented for the 1 ms lag window only");
-    extern __shared__ __align__(16) unsigned char smem[];
-    const FftSmem s = fft_smem_carve(smem);
-    unsigned char *tail = smem + fft_smem_bytes();
-    float2 *Z = reinterpret_cast<float2 *>(tail);  // M == 4 only
-    if (M == 4) tail += kZBytes;
-    float *red_f = reinterpret_cast<float *>(tail);
-    int *red_i = reinterpret_cast<int *>(tail + 16 * sizeof(float));
-    const int t = threadIdx.x;
-    constexpr int L = (M == 1) ? ACQ_LAGS_L1 : ACQ_LAGS_E1B;
-
-    fft_load_tables(s, p.tables, t, 256);
-
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int d = (int)(tile % p.n_dop);
+struct TileIdx {
+    int sat, slot, cap, d, dop, v;
+    __device__ __forceinline__ TileIdx(const SearchArgs &p, long long tile)
+    {
+        d = (int)(tile % p.n_dop);
         const long long cw = tile / p.n_dop;
         const int wi = (int)(cw % p.n_work);
-        const int cap = (int)(cw / p.n_work);
+        cap = (int)(cw / p.n_work);
         const int2 wk = p.work[wi];
-        const int sat = wk.x, slot = wk.y;
+        sat = wk.x;
+        slot = wk.y;
         const int h = p.dop_lo + d;
-        const int v = p.half_bin ? (h & 1) : 0;
-        const int dop = p.half_bin ? ((h - v) >> 1) : h;
-
-        float P[MULTI ? 16 : 1];
-        Peak best;
-        best.p = 0.0f;
-        best.n = 0x7fffffff;
-        best.sum = 0.0f;
-
-        for (int b = 0; b < p.K; b++) {
-            const float2 *Dblk = p.Dp + ((size_t)((size_t)cap * p.K + b) * p.nvar + v) * kN + t;
-            float2 x[16];
-            float2 acc[16];
-            for (int k2 = 0; k2 < 4; k2++) {
-                const int r = (k2 - dop) & 3;
-                const int q = (k2 - dop - r) >> 2;
-                const float2 *Dk = Dblk + k2 * kSub;
-                const float2 *Ek = p.Ep + (size_t)(sat * 4 + r) * p.ext_len + p.Q + q + t;
-                // prod = conj(data) * code[k - dop]   (search.cpp:471, support/simd.cpp:12-40)
-#pragma unroll
-                for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(__ldg(Dk + 256 * a), __ldg(Ek + 256 * a));
-                subfft4096_inv(x, k2, s, t);
-                if (M == 1) {
-                    if (k2 == 0) {
-#pragma unroll
-                        for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
-                    } else {
-#pragma unroll
-                        for (int n2 = 0; n2 < 16; n2++) acc[n2] = cadd(acc[n2], cmul(x[r16(n2)], c_cC[k2][n2]));
-                    }
-                } else if (k2 < 3) {
-#pragma unroll
-                    for (int n2 = 0; n2 < 16; n2++) {
-                        const float2 z = (k2 == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[k2][n2]);
-                        Z[(k2 * 16 + n2) * 256 + t] = z;
-                    }
-                }
-            }
-
-            if (M == 1 && !MULTI) {
-                // power, max, first argmax, sum over lags n = t + 256*n2 < 4092   (search.cpp:486-490)
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) {
-                    const int n = t + 256 * n2;
-                    const float pw = acc[n2].x * acc[n2].x + acc[n2].y * acc[n2].y;
-                    if (n < L) {
-                        if (pw > best.p) best.p = pw, best.n = n;
-                        best.sum += pw;
-                    }
-                }
-            } else if (M == 1 && MULTI) {
-                // block b was delayed by 16*b samples in the front end (k_hb2), so lag n lines up across blocks
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) {
-                    const float pw = acc[n2].x * acc[n2].x + acc[n2].y * acc[n2].y;
-                    P[n2] = (b == 0) ? pw : P[n2] + pw;
-                }
-            } else {
-                // E1B: radix-4 combine over k2, lags n = t + 256*n2 + 4096*m < 16368
-                // (lags are not visited in increasing order here, so ties compare the index explicitly)
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) {
-                    float2 z0 = Z[(0 * 16 + n2) * 256 + t];
-                    float2 z1 = Z[(1 * 16 + n2) * 256 + t];
-                    float2 z2 = Z[(2 * 16 + n2) * 256 + t];
-                    float2 z3 = cmul(x[r16(n2)], c_cC[3][n2]);
-                    radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
-                    const float2 zz[4] = {z0, z1, z2, z3};
-#pragma unroll
-                    for (int m = 0; m < 4; m++) {
-                        const int n = t + 256 * n2 + 4096 * m;
-                        const float pw = zz[m].x * zz[m].x + zz[m].y * zz[m].y;
-                        if (n < L) peak_merge(best, pw, n, pw);
-                    }
-                }
-            }
-        }
-
-        if (MULTI) {
-#pragma unroll
-            for (int n2 = 0; n2 < 16; n2++) {
-                const int n = t + 256 * n2;
-                if (n < L) {
-                    if (P[n2] > best.p) best.p = P[n2], best.n = n;
-                    best.sum += P[n2];
-                }
-            }
-        }
-
-        const Peak tot = block_reduce_peak(best, red_f, red_i, t);
-        if (t == 0) {
-            acq_cell c;
-            c.peak = tot.p;
-            c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
-            c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
-            c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
-            p.cells[((size_t)cap * p.n_slots + slot) * p.n_dop + d] = c;
-        }
-        // red_f/red_i are next written after >= 8 barriers of the following tile: no extra barrier.
+        v = p.half_bin ? (h & 1) : 0;
+        dop = p.half_bin ? ((h - v) >> 1) : h;
     }
+};
+
+__device__ __forceinline__ void store_cell(const SearchArgs &p, const TileIdx &ti, const Peak &tot, int L)
+{
+    acq_cell c;
+    c.peak = tot.p;
+    c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
+    c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
+    c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
+    p.cells[((size_t)ti.cap * p.n_slots + ti.slot) * p.n_dop + ti.d] = c;
 }
 
-// ---------------------------------------------------------------------------------------------
-// K3-5, packed variant for the 1 ms lag window (Navstar / QZSS): two Doppler indices per thread in the two
-// lanes of f32x2 instructions (see acq_search2.cuh).  One persistent 256-thread CTA per SM strides over
-// (capture, satellite, Doppler pair).  Lane A = index d0, lane B = index d1 = d0 + 1 bin (d1 == d0 for the
-// unpaired last index, whose lane-B result is dropped).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_split_planar(const float2 *__restrict__ Ep, float *__restrict__ ERp,
-                                                      float *__restrict__ EIp, size_t n)
+// x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471, support/simd.cpp:12-40).
+// The Doppler shift is a pointer offset (r, q) into the margin-extended polyphase code rows.
+__device__ __forceinline__ void load_products(float2 (&x)[16], const SearchArgs &p, const TileIdx &ti, int b, int k2,
+                                              int t)
 {
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < n) {
-        const float2 v = Ep[i];
-        ERp[i] = v.x;
-        EIp[i] = v.y;
-    }
+    const int r = (k2 - ti.dop) & 3;
+    const int q = (k2 - ti.dop - r) >> 2;
+    const float2 *Dk = p.Dp + ((size_t)((size_t)ti.cap * p.K + b) * p.nvar + ti.v) * kN + k2 * kSub + t;
+    const float2 *Ek = p.Ep + (size_t)(ti.sat * 4 + r) * p.ext_len + p.Q + q + t;
+#pragma unroll
+    for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(__ldg(Dk + 256 * a), __ldg(Ek + 256 * a));
+}
+
+__device__ __forceinline__ float cpower(float2 a)
+{
+    const float2 sq = __fmul2_rn(a, a);
+    return sq.x + sq.y;  // re^2 + im^2   (search.cpp:487)
 }
 
 template <bool MULTI>
-__global__ void __launch_bounds__(256, 1) k_search2(const SearchArgs p)
+__global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const FftSmem2 s = fft_smem2_carve(smem);
-    float *red_f = reinterpret_cast<float *>(smem + fft_smem2_bytes());
-    int *red_i = reinterpret_cast<int *>(red_f + 32);
+    const FftSmem3 s = fft_smem3_carve(smem);
+    float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes());
+    int *red_i = reinterpret_cast<int *>(red_f + 16);
     const int t = threadIdx.x;
     constexpr int L = ACQ_LAGS_L1;
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
-        float4 *dst = reinterpret_cast<float4 *>(s.T1);
-        for (int i = t; i < (kT1Elems + kT2Elems) / 2; i += 256) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
+    load_t2(s, p.tables, t);
+    const float2 *base = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
+    int buf = 0;
 
-    const long long n_pairs = (long long)p.n_cap * p.n_work * p.ppr;
-    for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-        const int j = (int)(pr % p.ppr);
-        const long long cw = pr / p.ppr;
-        const int wi = (int)(cw % p.n_work);
-        const int cap = (int)(cw / p.n_work);
-        const int2 wk = p.work[wi];
-        const int sat = wk.x, slot = wk.y;
-        const int2 dd = p.pairs[j];
-        const int h0 = p.dop_lo + dd.x;
-        const int v = p.half_bin ? (h0 & 1) : 0;
-        const int dopA = p.half_bin ? ((h0 - v) >> 1) : h0;
-        const int dopB = (dd.y != dd.x) ? dopA + 1 : dopA;
-
-        CP acc[16];
-        float2 P[MULTI ? 16 : 1];
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileIdx ti(p, tile);
+        float P[MULTI ? 16 : 1];
+        float2 acc[16];
         for (int b = 0; b < p.K; b++) {
-            const float2 *Dblk = p.Dp + ((size_t)((size_t)cap * p.K + b) * p.nvar + v) * kN + t;
-            CP x[16];
+            float2 x[16];
+#pragma unroll 1
             for (int k2 = 0; k2 < 4; k2++) {
-                const int rA = (k2 - dopA) & 3, qA = (k2 - dopA - rA) >> 2;
-                const int rB = (k2 - dopB) & 3, qB = (k2 - dopB - rB) >> 2;
-                const size_t oA = (size_t)(sat * 4 + rA) * p.ext_len + p.Q + qA + t;
-                const size_t oB = (size_t)(sat * 4 + rB) * p.ext_len + p.Q + qB + t;
-                const float2 *Dk = Dblk + k2 * kSub;
-                const float *erA = p.ERp + oA, *eiA = p.EIp + oA, *erB = p.ERp + oB, *eiB = p.EIp + oB;
-                // prod = conj(D) * E for both lanes; D enters as a broadcast scalar operand
-#pragma unroll
-                for (int a = 0; a < 16; a++) {
-                    const float2 dv = __ldg(Dk + 256 * a);
-                    const float2 ER = make_float2(__ldg(erA + 256 * a), __ldg(erB + 256 * a));
-                    const float2 EI = make_float2(__ldg(eiA + 256 * a), __ldg(eiB + 256 * a));
-                    x[a].re = p_fma(EI, p_bc(dv.y), p_mul(ER, p_bc(dv.x)));
-                    x[a].im = p_fma(ER, p_bc(-dv.y), p_mul(EI, p_bc(dv.x)));
-                }
-                subfft4096_inv2(x, k2, s, t);
+                load_products(x, p, ti, b, k2, t);
+                subfft4096_inv3(x, k2, __ldg(base + k2 * 256), buf, s, t);
+                buf ^= 1;
                 if (k2 == 0) {
 #pragma unroll
                     for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
                 } else {
 #pragma unroll
-                    for (int n2 = 0; n2 < 16; n2++) {
-                        const float2 w = c_cC[k2][n2];
-                        const CP z = x[r16(n2)];
-                        acc[n2].re = p_fma(z.im, p_bc(-w.y), p_fma(z.re, p_bc(w.x), acc[n2].re));
-                        acc[n2].im = p_fma(z.im, p_bc(w.x), p_fma(z.re, p_bc(w.y), acc[n2].im));
-                    }
+                    for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
                 }
             }
             if (MULTI) {
+                // block b was delayed by 16*b samples in the front end (k_hb2), so lag n lines up across blocks
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
+            }
+        }
+        // power, max, first argmax, sum over lags n < 4092   (search.cpp:486-490); a thread's n grows with n2
+        Peak best;
+        best.p = 0.0f;
+        best.n = 0x7fffffff;
+        best.sum = 0.0f;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) {
+            const int n = lag_of3(t, n2);
+            const float pw = MULTI ? P[n2] : cpower(acc[n2]);
+            if (n2 < 15 || n < L) {
+                if (pw > best.p) best.p = pw, best.n = n;
+                best.sum += pw;
+            }
+        }
+        const Peak tot = block_reduce_peak(best, red_f, red_i, t);
+        if (t == 0) store_cell(p, ti, tot, L);
+        // red_f/red_i are next written after the 4 barriers of the following tile: no extra barrier.
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) k_search_e1b(const SearchArgs p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const FftSmem3 s = fft_smem3_carve(smem);
+    float2 *Z = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());
+    float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes() + kZBytes);
+    int *red_i = reinterpret_cast<int *>(red_f + 16);
+    const int t = threadIdx.x;
+    constexpr int L = ACQ_LAGS_E1B;
+    load_t2(s, p.tables, t);
+    const float2 *base = p.tables + kT2Elems + t;
+    int buf = 0;
+
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileIdx ti(p, tile);
+        float2 x[16];
+#pragma unroll 1
+        for (int k2 = 0; k2 < 4; k2++) {
+            load_products(x, p, ti, 0, k2, t);
+            subfft4096_inv3(x, k2, __ldg(base + k2 * 256), buf, s, t);
+            buf ^= 1;
+            if (k2 < 3) {
 #pragma unroll
                 for (int n2 = 0; n2 < 16; n2++) {
-                    const float2 pw = p_fma(acc[n2].im, acc[n2].im, p_mul(acc[n2].re, acc[n2].re));
-                    P[n2] = (b == 0) ? pw : p_add(P[n2], pw);
+                    const float2 z = (k2 == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[k2][n2]);
+                    Z[(k2 * 16 + n2) * 256 + t] = z;
                 }
             }
         }
-
-        Peak bA, bB;
-        bA.p = bB.p = 0.0f;
-        bA.n = bB.n = 0x7fffffff;
-        float2 sum = make_float2(0.0f, 0.0f);
+        // radix-4 combine over k2, lags n = lag_of3(t, n2) + 4096 m < 16368.  Lags are not visited in
+        // increasing order here, so ties compare the index explicitly (first index wins, search.cpp:488).
+        Peak best;
+        best.p = 0.0f;
+        best.n = 0x7fffffff;
+        best.sum = 0.0f;
 #pragma unroll
         for (int n2 = 0; n2 < 16; n2++) {
-            const int n = t + 256 * n2;
-            float2 pw = MULTI ? P[n2] : p_fma(acc[n2].im, acc[n2].im, p_mul(acc[n2].re, acc[n2].re));
-            if (n2 == 15 && n >= L) pw = make_float2(0.0f, 0.0f);  // lags 4092..4095 are not scanned (search.cpp:486)
-            if (pw.x > bA.p) bA.p = pw.x, bA.n = n;
-            if (pw.y > bB.p) bB.p = pw.y, bB.n = n;
-            sum = p_add(sum, pw);
-        }
-        bA.sum = sum.x;
-        bB.sum = sum.y;
-        // block reduction of both lanes (shuffles, then one partial per warp)
+            float2 z0 = Z[(0 * 16 + n2) * 256 + t];
+            float2 z1 = Z[(1 * 16 + n2) * 256 + t];
+            float2 z2 = Z[(2 * 16 + n2) * 256 + t];
+            float2 z3 = cmul(x[r16(n2)], c_cC[3][n2]);
+            radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
+            const float2 zz[4] = {z0, z1, z2, z3};
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            peak_merge(bA, __shfl_xor_sync(0xffffffffu, bA.p, off), __shfl_xor_sync(0xffffffffu, bA.n, off),
-                       __shfl_xor_sync(0xffffffffu, bA.sum, off));
-            peak_merge(bB, __shfl_xor_sync(0xffffffffu, bB.p, off), __shfl_xor_sync(0xffffffffu, bB.n, off),
-                       __shfl_xor_sync(0xffffffffu, bB.sum, off));
+            for (int m = 0; m < 4; m++) {
+                const int n = lag_of3(t, n2) + 4096 * m;
+                const float pw = cpower(zz[m]);
+                if (n < L) peak_merge(best, pw, n, pw);
+            }
         }
-        const int w = t >> 5;
-        if ((t & 31) == 0) {
-            red_f[w] = bA.p;
-            red_f[8 + w] = bA.sum;
-            red_f[16 + w] = bB.p;
-            red_f[24 + w] = bB.sum;
-            red_i[w] = bA.n;
-            red_i[8 + w] = bB.n;
-        }
-        __syncthreads();
-        if (t < 2 && (t == 0 || dd.y != dd.x)) {
-            Peak tot;
-            const int o = t * 16, oi = t * 8;
-            tot.p = red_f[o];
-            tot.n = red_i[oi];
-            tot.sum = red_f[o + 8];
-#pragma unroll
-            for (int k = 1; k < 8; k++) peak_merge(tot, red_f[o + k], red_i[oi + k], red_f[o + 8 + k]);
-            acq_cell c;
-            c.peak = tot.p;
-            c.noise = __fdiv_rn(tot.sum, (float)L);
-            c.snr = __fdiv_rn(tot.p, c.noise);
-            c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
-            p.cells[((size_t)cap * p.n_slots + slot) * p.n_dop + (t == 0 ? dd.x : dd.y)] = c;
-        }
-        // red_* are rewritten only after the >= 8 barriers of the next pair
+        const Peak tot = block_reduce_peak(best, red_f, red_i, t);
+        if (t == 0) store_cell(p, ti, tot, L);
     }
 }
 
@@ -596,20 +500,17 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static size_t search2_smem_bytes() { return fft_smem2_bytes() + 64 * sizeof(float); }
-size_t search_smem_bytes(bool e1b) { return fft_smem_bytes() + (e1b ? kZBytes : 0) + 64 * sizeof(float); }
-static size_t fwd_smem_bytes() { return fft_smem_bytes() + kZBytes; }
+static size_t search_l1_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
+static size_t search_e1b_smem_bytes() { return fft_smem3_bytes() + kZBytes + 64 * sizeof(float); }
+static size_t fwd_smem_bytes() { return fft_smem3_bytes() + kZBytes; }
 
 cudaError_t search_kernels_configure()
 {
     cudaError_t e;
-    const int l1 = (int)search_smem_bytes(false), e1 = (int)search_smem_bytes(true), fw = (int)fwd_smem_bytes();
-    if ((e = cudaFuncSetAttribute(k_search<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
-    if ((e = cudaFuncSetAttribute(k_search<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
-    if ((e = cudaFuncSetAttribute(k_search<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
-    const int s2 = (int)search2_smem_bytes();
-    if ((e = cudaFuncSetAttribute(k_search2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2))) return e;
-    if ((e = cudaFuncSetAttribute(k_search2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2))) return e;
+    const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
+    if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     return cudaSuccess;
@@ -663,26 +564,9 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st)
     if (a.n_tiles <= 0) return 0;
     const long long max_ctas = (long long)sm_count * (e1b ? 1 : 2);
     const int grid = (int)(a.n_tiles < max_ctas ? a.n_tiles : max_ctas);
-    const size_t smem = search_smem_bytes(e1b);
-    if (e1b) k_search<4, false><<<grid, 256, smem, st>>>(a);
-    else if (a.K > 1) k_search<1, true><<<grid, 256, smem, st>>>(a);
-    else k_search<1, false><<<grid, 256, smem, st>>>(a);
-    return 1;
-}
-
-int launch_search2(const SearchArgs &a, int sm_count, cudaStream_t st)
-{
-    const long long n_pairs = (long long)a.n_cap * a.n_work * a.ppr;
-    if (n_pairs <= 0) return 0;
-    const int grid = (int)(n_pairs < sm_count ? n_pairs : sm_count);
-    if (a.K > 1) k_search2<true><<<grid, 256, search2_smem_bytes(), st>>>(a);
-    else k_search2<false><<<grid, 256, search2_smem_bytes(), st>>>(a);
-    return 1;
-}
-
-int launch_build_ext_planar(const float2 *Ep, float *ERp, float *EIp, size_t n, cudaStream_t st)
-{
-    k_split_planar<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Ep, ERp, EIp, n);
+    if (e1b) k_search_e1b<<<grid, 256, search_e1b_smem_bytes(), st>>>(a);
+    else if (a.K > 1) k_search_l1<true><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
+    else k_search_l1<false><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
     return 1;
 }
 

@@ -13,21 +13,15 @@ namespace acq {
 struct SearchArgs {
     const float2 *Dp;      // capture spectra, polyphase: [((cap*K + b)*nvar + v)*4 + k2][4096], D[4*k1 + k2]
     const float2 *Ep;      // extended code spectra, polyphase: [(sat*4 + r)][ext_len], E[4*(m - Q) + r]
-    const float2 *tables;  // twiddle tables (kT1Elems + kT2Elems float2)
+    const float2 *tables;  // twiddle tables: T2 (kT2Elems), then stage-A bases W16384^{4t+k2} (kBaseElems)
     const int2 *work;      // [n_work] (sat, output slot)
     acq_cell *cells;       // [cap][n_slots][n_dop]
     long long n_tiles;
     int n_work, n_slots, n_dop, dop_lo, half_bin, K, nvar, ext_len, Q;
-    // two-bins-per-thread kernel (k_search2): planar extended code rows and the Doppler pairing
-    const float *ERp;      // [(sat*4 + r)][ext_len] real parts
-    const float *EIp;      // [(sat*4 + r)][ext_len] imaginary parts
-    const int2 *pairs;     // [ppr] (d0, d1): Doppler indices sharing a thread; d1 == d0 marks an unpaired index
-    int ppr;               // pairs per (capture, satellite) row
-    int n_cap;
 };
 
 // host-side launchers (all asynchronous on `st`; each returns the number of kernels it launched)
-int launch_tables_init(const float2 *h_cA, const float2 *h_cC, const float *h_hb);
+int launch_tables_init(const float2 *h_cC, const float *h_hb);
 int launch_hb1_bits(const uint8_t *packed, float2 *x1, int n_blocks, cudaStream_t st);
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
 int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st);
@@ -35,11 +29,8 @@ int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_ro
                    cudaStream_t st);
 int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len, int wrap_mode, cudaStream_t st);
 int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st);
-int launch_search2(const SearchArgs &a, int sm_count, cudaStream_t st);
-int launch_build_ext_planar(const float2 *Ep, float *ERp, float *EIp, size_t n, cudaStream_t st);
 int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
                     int dop_lo, cudaStream_t st);
 cudaError_t search_kernels_configure();
-size_t search_smem_bytes(bool e1b);
 
 }  // namespace acq
