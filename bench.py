@@ -196,6 +196,26 @@ def reference_arm(args):
     return 0
 
 
+def cufft_point(torch, stream, batch=256, reps=20):
+    """cuFFT through torch.fft.ifft: `batch` unnormalised-size 16384-point complex64 inverse transforms per call,
+    input and output resident (32 MiB each way, L2-sized).  This is ONLY the transform: the engine's tile also
+    forms the product, the power, the non-coherent sum and the peak search, and never writes the lags."""
+    x = torch.randn(batch, 16384, dtype=torch.complex64, device="cuda")
+    for _ in range(3):
+        y = torch.fft.ifft(x, norm="forward")
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        y = torch.fft.ifft(x, norm="forward")
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    del y
+    return {"what": "torch.fft.ifft (cuFFT) %d x 16384 complex64, out-of-place, transform only" % batch,
+            "ms_per_call": ms, "transforms_per_s": batch / (ms * 1e-3)}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -206,6 +226,9 @@ def main():
     ap.add_argument("--captures-per-gpu", type=int, default=0, help="0 = 1 (cfg5: 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cufft", action="store_true",
+                    help="also time torch.fft.ifft (cuFFT) on a batch of 16384-point transforms: the permitted "
+                         "timed comparison point (inverse FFT only, no product / power / peak search)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -335,6 +358,7 @@ def main():
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get(args.config)
+        traffic = traffic and traffic.get("bytes")
     except Exception:
         pass
     # The binding roof is on-SM: ncu shows the L1/shared-memory data pipe as the busiest unit
@@ -342,7 +366,7 @@ def main():
     # model per tile; the kernel itself moves fewer bytes (3 exchange passes + output pruning).
     roofline = {
         "bound": "smem",
-        "kernel": "k_search (conj-multiply + 16384-pt inverse FFT + |.|^2 + peak search)",
+        "kernel": "k_search_l1 / k_search_e1b (conj-multiply + 16384-pt inverse FFT + |.|^2 + peak search)",
         "achieved": smem_ach * 1e3, "peak": mb["smem_tbs"] * 1e3, "unit": "GB/s", "frac": smem_ach / mb["smem_tbs"],
         "peak_source": "shared-memory micro-benchmark in this run (acq_microbench: conflict-free 8-byte LDS+STS); "
                        "nominal 148 SM x 128 B/clk",
@@ -379,6 +403,8 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
     }
+    if args.cufft:
+        line["cufft_comparison"] = cufft_point(torch, stream)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, table, kw, packed)
     print(json.dumps(line), flush=True)

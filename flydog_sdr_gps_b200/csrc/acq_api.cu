@@ -98,6 +98,7 @@ struct acq_engine {
     bool profiling = false, prof_valid = false;
     cudaEvent_t prof[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
+    int e1b_kernel = 0;  // 0 = by tile count, 1 = one CTA per tile, 2 = cluster of four CTAs per tile (ACQ_E1B_KERNEL)
     // persistent device data
     float2 *d_tables = nullptr, *d_rot = nullptr, *d_C = nullptr, *d_Ep = nullptr;
     // per-call scratch (grown on demand)
@@ -267,7 +268,13 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         a.work = e->d_work + e->n_l1;
         a.n_work = e->n_e1b;
         a.n_tiles = (long long)n_captures * e->n_e1b * e->n_dop;
-        e->launches += launch_search(a, true, e->sm_count, st);
+        // Cluster/DSMEM form when every tile can have a cluster of its own (one wave: 9 us per tile against
+        // 12.5 us for the one-CTA form, measured), when forced (A/B runs), and always for non-coherent sums
+        // (its threads keep the block powers of their 16 lags in registers).  With more tiles than that the
+        // one-CTA-per-tile form has 2.9x the throughput (profiles/r1_e1b_cluster_ab.json).
+        const bool use_cluster = K > 1 || e->e1b_kernel == 2 || (e->e1b_kernel == 0 && a.n_tiles <= e->sm_count / 4);
+        if (use_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st);
+        else e->launches += launch_search(a, true, e->sm_count, st);
     }
     if (prof) CU(cudaEventRecord(e->prof[4], st));
     e->launches += launch_best_dop(e->d_cells, e->d_slot_sat, out_dev, n_captures, e->n_slots, e->n_dop,
@@ -355,8 +362,6 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
         const acq_sat &s = sats[i];
         if (s.type == ACQ_E1B) {
             if (s.prn < 1 || s.prn > 50) return fail(ACQ_ERR_ARG, "sat %d: E1B prn %d outside 1..50", i, s.prn);
-            if (prm.k_noncoh > 1)
-                return fail(ACQ_ERR_UNSUPPORTED, "k_noncoh > 1 is implemented for Navstar/QZSS only (sat %d is E1B)", i);
         } else if (s.type == ACQ_NAVSTAR || s.type == ACQ_QZSS || s.type == ACQ_SBAS) {
             const bool preset = (s.t1 > 10 || s.t2 > 10);
             if (!preset && (s.t1 < 1 || s.t2 < 1)) return fail(ACQ_ERR_ARG, "sat %d: G2 taps must be in 1..10", i);
@@ -400,6 +405,7 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
         }                                                                                           \
     } while (0)
 
+    if (const char *kv = getenv("ACQ_E1B_KERNEL")) e->e1b_kernel = !strcmp(kv, "cta") ? 1 : !strcmp(kv, "cluster") ? 2 : 0;
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUE(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
     CUE(search_kernels_configure());

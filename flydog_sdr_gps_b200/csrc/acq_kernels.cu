@@ -11,6 +11,8 @@
 //
 // The half-band stages use explicit round-to-nearest mul/add in the reference's summation order
 // (no FMA contraction), so the FFT inputs are bit-identical to the reference's x86 build.
+#include <cooperative_groups.h>
+
 #include "acq_fft.cuh"
 #include "acq_kernels.cuh"
 
@@ -453,6 +455,106 @@ __global__ void __launch_bounds__(256, 1) k_search_e1b(const SearchArgs p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3-5, cluster form of the E1B search: one tile per thread-block CLUSTER of four CTAs.  CTA rank k2 runs the
+// 4096-point sub-FFT of input residue k2 (all four in parallel on four SMs) and publishes its twiddled output
+// Y_k2[n'] in its own shared memory.  After a cluster barrier CTA rank c forms ALL FOUR lag quarters for its
+// slice of n' (n2 in 4c .. 4c+3),
+//     r[n' + 4096 m] = sum_k2 j^{k2 m} Y_k2[n'],      m = 0..3,
+// reading the other three CTAs' slices through distributed shared memory (DSMEM, ld.shared::cluster): 24 KiB of
+// remote reads per CTA and tile.  (Splitting by m instead would make every CTA read all of every Y: 96 KiB.)
+// Peaks are reduced per CTA, sent to rank 0 through DSMEM and merged there; only the 16-byte cell leaves the
+// cluster.  No thread-private scratch, four SMs per tile: shorter latency per tile and a 4x finer scheduling
+// grain than k_search_e1b.  The host picks the form in acq_api.cu (ACQ_E1B_KERNEL=cta|cluster forces one).
+// MULTI (k_noncoh > 1): each thread owns 16 lags (4 values of n2 x 4 quarters), so the block powers are summed
+// in registers exactly as in k_search_l1 (front-end block delay, see k_hb2).  Y is double
+// buffered: one cluster barrier per block (a buffer is rewritten two blocks later, after the barrier every
+// CTA reached only when it had finished reading it).
+template <bool MULTI>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b_cluster(const SearchArgs p)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem[];
+    const FftSmem3 s = fft_smem3_carve(smem);
+    float2 *Y = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());            // [2][16][256] own residue
+    float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes() + 2 * sizeof(float2) * kSub);
+    int *red_i = reinterpret_cast<int *>(red_f + 16);
+    float *peaks_f = red_f + 32;  // [4][2] (peak, sum) per rank, filled through DSMEM in rank 0
+    int *peaks_i = reinterpret_cast<int *>(red_f + 40);
+    const int t = threadIdx.x;
+    const int rank = (int)cluster.block_rank();  // = k2 in the sub-FFT phase, = n2 slice in the combine phase
+    constexpr int L = ACQ_LAGS_E1B;
+    load_t2(s, p.tables, t);
+    const float2 bw = __ldg(p.tables + kT2Elems + rank * 256 + t);
+    const float2 *Yr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) Yr[k] = cluster.map_shared_rank(Y, k);
+    float *peaks_f0 = cluster.map_shared_rank(peaks_f, 0);
+    int *peaks_i0 = cluster.map_shared_rank(peaks_i, 0);
+    const int n_clusters = gridDim.x >> 2;
+    int buf = 0, yb = 0;
+
+    for (long long tile = blockIdx.x >> 2; tile < p.n_tiles; tile += n_clusters) {
+        const TileIdx ti(p, tile);
+        float P[16];
+        for (int b = 0; b < p.K; b++) {
+            float2 x[16];
+            load_products(x, p, ti, b, rank, t);
+            subfft4096_inv3(x, rank, bw, buf, s, t);
+            buf ^= 1;
+            float2 *Yw = Y + yb * kSub;
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++)
+                Yw[n2 * 256 + t] = (rank == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[rank][n2]);
+            cluster.sync();  // every Y_k2 of this block is complete and visible cluster-wide
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int o = yb * kSub + (4 * rank + i) * 256 + t;
+                float2 z0 = Yr[0][o], z1 = Yr[1][o], z2 = Yr[2][o], z3 = Yr[3][o];
+                radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
+                const float2 zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const float pw = cpower(zz[m]);
+                    P[4 * m + i] = (!MULTI || b == 0) ? pw : P[4 * m + i] + pw;
+                }
+            }
+            yb ^= 1;
+        }
+        Peak best;
+        best.p = 0.0f;
+        best.n = 0x7fffffff;
+        best.sum = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {   // q = 4 m + i: this thread's lags in increasing order
+            const int n = lag_of3(t, 4 * rank + (q & 3)) + 4096 * (q >> 2);
+            if (n < L) {   // strict > keeps the first maximum (search.cpp:488)
+                if (P[q] > best.p) best.p = P[q], best.n = n;
+                best.sum += P[q];
+            }
+        }
+        const Peak tot = block_reduce_peak(best, red_f, red_i, t);
+        if (t == 0) {
+            peaks_f0[2 * rank] = tot.p;
+            peaks_f0[2 * rank + 1] = tot.sum;
+            peaks_i0[rank] = tot.n;
+        }
+        cluster.sync();  // peaks have landed in rank 0
+        if (rank == 0 && t == 0) {
+            Peak all;
+            all.p = peaks_f[0];
+            all.sum = peaks_f[1];
+            all.n = peaks_i[0];
+#pragma unroll
+            for (int k = 1; k < 4; k++) peak_merge(all, peaks_f[2 * k], peaks_i[k], peaks_f[2 * k + 1]);
+            store_cell(p, ti, all, L);
+        }
+        // the peak slots are rewritten only after the next tile's first cluster barrier, which rank 0's
+        // thread 0 reaches after the merge above
+    }
+}
+
 // K5b.  max_snr = 0; for dop ascending: if (snr > max_snr) take it   (search.cpp:455,495).
 // One warp per (capture, sat) row: lanes stride over the Doppler cells, then a shuffle reduction that
 // prefers the larger snr and, on equal snr, the lower Doppler index (what the sequential scan keeps).
@@ -502,6 +604,7 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 // ---------------------------------------------------------------------------------------------
 static size_t search_l1_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
 static size_t search_e1b_smem_bytes() { return fft_smem3_bytes() + kZBytes + 64 * sizeof(float); }
+static size_t search_e1b_cluster_smem_bytes() { return fft_smem3_bytes() + 2 * sizeof(float2) * kSub + 64 * sizeof(float); }
 static size_t fwd_smem_bytes() { return fft_smem3_bytes() + kZBytes; }
 
 cudaError_t search_kernels_configure()
@@ -511,6 +614,9 @@ cudaError_t search_kernels_configure()
     if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
+    const int ec = (int)search_e1b_cluster_smem_bytes();
+    if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     return cudaSuccess;
@@ -567,6 +673,16 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st)
     if (e1b) k_search_e1b<<<grid, 256, search_e1b_smem_bytes(), st>>>(a);
     else if (a.K > 1) k_search_l1<true><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
     else k_search_l1<false><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
+    return 1;
+}
+
+int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st)
+{
+    if (a.n_tiles <= 0) return 0;
+    const long long max_clusters = sm_count / 4;
+    const int n_clusters = (int)(a.n_tiles < max_clusters ? a.n_tiles : max_clusters);
+    if (a.K > 1) k_search_e1b_cluster<true><<<4 * n_clusters, 256, search_e1b_cluster_smem_bytes(), st>>>(a);
+    else k_search_e1b_cluster<false><<<4 * n_clusters, 256, search_e1b_cluster_smem_bytes(), st>>>(a);
     return 1;
 }
 

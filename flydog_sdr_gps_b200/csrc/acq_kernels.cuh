@@ -29,6 +29,7 @@ int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_ro
                    cudaStream_t st);
 int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len, int wrap_mode, cudaStream_t st);
 int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st);
+int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st);
 int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
                     int dop_lo, cudaStream_t st);
 cudaError_t search_kernels_configure();

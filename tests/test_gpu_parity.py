@@ -276,8 +276,8 @@ def test_error_paths(nav_engine):
     assert L.acq_search(nav_engine._h, None, 1, None, 0, out.ctypes.data) == -1
     assert L.acq_search(nav_engine._h, cap.ctypes.data, 0, None, 0, out.ctypes.data) == -1
     with pytest.raises(F.AcqError) as ei:
-        F.AcqEngine(S.e1b([1, 2]), F.default_params(k_noncoh=4))
-    assert ei.value.code == -4  # ACQ_ERR_UNSUPPORTED, stated not silently degraded
+        F.AcqEngine(S.e1b([1, 2]), F.default_params(k_noncoh=300))
+    assert ei.value.code == -1
     with pytest.raises(F.AcqError):
         F.AcqEngine(S.navstar(), F.default_params(dop_lo=5, dop_hi=-5))
     with pytest.raises(F.AcqError):
@@ -346,3 +346,38 @@ def test_dropin_batch_mode_and_gsig(gpu_required, golden_search):
     assert started2 == sorted(np.nonzero(golden_search["snr"][0][:32] >= 60)[0].tolist())
     assert all(e[1] < 32 for e in rx2.events if e[0] == "chan_reset")
     d2.close()
+
+
+def test_e1b_cluster_kernel_equals_single_cta_kernel(gpu_required, oracle, monkeypatch):
+    """The cluster/DSMEM form of the E1B search (four CTAs per tile) against the one-CTA-per-tile form on the same
+    capture: same sub-FFTs and combine, so peaks and lags are bitwise equal; only the order of the noise sum
+    differs.  Both against the oracle."""
+    table = scenarios.table("cfg3")[:12]
+    kw = scenarios.params_kw("cfg3")
+    cap = synth.make_capture(33, 1, table, [(1, 30000, -6 * F.BIN_HZ, 47, 0.4), (7, 1000, 31 * F.BIN_HZ, 46, 1.4),
+                                            (11, 65000, 0.0, 45, 2.4)])
+    out = {}
+    for kind in ("cta", "cluster"):
+        monkeypatch.setenv("ACQ_E1B_KERNEL", kind)
+        with F.AcqEngine(table, F.default_params(**kw)) as eng:
+            out[kind] = eng.search(cap, want_grid=True)
+    (ra, ga), (rb, gb) = out["cta"], out["cluster"]
+    assert np.array_equal(ga["peak"], gb["peak"]) and np.array_equal(ga["lag"], gb["lag"])
+    np.testing.assert_allclose(ga["noise"], gb["noise"], rtol=2e-6)
+    assert np.array_equal(ra["lag"], rb["lag"]) and np.array_equal(ra["dop"], rb["dop"])
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
+    compare_records(rb[0], orec, ogrid, kw["dop_lo"], 16.0, ggrid=gb[0], max_ties=1)
+    assert {int(r["sat"]) for r in rb[0] if r["snr"] >= 16} >= {1, 7, 11}
+
+
+def test_e1b_noncoherent_blocks(gpu_required, oracle):
+    """Galileo E1B with K = 4 non-coherent blocks and half-bin Doppler (cluster kernel, block powers summed in
+    registers per lag quarter) against the oracle's extension of search.cpp."""
+    table = scenarios.table("cfg3")[:10]
+    kw = dict(dop_lo=-12, dop_hi=12, half_bin=1, k_noncoh=4, thr_e1b=8.0)
+    cap = synth.make_capture(35, 4, table, [(2, 20000, 3.5 * F.BIN_HZ, 40, 0.3), (6, 61000, -2 * F.BIN_HZ, 39, 1.1)])
+    with F.AcqEngine(table, F.default_params(**kw)) as eng:
+        rec, grid = eng.search(cap, want_grid=True)
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
+    compare_records(rec[0], orec, ogrid, kw["dop_lo"], kw["thr_e1b"], ggrid=grid[0], max_ties=1)
+    assert {int(r["sat"]) for r in rec[0] if r["snr"] >= kw["thr_e1b"]} >= {2, 6}
