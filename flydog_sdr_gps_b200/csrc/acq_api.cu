@@ -96,7 +96,7 @@ struct acq_engine {
     bool pending = false;
     int64_t launches = 0;
     bool profiling = false, prof_valid = false;
-    cudaEvent_t prof[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t prof[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
     int e1b_kernel = 0;  // 0 = by tile count, 1 = one CTA per tile, 2 = cluster of four CTAs per tile (ACQ_E1B_KERNEL)
     // persistent device data
@@ -104,7 +104,7 @@ struct acq_engine {
     // per-call scratch (grown on demand)
     size_t cap_blocks = 0, cap_cells = 0, cap_rows = 0, cap_packed = 0;
     uint8_t *d_packed = nullptr;
-    float2 *d_x1 = nullptr, *d_x2 = nullptr, *d_Dp = nullptr;
+    float2 *d_x2 = nullptr, *d_Dp = nullptr;
     acq_cell *d_cells = nullptr;
     acq_record *d_records = nullptr;
     // selection cache
@@ -130,7 +130,6 @@ int free_engine(acq_engine *e)
     cudaFree(e->d_C);
     cudaFree(e->d_Ep);
     cudaFree(e->d_packed);
-    cudaFree(e->d_x1);
     cudaFree(e->d_x2);
     cudaFree(e->d_Dp);
     cudaFree(e->d_cells);
@@ -160,15 +159,13 @@ int grow(T *&ptr, size_t &cap, size_t need_elems)
 int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool own_packed)
 {
     const size_t blocks = (size_t)n_captures * e->prm.k_noncoh;
-    if (blocks > e->cap_blocks || !e->d_x1) {
+    if (blocks > e->cap_blocks || !e->d_x2) {
         // changing scratch under an in-flight stream is not allowed: drain first
         CU(cudaStreamSynchronize(e->stream));
-        if (e->d_x1) CU(cudaFree(e->d_x1));
         if (e->d_x2) CU(cudaFree(e->d_x2));
         if (e->d_Dp) CU(cudaFree(e->d_Dp));
-        e->d_x1 = e->d_x2 = e->d_Dp = nullptr;
+        e->d_x2 = e->d_Dp = nullptr;
         e->cap_blocks = 0;
-        CU(cudaMalloc(&e->d_x1, blocks * 32768 * sizeof(float2)));
         CU(cudaMalloc(&e->d_x2, blocks * e->nvar * kN * sizeof(float2)));
         CU(cudaMalloc(&e->d_Dp, blocks * e->nvar * kN * sizeof(float2)));
         e->cap_blocks = blocks;
@@ -239,12 +236,10 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const int blocks = n_captures * K;
     const bool prof = e->profiling;
     if (prof) CU(cudaEventRecord(e->prof[0], st));
-    e->launches += launch_hb1_bits(packed_dev, e->d_x1, blocks, st);
+    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, st);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
-    e->launches += launch_hb2(e->d_x1, e->d_x2, e->d_rot, blocks, e->nvar, K, st);
-    if (prof) CU(cudaEventRecord(e->prof[2], st));
     e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar, true, e->sm_count, st);
-    if (prof) CU(cudaEventRecord(e->prof[3], st));
+    if (prof) CU(cudaEventRecord(e->prof[2], st));
     SearchArgs a{};
     a.Dp = e->d_Dp;
     a.Ep = e->d_Ep;
@@ -276,11 +271,11 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         if (use_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st);
         else e->launches += launch_search(a, true, e->sm_count, st);
     }
-    if (prof) CU(cudaEventRecord(e->prof[4], st));
+    if (prof) CU(cudaEventRecord(e->prof[3], st));
     e->launches += launch_best_dop(e->d_cells, e->d_slot_sat, out_dev, n_captures, e->n_slots, e->n_dop,
                                    e->prm.dop_lo, st);
     if (prof) {
-        CU(cudaEventRecord(e->prof[5], st));
+        CU(cudaEventRecord(e->prof[4], st));
         e->prof_valid = true;
     }
     CU(cudaGetLastError());
@@ -517,6 +512,8 @@ int acq_search_device(acq_engine *e, const uint8_t *packed_dev, int n_captures, 
 {
     int rc = check_search_args(e, packed_dev, n_captures, out_dev);
     if (rc) return rc;
+    if (((uintptr_t)packed_dev & 15) != 0)
+        return fail(ACQ_ERR_ARG, "packed_dev must be 16-byte aligned (the front end stages it with bulk async copies)");
     DeviceGuard g(e->device);
     if ((rc = set_selection(e, sel, n_sel))) return rc;
     if ((rc = ensure_scratch(e, n_captures, e->n_slots, false))) return rc;
@@ -577,13 +574,12 @@ int acq_get_capture_spectrum(acq_engine *e, const uint8_t *packed, int half_rot,
     if (e->pending) return fail(ACQ_ERR_ARG, "a submitted search is still pending");
     DeviceGuard g(e->device);
     uint8_t *d_pk = nullptr;
-    float2 *d_x1 = nullptr, *d_x2 = nullptr, *d_D = nullptr, *d_rot = nullptr;
+    float2 *d_x2 = nullptr, *d_D = nullptr, *d_rot = nullptr;
     std::vector<float2> rot;
     int rc = ACQ_OK;
     cudaError_t ce = cudaSuccess;
     do {
         if ((ce = cudaMalloc(&d_pk, ACQ_BLOCK_BYTES))) break;
-        if ((ce = cudaMalloc(&d_x1, 32768 * sizeof(float2)))) break;
         if ((ce = cudaMalloc(&d_x2, 2 * kN * sizeof(float2)))) break;
         if ((ce = cudaMalloc(&d_D, kN * sizeof(float2)))) break;
         if ((ce = cudaMemcpy(d_pk, packed, ACQ_BLOCK_BYTES, cudaMemcpyHostToDevice))) break;
@@ -599,8 +595,7 @@ int acq_get_capture_spectrum(acq_engine *e, const uint8_t *packed, int half_rot,
             if ((ce = cudaMemcpy(d_rot, rot.data(), kN * sizeof(float2), cudaMemcpyHostToDevice))) break;
             rotp = d_rot;
         }
-        e->launches += launch_hb1_bits(d_pk, d_x1, 1, e->stream);
-        e->launches += launch_hb2(d_x1, d_x2, rotp, 1, half_rot ? 2 : 1, 1, e->stream);
+        e->launches += launch_front_end(d_pk, d_x2, rotp, 1, half_rot ? 2 : 1, 1, e->stream);
         const float2 *sel_x2 = d_x2 + (half_rot ? kN : 0);
         e->launches += launch_fwd_fft(sel_x2, d_D, e->d_tables, 1, false, e->sm_count, e->stream);
         if ((ce = cudaGetLastError())) break;
@@ -609,7 +604,6 @@ int acq_get_capture_spectrum(acq_engine *e, const uint8_t *packed, int half_rot,
         if (D && (ce = cudaMemcpy(D, d_D, kN * sizeof(float2), cudaMemcpyDeviceToHost))) break;
     } while (0);
     cudaFree(d_pk);
-    cudaFree(d_x1);
     cudaFree(d_x2);
     cudaFree(d_D);
     cudaFree(d_rot);
@@ -641,11 +635,11 @@ int acq_set_profiling(acq_engine *e, int enable)
 
 int acq_get_kernel_ms(acq_engine *e, float *out, int n_out)
 {
-    if (!e || !out || n_out < 5) return fail(ACQ_ERR_ARG, "bad argument");
+    if (!e || !out || n_out < 4) return fail(ACQ_ERR_ARG, "bad argument");
     if (!e->prof_valid) return fail(ACQ_ERR_ARG, "no profiled search yet (call acq_set_profiling first)");
     DeviceGuard g(e->device);
-    CU(cudaEventSynchronize(e->prof[5]));
-    for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(&out[i], e->prof[i], e->prof[i + 1]));
+    CU(cudaEventSynchronize(e->prof[4]));
+    for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&out[i], e->prof[i], e->prof[i + 1]));
     return ACQ_OK;
 }
 

@@ -1,8 +1,9 @@
 // acq_kernels.cu -- sm_100a kernels of the acquisition engine.
 //
-//   K1a k_hb1_bits   : unpack 1-bit capture, fs/4 XOR mix, first half-band /2      (search.cpp:408-437)
+//   K1  k_front_end  : unpack 1-bit capture (TMA-staged), fs/4 XOR mix, both half-band /2 stages
+//                      (+ optional half-bin pre-rotation, block delay)              (search.cpp:408-441)
 //   K6a k_hb1_code   : C/A / E1B(BOC) replica samples, first half-band /2            (search.cpp:250-275,315-337)
-//   K1b k_hb2        : second half-band /2 (+ optional half-bin pre-rotation)       (search.cpp:439-441)
+//   K6a' k_hb2       : second half-band /2 of the replica                            (search.cpp:273-275)
 //   K2  k_fwd_fft    : 16384-point forward FFT of data or code                       (search.cpp:280,342,447)
 //   K6b k_build_ext  : polyphase, margin-extended code-spectrum rows                 (search.cpp:283-284,471)
 //   K3-5 k_search_l1 / k_search_e1b : conj(D).C product, 16384-point inverse FFT, |.|^2, non-coherent
@@ -46,48 +47,117 @@ struct HbAcc {
     }
 };
 
-// K1a.  One thread per output sample o of x1 (32768 per block).  Sample i of the block is bit i&7 of
-// byte i>>3 (search.cpp:408-411); LO phase is i&3 (lo_rate == 1, search.cpp:386,422-423);
-// I = bit ^ {1,1,0,0}[i&3], Q = bit ^ {1,0,0,1}[i&3]; value = bit ? -1 : +1 (search.cpp:62-66,172-175).
-__global__ void __launch_bounds__(256) k_hb1_bits(const uint8_t *__restrict__ packed, float2 *__restrict__ x1)
+// K1.  Fused capture front end: unpack + fs/4 XOR mix + both half-band /2 stages, one launch.
+// A CTA produces 1024 consecutive samples of x2 for one 65536-sample block.  It needs x1[2 o0 .. 2 o0 + 2077],
+// i.e. capture bits 4 o0 .. 4 o0 + 4185 = 524 bytes starting at byte 512*chunk: the packed bytes are staged
+// into shared memory by ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier complete_tx; SASS UBLKCP),
+// x1 is formed in shared memory (never written to HBM), then x2.
+// Sample i of the block is bit i&7 of byte i>>3 (search.cpp:408-411); LO phase is i&3 (lo_rate == 1,
+// search.cpp:386,422-423); I = bit ^ {1,1,0,0}[i&3], Q = bit ^ {1,0,0,1}[i&3]; value = bit ? -1 : +1
+// (search.cpp:62-66,172-175).  Past the end of the block both stages see zeros (search.cpp:145).
+// Second stage as k_hb2 (optional half-bin variant, block delay for non-coherent sums).
+constexpr int kFeOut = 1024;                   // x2 samples per CTA
+constexpr int kFeX1 = 2 * kFeOut + 30;         // x1 samples needed (2078)
+constexpr int kFeBytes = 544;                  // staged capture bytes (>= 524, multiple of 16)
+
+__global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ packed, float2 *__restrict__ x2,
+                                                   const float2 *__restrict__ rot, int nvar, int K, int row0)
 {
-    const int o = blockIdx.x * 256 + threadIdx.x;
-    const uint8_t *pk = packed + (size_t)blockIdx.y * ACQ_BLOCK_BYTES;
-    const int i0 = 2 * o;
-    unsigned long long win = 0;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const int idx = (i0 >> 3) + k;
-        const unsigned byte = (idx < ACQ_BLOCK_BYTES) ? pk[idx] : 0u;
-        win |= (unsigned long long)byte << (8 * k);
+    __shared__ __align__(16) uint8_t sbits[kFeBytes + 16];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ float2 x1s[kFeX1 + 2];
+    const int t = threadIdx.x;
+    const int chunk = blockIdx.x;                      // 16 chunks per block
+    const uint8_t *pk = packed + (size_t)blockIdx.y * ACQ_BLOCK_BYTES + 512 * chunk;
+    const int avail = ACQ_BLOCK_BYTES - 512 * chunk;   // bytes of this block from the chunk start
+    const int nbytes = avail < kFeBytes ? avail : kFeBytes;  // 512 for the last chunk: never read past the block
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(sbits);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    win >>= (i0 & 7);
-    auto sample = [&](int j, float &xr, float &xi) {
-        const int i = i0 + j;
-        if (i < ACQ_NSAMPLES) {
-            const unsigned bit = (unsigned)(win >> j) & 1u;
-            const unsigned ph = i & 3;
-            const unsigned lsin = (ph < 2) ? 1u : 0u;             // {1,1,0,0}
-            const unsigned lcos = (ph == 0 || ph == 3) ? 1u : 0u; // {1,0,0,1}
-            xr = (bit ^ lsin) ? -1.0f : 1.0f;
-            xi = (bit ^ lcos) ? -1.0f : 1.0f;
-        } else {  // zero padding past the end of the block (search.cpp:145)
-            xr = 0.0f;
-            xi = 0.0f;
+    for (int i = nbytes + t; i < kFeBytes + 16; i += 256) sbits[i] = 0;  // zero tail (samples past the block)
+    __syncthreads();
+    if (t == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(nbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                     "l"(pk), "r"(nbytes), "r"(bar_a)
+                     : "memory");
+    }
+    {   // every thread waits for the bytes to land (phase 0)
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "FE_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+            "@P1 bra FE_DONE;\n"
+            "bra FE_WAIT;\n"
+            "FE_DONE:\n"
+            "}\n" ::"r"(bar_a)
+            : "memory");
+    }
+    // ---- first half-band stage into shared memory: x1s[m] = x1[2*o0 + m]
+    const int i_base = 4 * kFeOut * chunk;  // first capture sample of this chunk (= bit 0 of sbits)
+    for (int m = t; m < kFeX1; m += 256) {
+        const int r0 = 2 * m;  // chunk-relative sample index of the first tap
+        unsigned long long win = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) win |= (unsigned long long)sbits[(r0 >> 3) + k] << (8 * k);
+        win >>= (r0 & 7);
+        auto sample = [&](int j, float &xr, float &xi) {
+            const int i = i_base + r0 + j;
+            if (i < ACQ_NSAMPLES) {
+                const unsigned bit = (unsigned)(win >> j) & 1u;
+                const unsigned ph = i & 3;
+                const unsigned lsin = (ph < 2) ? 1u : 0u;             // {1,1,0,0}
+                const unsigned lcos = (ph == 0 || ph == 3) ? 1u : 0u; // {1,0,0,1}
+                xr = (bit ^ lsin) ? -1.0f : 1.0f;
+                xi = (bit ^ lcos) ? -1.0f : 1.0f;
+            } else {  // zero padding past the end of the block (search.cpp:145)
+                xr = 0.0f;
+                xi = 0.0f;
+            }
+        };
+        HbAcc acc;
+        float xr, xi;
+        sample(0, xr, xi);
+        acc.first(xr, xi, c_hb[0]);
+#pragma unroll
+        for (int j = 2; j <= 30; j += 2) {
+            sample(j, xr, xi);
+            acc.add(xr, xi, c_hb[j / 2]);
         }
-    };
-    HbAcc acc;
-    float xr, xi;
-    sample(0, xr, xi);
-    acc.first(xr, xi, c_hb[0]);
-#pragma unroll
-    for (int j = 2; j <= 30; j += 2) {
-        sample(j, xr, xi);
-        acc.add(xr, xi, c_hb[j / 2]);
+        sample(15, xr, xi);
+        acc.add(xr, xi, c_hb[16]);
+        // x1 has 32768 samples; the second stage pads with zeros beyond (search.cpp:145)
+        x1s[m] = (2 * kFeOut * chunk + m < 32768) ? make_float2(acc.re, acc.im) : make_float2(0.0f, 0.0f);
     }
-    sample(15, xr, xi);
-    acc.add(xr, xi, c_hb[16]);
-    x1[(size_t)blockIdx.y * 32768 + o] = make_float2(acc.re, acc.im);
+    __syncthreads();
+    // ---- second half-band stage: x2[o0 + oo] from x1s[2*oo + j]
+    float2 *out = x2 + (size_t)blockIdx.y * nvar * kN;
+    const int delay = 16 * (int)((row0 + blockIdx.y) % K);
+    for (int oo = t; oo < kFeOut; oo += 256) {
+        const float2 *in = x1s + 2 * oo;
+        HbAcc acc;
+        float2 v = in[0];
+        acc.first(v.x, v.y, c_hb[0]);
+#pragma unroll
+        for (int j = 2; j <= 30; j += 2) {
+            v = in[j];
+            acc.add(v.x, v.y, c_hb[j / 2]);
+        }
+        v = in[15];
+        acc.add(v.x, v.y, c_hb[16]);
+        const int o = kFeOut * chunk + oo;
+        const int od = (o + delay) & (kN - 1);
+        out[od] = make_float2(acc.re, acc.im);
+        if (nvar == 2) {
+            const float2 w = rot[o];
+            out[kN + od] = make_float2(__fsub_rn(__fmul_rn(acc.re, w.x), __fmul_rn(acc.im, w.y)),
+                                      __fadd_rn(__fmul_rn(acc.re, w.y), __fmul_rn(acc.im, w.x)));
+        }
+    }
 }
 
 // K6a.  Replica: sample i carries chip (i>>4) mod codelen (ca_rate = 1/16 exactly, search.cpp:205,254-258),
@@ -622,12 +692,13 @@ cudaError_t search_kernels_configure()
     return cudaSuccess;
 }
 
-int launch_hb1_bits(const uint8_t *packed, float2 *x1, int n_blocks, cudaStream_t st)
+int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, cudaStream_t st)
 {
     int launched = 0;
     for (int b0 = 0; b0 < n_blocks; b0 += 32768) {  // gridDim.y <= 65535
         const int nb = (n_blocks - b0 < 32768) ? (n_blocks - b0) : 32768;
-        k_hb1_bits<<<dim3(128, nb), 256, 0, st>>>(packed + (size_t)b0 * ACQ_BLOCK_BYTES, x1 + (size_t)b0 * 32768);
+        k_front_end<<<dim3(kN / kFeOut, nb), 256, 0, st>>>(packed + (size_t)b0 * ACQ_BLOCK_BYTES,
+                                                          x2 + (size_t)b0 * nvar * kN, rot, nvar, K, b0);
         launched++;
     }
     return launched;

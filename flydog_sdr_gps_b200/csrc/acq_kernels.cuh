@@ -22,7 +22,7 @@ struct SearchArgs {
 
 // host-side launchers (all asynchronous on `st`; each returns the number of kernels it launched)
 int launch_tables_init(const float2 *h_cC, const float *h_hb);
-int launch_hb1_bits(const uint8_t *packed, float2 *x1, int n_blocks, cudaStream_t st);
+int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, cudaStream_t st);
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
 int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st);
 int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_rows, bool polyphase, int sm_count,

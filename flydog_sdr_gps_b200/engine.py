@@ -102,9 +102,9 @@ class AcqEngine:
 
     def kernel_ms(self):
         """Device time of each kernel of the most recent search (needs set_profiling(True))."""
-        out = (C.c_float * 5)()
-        _check(self._L.acq_get_kernel_ms(self._h, out, 5))
-        return dict(zip(["hb1", "hb2", "fwd_fft", "search", "best_dop"], [float(v) for v in out]))
+        out = (C.c_float * 4)()
+        _check(self._L.acq_get_kernel_ms(self._h, out, 4))
+        return dict(zip(["front_end", "fwd_fft", "search", "best_dop"], [float(v) for v in out]))
 
     def device_info(self):
         d, s, c = C.c_int(), C.c_int(), C.c_int()

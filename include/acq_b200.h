@@ -136,7 +136,8 @@ int acq_search_grid(acq_engine *e, const uint8_t *packed, int n_captures, const 
 
 /* Device-resident variant: packed and out are DEVICE pointers on the engine's GPU, work is
  * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the engine's own stream) and the
- * call returns without synchronising.  sel is a HOST array, consumed before returning. */
+ * call returns without synchronising.  sel is a HOST array, consumed before returning.
+ * packed_dev must be 16-byte aligned (the front end stages the capture with bulk asynchronous copies). */
 int acq_search_device(acq_engine *e, const uint8_t *packed_dev, int n_captures, const int32_t *sel, int n_sel,
                       acq_record *out_dev, void *stream);
 
@@ -168,9 +169,9 @@ int acq_get_params(const acq_engine *e, acq_params *p);
 int64_t acq_launch_count(const acq_engine *e);
 /* Per-kernel device timing of the most recent search (CUDA events recorded on the launching stream
  * around each kernel when enabled).  acq_get_kernel_ms waits for that search and fills
- *   out[0] = unpack+mix+half-band 1, out[1] = half-band 2, out[2] = forward FFT,
- *   out[3] = fused correlate + inverse FFT + peak search (all constellations), out[4] = best-Doppler pick
- * in milliseconds; n_out >= 5. */
+ *   out[0] = capture front end (unpack + mix + both half-band stages), out[1] = forward FFT,
+ *   out[2] = fused correlate + inverse FFT + peak search (all constellations), out[3] = best-Doppler pick
+ * in milliseconds; n_out >= 4. */
 int acq_set_profiling(acq_engine *e, int enable);
 int acq_get_kernel_ms(acq_engine *e, float *out, int n_out);
 /* Device ordinal and SM count of the engine's GPU. */

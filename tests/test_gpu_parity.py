@@ -261,7 +261,7 @@ def test_device_resident_api_on_torch_stream(nav_engine):
     n0 = nav_engine.launch_count
     nav_engine.search_device(d_in.data_ptr(), d_out.data_ptr(), 4)
     torch.cuda.synchronize()
-    assert nav_engine.launch_count - n0 == 5  # hb1, hb2, fwd FFT, search, best-Doppler
+    assert nav_engine.launch_count - n0 == 4  # front end, forward FFT, search, best-Doppler
 
 
 def test_error_paths(nav_engine):
