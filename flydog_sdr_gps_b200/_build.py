@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libacq_b200.so")
 CU_SOURCES = ["acq_kernels.cu", "acq_api.cu", "acq_microbench.cu"]
 CPP_SOURCES = ["search_dropin.cpp"]
-HEADERS = ["acq_fft.cuh", "acq_geom.h", "acq_kernels.cuh", "e1b_codes.inc", "search_dropin.h",
+HEADERS = ["acq_fft.cuh", "acq_geom.h", "acq_kernels.cuh", "e1b_codes.inc", os.path.join("..", "..", "include", "search_dropin.h"),
            os.path.join("..", "..", "include", "acq_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,6 +1,7 @@
 // search_dropin.cpp -- see search_dropin.h.  Host C++ above the C ABI; no CUDA types here.
-#include "search_dropin.h"
+#include "../../include/search_dropin.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -206,6 +207,84 @@ int acq_dropin_pass(acq_dropin *d, int mode)
     if (mode == ACQ_DROPIN_LITERAL) return pass_literal(d);
     if (mode == ACQ_DROPIN_BATCH) return pass_batch(d);
     return ACQ_ERR_ARG;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// capture sources
+// ---------------------------------------------------------------------------------------------
+struct acq_capture_file {
+    FILE *fp = nullptr;
+    long long size = 0, pos = 0;
+};
+
+extern "C" {
+
+int acq_capture_from_packets(const uint8_t *const *packets, int n_packets, int packet_bytes, uint8_t *dst)
+{
+    if (!packets || !dst || n_packets <= 0 || packet_bytes <= 0) return ACQ_ERR_ARG;
+    if ((long long)n_packets * packet_bytes != ACQ_BLOCK_BYTES) return ACQ_ERR_ARG;
+    for (int k = 0; k < n_packets; k++) {
+        if (!packets[k]) return ACQ_ERR_ARG;
+        memcpy(dst + (size_t)k * packet_bytes, packets[k], packet_bytes);  // search.cpp:399-406
+    }
+    return ACQ_OK;
+}
+
+int acq_capture_file_open(acq_capture_file **out, const char *path)
+{
+    if (!out || !path) return ACQ_ERR_ARG;
+    *out = nullptr;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return ACQ_ERR_ARG;
+    acq_capture_file *f = new (std::nothrow) acq_capture_file;
+    if (!f || fseek(fp, 0, SEEK_END) != 0) {
+        fclose(fp);
+        delete f;
+        return ACQ_ERR_ARG;
+    }
+    f->fp = fp;
+    f->size = ftell(fp);
+    rewind(fp);
+    *out = f;
+    return ACQ_OK;
+}
+
+int acq_capture_file_next(acq_capture_file *f, uint8_t *dst, int n_blocks)
+{
+    if (!f || !f->fp || !dst || n_blocks <= 0) return ACQ_ERR_ARG;
+    const long long want = (long long)n_blocks * ACQ_BLOCK_BYTES;
+    if (f->size - f->pos < want) return ACQ_CAPTURE_EOF;  // search.cpp:375-378
+    if (fread(dst, 1, (size_t)want, f->fp) != (size_t)want) return ACQ_ERR_ARG;
+    f->pos += want;
+    return ACQ_OK;
+}
+
+long long acq_capture_file_remaining(const acq_capture_file *f)
+{
+    return (f && f->fp) ? (f->size - f->pos) / ACQ_BLOCK_BYTES : 0;
+}
+
+int acq_capture_file_rewind(acq_capture_file *f)
+{
+    if (!f || !f->fp) return ACQ_ERR_ARG;
+    rewind(f->fp);
+    f->pos = 0;
+    return ACQ_OK;
+}
+
+int acq_capture_file_close(acq_capture_file *f)
+{
+    if (!f) return ACQ_OK;
+    if (f->fp) fclose(f->fp);
+    delete f;
+    return ACQ_OK;
+}
+
+int acq_capture_file_iface(void *user, uint8_t *dst)
+{
+    return acq_capture_file_next(static_cast<acq_capture_file *>(user), dst, 1);
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-"""ctypes binding of the host drop-in shim (csrc/search_dropin.h) with Python callbacks as the host
+"""ctypes binding of the host drop-in shim (include/search_dropin.h) with Python callbacks as the host
 side (ChanReset / ChanStart / GPSstat / SPI capture / timer).  Used by the tests to replay the
 reference's SearchTask loop against a mock receiver."""
 import ctypes as C

@@ -6,7 +6,7 @@
  * its boundary is the six free functions of gps/gps.h:140-145 plus the two file-static
  * workers Sample() (gps/search.cpp:382) and Correlate() (gps/search.cpp:453).  Each entry
  * point below names the reference code it replaces.  The host shim that keeps the six
- * SearchXxx symbols and routes them here is flydog_sdr_gps_b200/csrc/search_dropin.cpp;
+ * SearchXxx symbols and routes them here is include/search_dropin.h (flydog_sdr_gps_b200/csrc/search_dropin.cpp);
  * INTEGRATION.md shows the lines a maintainer changes in the reference tree.
  *
  * Conventions

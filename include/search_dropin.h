@@ -17,7 +17,7 @@
 #ifndef ACQ_SEARCH_DROPIN_H
 #define ACQ_SEARCH_DROPIN_H
 
-#include "../../include/acq_b200.h"
+#include "acq_b200.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -68,6 +68,30 @@ int acq_dropin_is_busy(const acq_dropin *d, int sat);
 int acq_dropin_pass(acq_dropin *d, int mode);
 /* The engine underneath (for acq_last_error-style diagnostics and direct searches). */
 acq_engine *acq_dropin_engine(acq_dropin *d);
+
+/* ---- capture sources: the data formats on the input side of the path ----------------
+ * The wire format is the FPGA sampler's: 65536 one-bit samples per capture, LSB first (sample i = bit i&7 of
+ * byte i>>3, gps/search.cpp:408-411), delivered as 16 SPI packets of GPS_SAMPS*2 = 512 bytes
+ * (gps/search.cpp:389,399-406) or, with GPS_SAMPLES_FROM_FILE, read 512 bytes at a time from a raw file of
+ * consecutive captures (gps/search.cpp:361-380,400-401). */
+
+/* Concatenate SPI packets into one capture block: dst[k*packet_bytes ..] = packets[k][0 .. packet_bytes).
+ * n_packets * packet_bytes must equal ACQ_BLOCK_BYTES (16 x 512 on the reference hardware). */
+int acq_capture_from_packets(const uint8_t *const *packets, int n_packets, int packet_bytes, uint8_t *dst);
+
+/* Raw capture file (the GPS_SAMPLES_FROM_FILE format: fs 16.368 MHz, IF 4.092 MHz, 1 bit per sample, packed
+ * LSB first).  acq_capture_file_next reads the next n_blocks * 8192 bytes; it returns ACQ_OK, or
+ * ACQ_CAPTURE_EOF when fewer bytes remain (the reference prints "end of GPS samples data file" and exits,
+ * gps/search.cpp:375-378), or ACQ_ERR_ARG on I/O errors. */
+#define ACQ_CAPTURE_EOF 1
+typedef struct acq_capture_file acq_capture_file;
+int acq_capture_file_open(acq_capture_file **out, const char *path);
+int acq_capture_file_next(acq_capture_file *f, uint8_t *dst, int n_blocks);
+long long acq_capture_file_remaining(const acq_capture_file *f);  /* whole capture blocks left */
+int acq_capture_file_rewind(acq_capture_file *f);
+int acq_capture_file_close(acq_capture_file *f);
+/* acq_host_iface.capture adaptor: user = acq_capture_file*, one block per call, non-zero at end of file. */
+int acq_capture_file_iface(void *user, uint8_t *dst);
 
 #ifdef __cplusplus
 }

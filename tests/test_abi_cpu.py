@@ -12,8 +12,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "acq_b200.h")
 
 
-def declared_functions():
-    text = open(HEADER).read()
+DROPIN_HEADER = os.path.join(ROOT, "include", "search_dropin.h")
+
+
+def declared_functions(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(acq_[a-z0-9_]+)\s*\(", text)))
 
@@ -28,6 +31,11 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(L, n), "libacq_b200.so does not export %s" % n
     # the ctypes binding covers the same set
     assert sorted(_lib.exported_symbols()) == names
+    # the host shim header (drop-in scheduling + capture sources) is exported by the same library
+    shim = declared_functions(DROPIN_HEADER)
+    assert len(shim) >= 14
+    for n in shim:
+        assert hasattr(L, n), "libacq_b200.so does not export %s" % n
 
 
 def test_struct_layouts_match_header():
@@ -77,3 +85,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_py" not in text and "acq_oracle" not in text and "orc_fft" not in text, f
+
+
+def test_capture_sources(tmp_path):
+    """SPI packet assembly and the raw capture file reader (gps/search.cpp:361-406): host-only code."""
+    import numpy as np
+    from flydog_sdr_gps_b200 import capture
+    rng = np.random.default_rng(3)
+    caps = rng.integers(0, 256, (3, 8192), dtype=np.uint8)
+    # 16 x 512-byte packets in arrival order == the capture
+    assert np.array_equal(capture.from_packets([caps[0][k * 512:(k + 1) * 512] for k in range(16)]), caps[0])
+    with pytest.raises(ValueError):
+        capture.from_packets([caps[0][:512]] * 15)
+    path = tmp_path / "if.4092.dat"
+    path.write_bytes(caps.tobytes() + b"\x55" * 100)  # a trailing partial capture is never returned
+    with capture.CaptureFile(path) as f:
+        assert f.remaining() == 3
+        assert np.array_equal(f.next(), caps[0])
+        assert np.array_equal(f.next(2), caps[1:].reshape(-1))
+        assert f.next() is None and f.remaining() == 0
+        f.rewind()
+        assert f.next(4) is None  # non-coherent capture of 4 blocks: not enough data, nothing consumed
+        assert np.array_equal(f.next(3), caps.reshape(-1))
+    with pytest.raises(OSError):
+        capture.CaptureFile(tmp_path / "missing.dat")

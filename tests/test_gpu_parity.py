@@ -381,3 +381,41 @@ def test_e1b_noncoherent_blocks(gpu_required, oracle):
     orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
     compare_records(rec[0], orec, ogrid, kw["dop_lo"], kw["thr_e1b"], ggrid=grid[0], max_ties=1)
     assert {int(r["sat"]) for r in rec[0] if r["snr"] >= kw["thr_e1b"]} >= {2, 6}
+
+
+def test_dropin_with_capture_file_source(gpu_required, golden_search, tmp_path):
+    """GPS_SAMPLES_FROM_FILE path (gps/search.cpp:361-380): the shim's capture callback fed from a raw capture
+    file gives the same detections as the golden per-capture answers, and the file's end stops the pass."""
+    from flydog_sdr_gps_b200 import capture, dropin
+    caps = golden_search["captures"]
+    path = tmp_path / "captures.if.4092.dat"
+    path.write_bytes(np.ascontiguousarray(caps[:2]).tobytes())
+    src = capture.CaptureFile(path)
+
+    class FileReceiver(dropin.MockReceiver):
+        def capture(self, _u, dst):
+            blk = src.next()
+            if blk is None:
+                return 1
+            C.memmove(dst, blk.ctypes.data, 8192)
+            self.samples += 1
+            return 0
+
+    rx = FileReceiver(caps[0], free_chans=12)
+    d = dropin.Dropin(S.reference_table(), rx)
+    for k in range(2):   # batch mode: one capture from the file per pass
+        rx.events.clear()
+        rx.free, rx.next_ch = 12, 0
+        for s in range(59):
+            d.enable(s)
+        d.search_pass(dropin.BATCH)
+        started = {e[2]: e for e in rx.events if e[0] == "chan_start"}
+        strong = np.nonzero(golden_search["snr"][k] >= 16 * (1 + RTOL))[0]
+        assert set(strong.tolist()) <= set(started)
+        for sat in strong:
+            assert started[sat][3] == golden_search["dop"][k][sat] and started[sat][4] == 4 * golden_search["lag"][k][sat]
+    with pytest.raises(RuntimeError):   # end of file: the capture callback fails, the pass reports it
+        d.search_pass(dropin.BATCH)
+    assert rx.samples == 2
+    d.close()
+    src.close()
