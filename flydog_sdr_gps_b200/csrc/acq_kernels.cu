@@ -291,6 +291,63 @@ __global__ void __launch_bounds__(256, 1) k_fwd_fft(const float2 *__restrict__ x
     }
 }
 
+// K2, cluster form for a handful of rows (single-capture searches, where one CTA per row leaves the GPU idle and
+// the forward FFT is a serial 4-sub-FFT chain): a cluster of four CTAs per row, CTA k2 runs one sub-FFT, the
+// radix-4 combine reads the other CTAs' outputs through DSMEM (slices of n', as in k_search_e1b_cluster).
+template <bool POLY>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1)
+    k_fwd_fft_cluster(const float2 *__restrict__ x2, float2 *__restrict__ out, const float2 *__restrict__ tables,
+                      int n_rows)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem[];
+    const FftSmem3 s = fft_smem3_carve(smem);
+    float2 *Y = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());  // [2][16][256]
+    const int t = threadIdx.x;
+    const int rank = (int)cluster.block_rank();
+    load_t2(s, tables, t);
+    const float2 bw = __ldg(tables + kT2Elems + rank * 256 + t);
+    const float2 *Yr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) Yr[k] = cluster.map_shared_rank(Y, k);
+    const int n_clusters = gridDim.x >> 2;
+    int buf = 0, yb = 0;
+    for (int row = blockIdx.x >> 2; row < n_rows; row += n_clusters) {
+        const float2 *in = x2 + (size_t)row * kN;
+        float2 *o = out + (size_t)row * kN;
+        float2 x[16];
+#pragma unroll
+        for (int a = 0; a < 16; a++) {
+            const float2 v = in[1024 * a + 4 * t + rank];
+            x[a] = make_float2(v.x, -v.y);
+        }
+        subfft4096_inv3(x, rank, bw, buf, s, t);
+        buf ^= 1;
+        float2 *Yw = Y + yb * kSub;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) Yw[n2 * 256 + t] = (rank == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[rank][n2]);
+        cluster.sync();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int n2 = 4 * rank + i;
+            const int oidx = yb * kSub + n2 * 256 + t;
+            float2 z0 = Yr[0][oidx], z1 = Yr[1][oidx], z2 = Yr[2][oidx], z3 = Yr[3][oidx];
+            radix4_inv(z0, z1, z2, z3);
+            const float2 zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int n = lag_of3(t, n2) + 4096 * m;
+                const float2 y = make_float2(zz[m].x, -zz[m].y);
+                if (POLY) o[(n & 3) * 4096 + (n >> 2)] = y;
+                else o[n] = y;
+            }
+        }
+        yb ^= 1;  // Y is double buffered: a buffer is rewritten two rows later, after the next cluster barrier
+    }
+    cluster.sync();  // no CTA may exit while another still reads its shared memory
+}
+
 // ---------------------------------------------------------------------------------------------
 // K6b.  Extended polyphase rows of the code spectra:
 //   Ep[(sat*4 + r)][mm] = E_sat[4*(mm - Q) + r],   E_sat[j] = C_sat[j mod N]          for j <  N
@@ -687,6 +744,9 @@ cudaError_t search_kernels_configure()
     const int ec = (int)search_e1b_cluster_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
+    const int fc = (int)(fft_smem3_bytes() + 2 * sizeof(float2) * kSub);
+    if ((e = cudaFuncSetAttribute(k_fwd_fft_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc))) return e;
+    if ((e = cudaFuncSetAttribute(k_fwd_fft_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     return cudaSuccess;
@@ -724,6 +784,12 @@ int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int 
 int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_rows, bool polyphase, int sm_count,
                    cudaStream_t st)
 {
+    if (n_rows <= sm_count / 4) {  // few rows: four CTAs per row (cluster + DSMEM), 2.5x shorter than the serial chain
+        const size_t smem = fft_smem3_bytes() + 2 * sizeof(float2) * kSub;
+        if (polyphase) k_fwd_fft_cluster<true><<<4 * n_rows, 256, smem, st>>>(x2, out, tables, n_rows);
+        else k_fwd_fft_cluster<false><<<4 * n_rows, 256, smem, st>>>(x2, out, tables, n_rows);
+        return 1;
+    }
     const int grid = n_rows < sm_count ? n_rows : sm_count;
     if (polyphase) k_fwd_fft<true><<<grid, 256, fwd_smem_bytes(), st>>>(x2, out, tables, n_rows);
     else k_fwd_fft<false><<<grid, 256, fwd_smem_bytes(), st>>>(x2, out, tables, n_rows);
