@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(256) k_build_ext(const float2 *__restrict__ C,
 //                        MULTI (k_noncoh > 1): block powers summed in registers,
 //                        P[n] += |r_b[(n + 16 b) mod N]|^2; the 16-lag-per-block code advance is removed
 //                        in the front end by delaying block b (see k_hb2).
-//   k_search_e1b       : Galileo E1B, lags 0..16367 -- three residues are parked in a thread-private shared
-//                        scratch and all four m are formed.  One CTA per SM.
+//   k_search_e1b       : Galileo E1B, lags 0..16367 -- three residues are parked in thread-private TENSOR MEMORY
+//                        (tcgen05.st / tcgen05.ld) and all four m are formed.  Two CTAs per SM.
 // ---------------------------------------------------------------------------------------------
 struct Peak {
     float p;
@@ -527,16 +527,60 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     }
 }
 
-__global__ void __launch_bounds__(256, 1) k_search_e1b(const SearchArgs p)
+// Tensor memory (TMEM, 256 KB per SM) as thread-private scratch.  The E1B combine needs the outputs of three
+// residues parked while the fourth is computed: 48 complex values per thread, 96 KiB per CTA.  In shared memory
+// that scratch limits the kernel to one CTA per SM and puts 96 extra loads/stores per thread and tile on the
+// L1/shared data pipe, the kernel's busiest unit.  TMEM is exactly "512 columns of 32 bits per thread lane":
+// tcgen05.st / tcgen05.ld (.32x32b: thread i of the warp <-> lane 32*(warp%4)+i, N consecutive columns <-> N
+// registers) move the parked values over the tensor-memory datapath instead.  Warps w and w+4 share lanes and
+// use disjoint column ranges; a CTA allocates 256 columns, so two CTAs fill the SM's 512.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float2 (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y), "f"(v[4].x),
+        "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y), "f"(v[8].x), "f"(v[8].y),
+        "f"(v[9].x), "f"(v[9].y), "f"(v[10].x), "f"(v[10].y), "f"(v[11].x), "f"(v[11].y), "f"(v[12].x), "f"(v[12].y),
+        "f"(v[13].x), "f"(v[13].y), "f"(v[14].x), "f"(v[14].y), "f"(v[15].x), "f"(v[15].y)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float2 (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x),
+                   "=f"(v[3].y)
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+constexpr int kE1bTmemCols = 256;  // 2 warp sets x 96 columns, rounded up to a power of two
+
+__global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const FftSmem3 s = fft_smem3_carve(smem);
-    float2 *Z = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());
-    float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes() + kZBytes);
+    float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes());
     int *red_i = reinterpret_cast<int *>(red_f + 16);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(red_f + 32);
     const int t = threadIdx.x;
+    const int warp = t >> 5;
     constexpr int L = ACQ_LAGS_E1B;
-    load_t2(s, p.tables, t);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(tmem_slot)),
+                     "n"(kE1bTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    load_t2(s, p.tables, t);  // ends with __syncthreads()
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // this thread's scratch: lane 32*(warp%4) + (t%32), columns [96*(warp/4), +96): [k2][n2] complex
+    const uint32_t zaddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 96);
     const float2 *base = p.tables + kT2Elems + t;
     int buf = 0;
 
@@ -549,11 +593,11 @@ __global__ void __launch_bounds__(256, 1) k_search_e1b(const SearchArgs p)
             subfft4096_inv3(x, k2, __ldg(base + k2 * 256), buf, s, t);
             buf ^= 1;
             if (k2 < 3) {
+                float2 z[16];
 #pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) {
-                    const float2 z = (k2 == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[k2][n2]);
-                    Z[(k2 * 16 + n2) * 256 + t] = z;
-                }
+                for (int n2 = 0; n2 < 16; n2++) z[n2] = (k2 == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[k2][n2]);
+                tmem_st16(zaddr + 32 * k2, z);
+                tmem_wait_st();
             }
         }
         // radix-4 combine over k2, lags n = lag_of3(t, n2) + 4096 m < 16368.  Lags are not visited in
@@ -563,23 +607,33 @@ __global__ void __launch_bounds__(256, 1) k_search_e1b(const SearchArgs p)
         best.n = 0x7fffffff;
         best.sum = 0.0f;
 #pragma unroll
-        for (int n2 = 0; n2 < 16; n2++) {
-            float2 z0 = Z[(0 * 16 + n2) * 256 + t];
-            float2 z1 = Z[(1 * 16 + n2) * 256 + t];
-            float2 z2 = Z[(2 * 16 + n2) * 256 + t];
-            float2 z3 = cmul(x[r16(n2)], c_cC[3][n2]);
-            radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
-            const float2 zz[4] = {z0, z1, z2, z3};
+        for (int c4 = 0; c4 < 4; c4++) {
+            float2 za[4], zb[4], zc[4];
+            tmem_ld4(zaddr + 0 * 32 + 8 * c4, za);
+            tmem_ld4(zaddr + 1 * 32 + 8 * c4, zb);
+            tmem_ld4(zaddr + 2 * 32 + 8 * c4, zc);
+            tmem_wait_ld();
 #pragma unroll
-            for (int m = 0; m < 4; m++) {
-                const int n = lag_of3(t, n2) + 4096 * m;
-                const float pw = cpower(zz[m]);
-                if (n < L) peak_merge(best, pw, n, pw);
+            for (int i = 0; i < 4; i++) {
+                const int n2 = 4 * c4 + i;
+                float2 z0 = za[i], z1 = zb[i], z2 = zc[i];
+                float2 z3 = cmul(x[r16(n2)], c_cC[3][n2]);
+                radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
+                const float2 zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const int n = lag_of3(t, n2) + 4096 * m;
+                    const float pw = cpower(zz[m]);
+                    if (n < L) peak_merge(best, pw, n, pw);
+                }
             }
         }
         const Peak tot = block_reduce_peak(best, red_f, red_i, t);
         if (t == 0) store_cell(p, ti, tot, L);
     }
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kE1bTmemCols) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -730,7 +784,7 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 // launchers
 // ---------------------------------------------------------------------------------------------
 static size_t search_l1_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
-static size_t search_e1b_smem_bytes() { return fft_smem3_bytes() + kZBytes + 64 * sizeof(float); }
+static size_t search_e1b_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
 static size_t search_e1b_cluster_smem_bytes() { return fft_smem3_bytes() + 2 * sizeof(float2) * kSub + 64 * sizeof(float); }
 static size_t fwd_smem_bytes() { return fft_smem3_bytes() + kZBytes; }
 
@@ -805,7 +859,7 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
 int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st)
 {
     if (a.n_tiles <= 0) return 0;
-    const long long max_ctas = (long long)sm_count * (e1b ? 1 : 2);
+    const long long max_ctas = (long long)sm_count * 2;
     const int grid = (int)(a.n_tiles < max_ctas ? a.n_tiles : max_ctas);
     if (e1b) k_search_e1b<<<grid, 256, search_e1b_smem_bytes(), st>>>(a);
     else if (a.K > 1) k_search_l1<true><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
