@@ -111,6 +111,77 @@ __device__ __forceinline__ void radix16_inv(float2 (&x)[16])
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tensor memory (TMEM) as thread-private storage: tcgen05.st / tcgen05.ld with the .32x32b shape map thread i
+// of a warp to TMEM lane 32*(warp%4)+i and N consecutive 32-bit columns to N registers.  Data parked there
+// moves over the tensor-memory datapath, not the L1/shared data pipe.  taddr = (lane base << 16) | column.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float2 (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y), "f"(v[4].x),
+        "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y), "f"(v[8].x), "f"(v[8].y),
+        "f"(v[9].x), "f"(v[9].y), "f"(v[10].x), "f"(v[10].y), "f"(v[11].x), "f"(v[11].y), "f"(v[12].x), "f"(v[12].y),
+        "f"(v[13].x), "f"(v[13].y), "f"(v[14].x), "f"(v[14].y), "f"(v[15].x), "f"(v[15].y)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float2 (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x),
+                   "=f"(v[3].y)
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float2 (&v)[8])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y), "f"(v[4].x),
+        "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[8])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+          "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
+        : "r"(taddr)
+        : "memory");
+}
+// One warp allocates `cols` columns (power of two >= 32) for the CTA; every thread gets the base address.
+// Contains a __syncthreads().
+template <int COLS>
+__device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t *slot, int t)
+{
+    if ((t >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(slot)),
+                     "n"(COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *slot;
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free_cta(uint32_t base, int t)
+{
+    __syncthreads();
+    if ((t >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+// lane base of this thread's warp (bits 31:16 of a TMEM address)
+__device__ __forceinline__ uint32_t tmem_lane_base(int t) { return (uint32_t)(((t >> 5) & 3) * 32) << 16; }
+
+// ---------------------------------------------------------------------------------------------
 // The 4096-point sub-FFT of one input residue k2.
 //   * The stage-A twiddles W16384^{(4t+k2)*n0}, n0 = 1..15, are successive powers of ONE per-thread base
 //     b = W16384^{4t+k2}: a chain of packed complex multiplies instead of a 30 KiB shared-memory table
@@ -192,6 +263,86 @@ __device__ __forceinline__ void subfft4096_inv3(float2 (&x)[16], const int k2, c
     }
     __syncwarp();
     // ---- stage C: thread (n0, n1) = (t >> 4, t & 15) gathers c = 0..15
+    {
+        const float2 *src = tile + 17 * (t & 15);
+#pragma unroll
+        for (int c = 0; c < 16; c++) x[c] = src[c];
+    }
+    radix16_inv(x);
+}
+
+// Same sub-FFT with the stage-B twiddles W1024^{(4c+k2)*n1} held in tensor memory instead of shared memory:
+// each thread keeps its own 4 x 15 values (c = t & 15) in 4 x 32 columns at `tw_taddr` (filled once per
+// kernel by subfft3_park_twiddles).  Takes 30 of the 240 L1/shared wavefronts per warp and sub-FFT off the
+// busiest pipe of the search kernel at no arithmetic cost.
+struct FftSmem3T {
+    float2 *S1;  // [2][4096]
+    float2 *S2;  // [16 half-warps][16*17]
+};
+__host__ __device__ constexpr size_t fft_smem3t_bytes() { return sizeof(float2) * (size_t)(2 * kS1Elems + 16 * kS2TileElems); }
+__device__ __forceinline__ FftSmem3T fft_smem3t_carve(unsigned char *base)
+{
+    FftSmem3T s;
+    s.S1 = reinterpret_cast<float2 *>(base);
+    s.S2 = s.S1 + 2 * kS1Elems;
+    return s;
+}
+constexpr int kTwCols = 4 * 32;  // TMEM columns of one thread's stage-B twiddles
+
+// tables: global T2 [4][15][16]; writes this thread's values to TMEM columns [32*k2 + 2*(n1-1), +2)
+__device__ __forceinline__ void subfft3_park_twiddles(const float2 *__restrict__ tables, uint32_t tw_taddr, int t)
+{
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) {
+        float2 v[8];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int n1 = 8 * h + i + 1;
+                v[i] = (n1 < 16) ? __ldg(tables + (k2 * 15 + (n1 - 1)) * 16 + (t & 15)) : make_float2(0.0f, 0.0f);
+            }
+            tmem_st8(tw_taddr + 32 * k2 + 16 * h, v);
+        }
+    }
+    tmem_wait_st();
+}
+
+__device__ __forceinline__ void subfft4096_inv3t(float2 (&x)[16], const int k2, const float2 b, const int buf,
+                                                 const FftSmem3T &s, const int t, const uint32_t tw_taddr)
+{
+    radix16_inv(x);
+    {
+        float2 *dst = s.S1 + buf * kS1Elems + t;
+        float2 tw = b;
+        dst[0] = x[r16(0)];
+#pragma unroll
+        for (int n0 = 1; n0 < 16; n0++) {
+            dst[n0 * 256] = cmul(x[r16(n0)], tw);
+            if (n0 < 15) tw = cmul(tw, b);
+        }
+    }
+    float2 tw[8], tw2[8];
+    tmem_ld8(tw_taddr + 32 * k2, tw);        // n1 = 1..8, in flight across the barrier
+    tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15 (+ one unused)
+    __syncthreads();
+    {
+        const float2 *src = s.S1 + buf * kS1Elems + (t & ~15) * 16 + (t & 15);
+#pragma unroll
+        for (int bb = 0; bb < 16; bb++) x[bb] = src[16 * bb];
+    }
+    radix16_inv(x);
+    tmem_wait_ld();
+    float2 *tile = s.S2 + (t >> 4) * kS2TileElems;
+    {
+        float2 *dst = tile + (t & 15);  // element (n1, c) at n1*17 + c
+        dst[0] = x[r16(0)];
+#pragma unroll
+        for (int i = 0; i < 8; i++) dst[(i + 1) * 17] = cmul(x[r16(i + 1)], tw[i]);
+#pragma unroll
+        for (int i = 0; i < 7; i++) dst[(i + 9) * 17] = cmul(x[r16(i + 9)], tw2[i]);
+    }
+    __syncwarp();
     {
         const float2 *src = tile + 17 * (t & 15);
 #pragma unroll

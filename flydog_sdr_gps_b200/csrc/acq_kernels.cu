@@ -473,12 +473,15 @@ template <bool MULTI>
 __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const FftSmem3 s = fft_smem3_carve(smem);
-    float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes());
+    const FftSmem3T s = fft_smem3t_carve(smem);
+    float *red_f = reinterpret_cast<float *>(smem + fft_smem3t_bytes());
     int *red_i = reinterpret_cast<int *>(red_f + 16);
     const int t = threadIdx.x;
     constexpr int L = ACQ_LAGS_L1;
-    load_t2(s, p.tables, t);
+    // stage-B twiddles live in tensor memory: 128 columns per thread, warps w and w+4 share lanes
+    const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 32), t);
+    const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
+    subfft3_park_twiddles(p.tables, tw_taddr, t);
     const float2 *base = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
     int buf = 0;
 
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 #pragma unroll 1
             for (int k2 = 0; k2 < 4; k2++) {
                 load_products(x, p, ti, b, k2, t);
-                subfft4096_inv3(x, k2, __ldg(base + k2 * 256), buf, s, t);
+                subfft4096_inv3t(x, k2, __ldg(base + k2 * 256), buf, s, t, tw_taddr);
                 buf ^= 1;
                 if (k2 == 0) {
 #pragma unroll
@@ -525,6 +528,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         if (t == 0) store_cell(p, ti, tot, L);
         // red_f/red_i are next written after the 4 barriers of the following tile: no extra barrier.
     }
+    tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
 // Tensor memory (TMEM, 256 KB per SM) as thread-private scratch.  The E1B combine needs the outputs of three
@@ -534,28 +538,6 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 // tcgen05.st / tcgen05.ld (.32x32b: thread i of the warp <-> lane 32*(warp%4)+i, N consecutive columns <-> N
 // registers) move the parked values over the tensor-memory datapath instead.  Warps w and w+4 share lanes and
 // use disjoint column ranges; a CTA allocates 256 columns, so two CTAs fill the SM's 512.
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float2 (&v)[16])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-        "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y), "f"(v[4].x),
-        "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y), "f"(v[8].x), "f"(v[8].y),
-        "f"(v[9].x), "f"(v[9].y), "f"(v[10].x), "f"(v[10].y), "f"(v[11].x), "f"(v[11].y), "f"(v[12].x), "f"(v[12].y),
-        "f"(v[13].x), "f"(v[13].y), "f"(v[14].x), "f"(v[14].y), "f"(v[15].x), "f"(v[15].y)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float2 (&v)[4])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x),
-                   "=f"(v[3].y)
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 constexpr int kE1bTmemCols = 256;  // 2 warp sets x 96 columns, rounded up to a power of two
 
 __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
@@ -564,23 +546,12 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     const FftSmem3 s = fft_smem3_carve(smem);
     float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes());
     int *red_i = reinterpret_cast<int *>(red_f + 16);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(red_f + 32);
     const int t = threadIdx.x;
-    const int warp = t >> 5;
     constexpr int L = ACQ_LAGS_E1B;
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         (uint32_t)__cvta_generic_to_shared(tmem_slot)),
-                     "n"(kE1bTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    load_t2(s, p.tables, t);  // ends with __syncthreads()
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = tmem_alloc_cta<kE1bTmemCols>(reinterpret_cast<uint32_t *>(red_f + 32), t);
+    load_t2(s, p.tables, t);
     // this thread's scratch: lane 32*(warp%4) + (t%32), columns [96*(warp/4), +96): [k2][n2] complex
-    const uint32_t zaddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 96);
+    const uint32_t zaddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * 96);
     const float2 *base = p.tables + kT2Elems + t;
     int buf = 0;
 
@@ -631,9 +602,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
         const Peak tot = block_reduce_peak(best, red_f, red_i, t);
         if (t == 0) store_cell(p, ti, tot, L);
     }
-    __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kE1bTmemCols) : "memory");
+    tmem_free_cta<kE1bTmemCols>(tmem_base, t);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -783,7 +752,7 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static size_t search_l1_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
+static size_t search_l1_smem_bytes() { return fft_smem3t_bytes() + 64 * sizeof(float); }
 static size_t search_e1b_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
 static size_t search_e1b_cluster_smem_bytes() { return fft_smem3_bytes() + 2 * sizeof(float2) * kSub + 64 * sizeof(float); }
 static size_t fwd_smem_bytes() { return fft_smem3_bytes() + kZBytes; }
