@@ -469,21 +469,64 @@ __device__ __forceinline__ float cpower(float2 a)
     return sq.x + sq.y;  // re^2 + im^2   (search.cpp:487)
 }
 
+// Warp-level part of the peak reduction: shuffles, then lane 0 leaves the warp's partial in `slot`.
+__device__ __forceinline__ void warp_reduce_peak(Peak v, float *slot_f, int *slot_i, int t)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float p = __shfl_xor_sync(0xffffffffu, v.p, off);
+        const int n = __shfl_xor_sync(0xffffffffu, v.n, off);
+        const float s = __shfl_xor_sync(0xffffffffu, v.sum, off);
+        peak_merge(v, p, n, s);
+    }
+    const int w = t >> 5;
+    if ((t & 31) == 0) {
+        slot_f[w] = v.p;
+        slot_f[8 + w] = v.sum;
+        slot_i[w] = v.n;
+    }
+}
+
+// Merge of the eight warp partials (one thread), after a CTA barrier that follows warp_reduce_peak.
+__device__ __forceinline__ Peak merge_warp_peaks(const float *slot_f, const int *slot_i)
+{
+    Peak v;
+    v.p = slot_f[0];
+    v.n = slot_i[0];
+    v.sum = slot_f[8];
+#pragma unroll
+    for (int k = 1; k < 8; k++) peak_merge(v, slot_f[k], slot_i[k], slot_f[8 + k]);
+    return v;
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const FftSmem3T s = fft_smem3t_carve(smem);
-    float *red_f = reinterpret_cast<float *>(smem + fft_smem3t_bytes());
-    int *red_i = reinterpret_cast<int *>(red_f + 16);
+    float *red_f = reinterpret_cast<float *>(smem + fft_smem3t_bytes());  // [2 parities][16]
+    int *red_i = reinterpret_cast<int *>(red_f + 32);                      // [2 parities][8]
     const int t = threadIdx.x;
     constexpr int L = ACQ_LAGS_L1;
     // stage-B twiddles live in tensor memory: 128 columns per thread, warps w and w+4 share lanes
-    const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 32), t);
+    const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
     const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
     subfft3_park_twiddles(p.tables, tw_taddr, t);
     const float2 *base = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
     int buf = 0;
+    // The cross-warp merge of a tile's peak is deferred to the next tile: the warp partials are left in a
+    // parity slot and thread 0 merges them after the next tile's first sub-FFT barrier, so the reduction
+    // costs no CTA barrier of its own (it matters at K = 1, where a tile is only four sub-FFTs).
+    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
+    auto flush = [&](int q) {
+        const Peak tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
+        acq_cell c;
+        c.peak = tot.p;
+        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
+        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
+        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
+        p.cells[((size_t)pend_cap * p.n_slots + pend_slot) * p.n_dop + pend_d] = c;
+    };
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileIdx ti(p, tile);
@@ -496,6 +539,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                 load_products(x, p, ti, b, k2, t);
                 subfft4096_inv3t(x, k2, __ldg(base + k2 * 256), buf, s, t, tw_taddr);
                 buf ^= 1;
+                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
                 if (k2 == 0) {
 #pragma unroll
                     for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
@@ -505,7 +549,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                 }
             }
             if (MULTI) {
-                // block b was delayed by 16*b samples in the front end (k_hb2), so lag n lines up across blocks
+                // block b was delayed by 16*b samples in the front end (k_front_end), so lag n lines up across blocks
 #pragma unroll
                 for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
             }
@@ -524,10 +568,15 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                 best.sum += pw;
             }
         }
-        const Peak tot = block_reduce_peak(best, red_f, red_i, t);
-        if (t == 0) store_cell(p, ti, tot, L);
-        // red_f/red_i are next written after the 4 barriers of the following tile: no extra barrier.
+        // parity slot `par` was last read (flush) during the previous tile, before >= 3 CTA barriers
+        warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
+        pend_cap = ti.cap;
+        pend_slot = ti.slot;
+        pend_d = ti.d;
+        par ^= 1;
     }
+    __syncthreads();
+    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
