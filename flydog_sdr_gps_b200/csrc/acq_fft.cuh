@@ -351,4 +351,115 @@ __device__ __forceinline__ void subfft4096_inv3t(float2 (&x)[16], const int k2, 
     radix16_inv(x);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Operand-prefetching form of the sub-FFT (used by k_search_l1).
+//   * Both operands of the NEXT sub-FFT are staged by TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
+//     while the current one computes: the capture-spectrum residue D (32 KiB, contiguous in the polyphase
+//     layout) lands in the idle half of the double-buffered A->B exchange buffer, exactly where thread t later
+//     writes its own stage-A outputs (it reads D[256 a + t] and writes S1[256 n0 + t]: the same 16 slots, so the
+//     reuse is thread-private), and the code-spectrum run E (32 KiB + 16 B: the Doppler offset is only 8-byte
+//     aligned) lands in a buffer of its own.  The L2 round trip leaves the dependent chain of every warp.
+//   * The B->C tile of a half-warp lives in the S1 row that half-warp has just consumed (row n0 = 256
+//     elements, read by nobody else), XOR-swizzled so that both the column writes and the row reads are
+//     conflict-free: element (n1, c) sits at 16 n1 + (c ^ n1).  No separate tile buffer.
+// Shared memory per CTA: 2 x 32 KiB (S1) + 32 KiB + 16 B (E) + one mbarrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEBufElems = kSub + 2;
+struct FftSmem4 {
+    float2 *S1;  // [2][4096]
+    float2 *E;   // [4098]
+    unsigned long long *bar;
+};
+__host__ __device__ constexpr size_t fft_smem4_bytes() { return sizeof(float2) * (size_t)(2 * kS1Elems + kEBufElems) + 16; }
+__device__ __forceinline__ FftSmem4 fft_smem4_carve(unsigned char *base)
+{
+    FftSmem4 s;
+    s.S1 = reinterpret_cast<float2 *>(base);
+    s.E = s.S1 + 2 * kS1Elems;
+    s.bar = reinterpret_cast<unsigned long long *>(s.E + kEBufElems);
+    return s;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+//   in : x[a] = product for input element k = 1024*a + 4*t + k2;  b = W16384^{4t+k2};  S1b = this sub-FFT's half of S1
+//   post_barrier(): called by every thread right after the CTA barrier (thread 0 issues the next TMA there)
+//   out: x[r16(n2)] = stage-C output for lag lag_of3(t, n2), before the W64^{k2*n2} factor
+template <class PostBarrier>
+__device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, const float2 b, float2 *S1b, const int t,
+                                                const uint32_t tw_taddr, PostBarrier &&post_barrier)
+{
+    radix16_inv(x);
+    {
+        float2 *dst = S1b + t;
+        float2 tw = b;
+        dst[0] = x[r16(0)];
+#pragma unroll
+        for (int n0 = 1; n0 < 16; n0++) {
+            dst[n0 * 256] = cmul(x[r16(n0)], tw);
+            if (n0 < 15) tw = cmul(tw, b);
+        }
+    }
+    float2 tw[8], tw2[8];
+    tmem_ld8(tw_taddr + 32 * k2, tw);        // n1 = 1..8, in flight across the barrier
+    tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15 (+ one unused)
+    __syncthreads();
+    post_barrier();
+    float2 *row = S1b + (t & ~15) * 16;  // row n0 = t >> 4
+    const int c = t & 15;
+    {
+        const float2 *src = row + c;
+#pragma unroll
+        for (int bb = 0; bb < 16; bb++) x[bb] = src[16 * bb];
+    }
+    radix16_inv(x);
+    tmem_wait_ld();
+    __syncwarp();  // the half-warp has consumed its row: reuse it as the B->C tile
+    {
+        row[c] = x[r16(0)];  // (n1 = 0, c) at 0 + (c ^ 0)
+#pragma unroll
+        for (int i = 0; i < 8; i++) row[16 * (i + 1) + (c ^ (i + 1))] = cmul(x[r16(i + 1)], tw[i]);
+#pragma unroll
+        for (int i = 0; i < 7; i++) row[16 * (i + 9) + (c ^ (i + 9))] = cmul(x[r16(i + 9)], tw2[i]);
+    }
+    __syncwarp();
+    {
+        const float2 *src = row + 16 * c;  // this thread is now (n0, n1 = c)
+#pragma unroll
+        for (int cc = 0; cc < 16; cc++) x[cc] = src[cc ^ c];
+    }
+    radix16_inv(x);
+}
+
 }  // namespace acq

@@ -13,6 +13,8 @@
 // The half-band stages use explicit round-to-nearest mul/add in the reference's summation order
 // (no FMA contraction), so the FFT inputs are bit-identical to the reference's x86 build.
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "acq_fft.cuh"
 #include "acq_kernels.cuh"
@@ -500,7 +502,7 @@ __device__ __forceinline__ Peak merge_warp_peaks(const float *slot_f, const int 
 }
 
 template <bool MULTI>
-__global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
+__global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const FftSmem3T s = fft_smem3t_carve(smem);
@@ -569,6 +571,114 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
             }
         }
         // parity slot `par` was last read (flush) during the previous tile, before >= 3 CTA barriers
+        warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
+        pend_cap = ti.cap;
+        pend_slot = ti.slot;
+        pend_d = ti.d;
+        par ^= 1;
+    }
+    __syncthreads();
+    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
+    tmem_free_cta<2 * kTwCols>(tmem_base, t);
+}
+
+// k_search_l1: as k_search_l1_ldg, but both operands of a sub-FFT are staged in shared memory by TMA bulk copies
+// issued one sub-FFT ahead (see subfft4096_inv4): D into the idle half of the exchange buffer, E into its own
+// 32 KiB buffer; the B->C tiles live inside the exchange rows.  The L2 round trip (the LDG of the _ldg form sits
+// at the head of every warp's dependent chain) is off the critical path; 98.6 KiB of shared memory per CTA.
+template <bool MULTI>
+__global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const FftSmem4 s = fft_smem4_carve(smem);
+    float *red_f = reinterpret_cast<float *>(smem + fft_smem4_bytes());  // [2 parities][16]
+    int *red_i = reinterpret_cast<int *>(red_f + 32);                     // [2 parities][8]
+    const int t = threadIdx.x;
+    constexpr int L = ACQ_LAGS_L1;
+    const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
+    const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
+    subfft3_park_twiddles(p.tables, tw_taddr, t);
+    const float2 *base = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
+    const uint32_t bar = smem_u32(s.bar);
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    // thread 0: stage the operands of sub-FFT (tn, bn, k2n) -- D into S1 half `half`, E into the E buffer
+    auto issue = [&](const TileIdx &tn, int bn, int k2n, int half) {
+        const int r = (k2n - tn.dop) & 3;
+        const int q = (k2n - tn.dop - r) >> 2;
+        const float2 *Dk = p.Dp + ((size_t)((size_t)tn.cap * p.K + bn) * p.nvar + tn.v) * kN + k2n * kSub;
+        const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
+        fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
+        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
+        tma_load_1d(smem_u32(s.S1 + half * kS1Elems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+        tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+    };
+    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+    int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
+    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
+    auto flush = [&](int q) {
+        const Peak tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
+        acq_cell c;
+        c.peak = tot.p;
+        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
+        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
+        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
+        p.cells[((size_t)pend_cap * p.n_slots + pend_slot) * p.n_dop + pend_d] = c;
+    };
+
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileIdx ti(p, tile);
+        float P[MULTI ? 16 : 1];
+        float2 acc[16];
+        for (int b = 0; b < p.K; b++) {
+            float2 x[16];
+#pragma unroll 1
+            for (int k2 = 0; k2 < 4; k2++) {
+                float2 *S1b = s.S1 + (it & 1) * kS1Elems;
+                {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471), operands from smem
+                    const int r = (k2 - ti.dop) & 3;
+                    const int q = (k2 - ti.dop - r) >> 2;
+                    const float2 *Dk = S1b + t;
+                    const float2 *Ek = s.E + ((p.Q + q) & 1) + t;
+                    mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+                    for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], Ek[256 * a]);
+                }
+                subfft4096_inv4(x, k2, __ldg(base + k2 * 256), S1b, t, tw_taddr, [&]() {
+                    if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                        if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
+                        else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
+                        else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
+                    }
+                });
+                it++;
+                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
+                if (k2 == 0) {
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
+                } else {
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
+                }
+            }
+            if (MULTI) {
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
+            }
+        }
+        Peak best;
+        best.p = 0.0f;
+        best.n = 0x7fffffff;
+        best.sum = 0.0f;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) {
+            const int n = lag_of3(t, n2);
+            const float pw = MULTI ? P[n2] : cpower(acc[n2]);
+            if (n2 < 15 || n < L) {
+                if (pw > best.p) best.p = pw, best.n = n;
+                best.sum += pw;
+            }
+        }
         warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
         pend_cap = ti.cap;
         pend_slot = ti.slot;
@@ -801,7 +911,13 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static size_t search_l1_smem_bytes() { return fft_smem3t_bytes() + 64 * sizeof(float); }
+static size_t search_l1_ldg_smem_bytes() { return fft_smem3t_bytes() + 64 * sizeof(float); }
+static size_t search_l1_smem_bytes() { return fft_smem4_bytes() + 64 * sizeof(float); }
+static bool use_ldg_kernel()
+{
+    static const bool v = [] { const char *k = getenv("ACQ_L1_KERNEL"); return k && !strcmp(k, "ldg"); }();  // A/B runs
+    return v;
+}
 static size_t search_e1b_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
 static size_t search_e1b_cluster_smem_bytes() { return fft_smem3_bytes() + 2 * sizeof(float2) * kSub + 64 * sizeof(float); }
 static size_t fwd_smem_bytes() { return fft_smem3_bytes() + kZBytes; }
@@ -812,6 +928,9 @@ cudaError_t search_kernels_configure()
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    const int l1g = (int)search_l1_ldg_smem_bytes();
+    if ((e = cudaFuncSetAttribute(k_search_l1_ldg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1g))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1_ldg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1g))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
     const int ec = (int)search_e1b_cluster_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
@@ -880,7 +999,10 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st)
     const long long max_ctas = (long long)sm_count * 2;
     const int grid = (int)(a.n_tiles < max_ctas ? a.n_tiles : max_ctas);
     if (e1b) k_search_e1b<<<grid, 256, search_e1b_smem_bytes(), st>>>(a);
-    else if (a.K > 1) k_search_l1<true><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
+    else if (use_ldg_kernel()) {
+        if (a.K > 1) k_search_l1_ldg<true><<<grid, 256, search_l1_ldg_smem_bytes(), st>>>(a);
+        else k_search_l1_ldg<false><<<grid, 256, search_l1_ldg_smem_bytes(), st>>>(a);
+    } else if (a.K > 1) k_search_l1<true><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
     else k_search_l1<false><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
     return 1;
 }

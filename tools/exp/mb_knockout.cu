@@ -6,7 +6,7 @@
 #include "acq_fft.cuh"
 using namespace acq;
 
-enum { NO_LDG = 1, NO_S1 = 2, NO_BAR = 4, NO_S2 = 8, NO_TW = 16, NO_R16 = 32, NO_ACC = 64 };
+enum { NO_LDG = 1, NO_S1 = 2, NO_BAR = 4, NO_S2 = 8, NO_TW = 16, NO_R16 = 32, NO_ACC = 64, LDS_OPS = 128, LDS_D = 256 };
 
 template <int F>
 __device__ __forceinline__ void sub3(float2 (&x)[16], const int k2, const float2 b, const int buf, const FftSmem3 &s, const int t)
@@ -83,7 +83,16 @@ __global__ void __launch_bounds__(256, 2) k3(const float2 *Dp, const float2 *Ep,
                 const float2 *Dk = Dblk + k2 * kSub;
                 const float2 *Ek = Ep + (size_t)(sat * 4 + r) * ext_len + Q + q + t;
                 const float2 bw = __ldg(base + k2 * 256);
-                if (F & NO_LDG) {
+                if (F & LDS_OPS) {   // operands as if prefetched into shared memory (garbage data, same access pattern)
+                    const float2 *sD = s.S1 + (buf ^ 1) * kS1Elems + t;
+                    const float2 *sE = s.S1 + buf * kS1Elems + ((t + q) & 255);
+#pragma unroll
+                    for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(sD[256 * a], sE[256 * a]);
+                } else if (F & LDS_D) {
+                    const float2 *sD = s.S1 + (buf ^ 1) * kS1Elems + t;
+#pragma unroll
+                    for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(sD[256 * a], __ldg(Ek + 256 * a));
+                } else if (F & NO_LDG) {
 #pragma unroll
                     for (int a = 0; a < 16; a++) x[a] = make_float2(bw.x + a, bw.y - a);
                 } else {
@@ -151,6 +160,9 @@ int main()
 #define RUN(F, name) run<F>(name, dD, dE, dT, out, n_tiles, K, n_dop, ext_len, Q)
     RUN(0, "full");
     RUN(NO_LDG, "no LDG");
+    RUN(LDS_OPS, "operands from smem (LDS)");
+    RUN(LDS_D, "D from smem, E by LDG");
+    RUN(LDS_OPS | NO_BAR, "operands from smem, no barrier");
     RUN(NO_S1, "no S1 exchange");
     RUN(NO_S2, "no S2 exchange");
     RUN(NO_S1 | NO_S2, "no exchanges");
