@@ -34,19 +34,21 @@ def needs_build():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA/C++ source of the engine into one shared library. Returns its path."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA/C++ source of the engine into one shared library. Returns its path.
+    `defines` / `out` build an experiment variant next to the product library (A/B runs: ACQ_B200_LIB=<path>)."""
+    if out is None and not force and not needs_build():
         return LIB
+    lib = out or LIB
     srcs = [os.path.join(CSRC, f) for f in CU_SOURCES + CPP_SOURCES if os.path.exists(os.path.join(CSRC, f))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + srcs
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib + ".tmp"] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
-    os.replace(LIB + ".tmp", LIB)
+    os.replace(lib + ".tmp", lib)
     if verbose:
         print(res.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

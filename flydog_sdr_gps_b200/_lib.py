@@ -56,7 +56,9 @@ def load():
     """Load libacq_b200.so (building it first if sources are newer).  Raises if that is impossible."""
     global _lib
     if _lib is None:
-        path = _build.build() if _build.needs_build() else _build.LIB
+        path = os.environ.get("ACQ_B200_LIB")  # experiment variant of the same CUDA library (A/B runs)
+        if not path:
+            path = _build.build() if _build.needs_build() else _build.LIB
         if not os.path.exists(path):
             raise RuntimeError("libacq_b200.so is missing and could not be built; the engine has no CPU fallback")
         L = C.CDLL(path)

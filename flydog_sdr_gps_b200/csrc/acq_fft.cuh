@@ -355,27 +355,35 @@ __device__ __forceinline__ void subfft4096_inv3t(float2 (&x)[16], const int k2, 
 // Operand-prefetching form of the sub-FFT (used by k_search_l1).
 //   * Both operands of the NEXT sub-FFT are staged by TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
 //     while the current one computes: the capture-spectrum residue D (32 KiB, contiguous in the polyphase
-//     layout) lands in the idle half of the double-buffered A->B exchange buffer, exactly where thread t later
-//     writes its own stage-A outputs (it reads D[256 a + t] and writes S1[256 n0 + t]: the same 16 slots, so the
-//     reuse is thread-private), and the code-spectrum run E (32 KiB + 16 B: the Doppler offset is only 8-byte
-//     aligned) lands in a buffer of its own.  The L2 round trip leaves the dependent chain of every warp.
-//   * The B->C tile of a half-warp lives in the S1 row that half-warp has just consumed (row n0 = 256
-//     elements, read by nobody else), XOR-swizzled so that both the column writes and the row reads are
-//     conflict-free: element (n1, c) sits at 16 n1 + (c ^ n1).  No separate tile buffer.
-// Shared memory per CTA: 2 x 32 KiB (S1) + 32 KiB + 16 B (E) + one mbarrier.
+//     layout; one 2 KiB copy per exchange row) lands in the idle half of the double-buffered A->B exchange
+//     buffer, exactly where thread t later writes its own stage-A outputs (it reads D[256 a + t] from row a,
+//     column t and writes its output n0 to row n0, column t: the same 16 slots, so the reuse is
+//     thread-private), and the code-spectrum run E (32 KiB + 16 B: the Doppler offset is only 8-byte aligned)
+//     lands in a buffer of its own.  The L2 round trip leaves the dependent chain of every warp.
+//   * Exchange rows are padded to 272 elements (16 x 17): the B->C tile of a half-warp lives in the row that
+//     half-warp has just consumed (row n0, read by nobody else), element (n1, c) at 17 n1 + c -- conflict-free
+//     column writes and row reads with compile-time offsets, and no separate tile buffer.
+//   * TMEM column 30/31 of residue k2 (the unused sixteenth twiddle slot) carries the stage-A base
+//     W16384^{4t + (k2+1 mod 4)} of the NEXT sub-FFT, so it arrives with the stage-B twiddles.
+// Shared memory per CTA: 2 x 34 KiB (S1) + 32 KiB + 16 B (E) + one mbarrier.
 // ---------------------------------------------------------------------------------------------
 constexpr int kEBufElems = kSub + 2;
+#ifndef ACQ_PADDED_ROWS
+#define ACQ_PADDED_ROWS 0
+#endif
+constexpr int kRowElems = ACQ_PADDED_ROWS ? 16 * 17 : 256;  // exchange row (padded: B->C tile at 17 n1 + c; else XOR swizzle)
+constexpr int kS1pElems = 16 * kRowElems;     // one half of the padded exchange buffer
 struct FftSmem4 {
-    float2 *S1;  // [2][4096]
+    float2 *S1;  // [2][16][272]
     float2 *E;   // [4098]
     unsigned long long *bar;
 };
-__host__ __device__ constexpr size_t fft_smem4_bytes() { return sizeof(float2) * (size_t)(2 * kS1Elems + kEBufElems) + 16; }
+__host__ __device__ constexpr size_t fft_smem4_bytes() { return sizeof(float2) * (size_t)(2 * kS1pElems + kEBufElems) + 16; }
 __device__ __forceinline__ FftSmem4 fft_smem4_carve(unsigned char *base)
 {
     FftSmem4 s;
     s.S1 = reinterpret_cast<float2 *>(base);
-    s.E = s.S1 + 2 * kS1Elems;
+    s.E = s.S1 + 2 * kS1pElems;
     s.bar = reinterpret_cast<unsigned long long *>(s.E + kEBufElems);
     return s;
 }
@@ -413,11 +421,33 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-//   in : x[a] = product for input element k = 1024*a + 4*t + k2;  b = W16384^{4t+k2};  S1b = this sub-FFT's half of S1
-//   post_barrier(): called by every thread right after the CTA barrier (thread 0 issues the next TMA there)
+// Twiddle parking for subfft4096_inv4: as subfft3_park_twiddles, plus the next residue's stage-A base in the
+// sixteenth slot.  tables: T2 [4][15][16], then bases [4][256].
+__device__ __forceinline__ void subfft4_park_twiddles(const float2 *__restrict__ tables, uint32_t tw_taddr, int t)
+{
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) {
+        float2 v[8];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int n1 = 8 * h + i + 1;
+                v[i] = (n1 < 16) ? __ldg(tables + (k2 * 15 + (n1 - 1)) * 16 + (t & 15))
+                                 : __ldg(tables + kT2Elems + ((k2 + 1) & 3) * 256 + t);
+            }
+            tmem_st8(tw_taddr + 32 * k2 + 16 * h, v);
+        }
+    }
+    tmem_wait_st();
+}
+
+//   in : x[a] = product for input element k = 1024*a + 4*t + k2;  b = W16384^{4t+k2} (in/out: replaced by the
+//        next residue's base);  S1b = this sub-FFT's half of S1
+//   post_barrier(): called by every thread right after the CTA barrier (warp 0 issues the next TMA there)
 //   out: x[r16(n2)] = stage-C output for lag lag_of3(t, n2), before the W64^{k2*n2} factor
 template <class PostBarrier>
-__device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, const float2 b, float2 *S1b, const int t,
+__device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
                                                 const uint32_t tw_taddr, PostBarrier &&post_barrier)
 {
     radix16_inv(x);
@@ -427,16 +457,16 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, c
         dst[0] = x[r16(0)];
 #pragma unroll
         for (int n0 = 1; n0 < 16; n0++) {
-            dst[n0 * 256] = cmul(x[r16(n0)], tw);
+            dst[n0 * kRowElems] = cmul(x[r16(n0)], tw);
             if (n0 < 15) tw = cmul(tw, b);
         }
     }
     float2 tw[8], tw2[8];
     tmem_ld8(tw_taddr + 32 * k2, tw);        // n1 = 1..8, in flight across the barrier
-    tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15 (+ one unused)
+    tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15, then the next residue's stage-A base
     __syncthreads();
     post_barrier();
-    float2 *row = S1b + (t & ~15) * 16;  // row n0 = t >> 4
+    float2 *row = S1b + (t >> 4) * kRowElems;  // row n0 = t >> 4
     const int c = t & 15;
     {
         const float2 *src = row + c;
@@ -445,20 +475,43 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, c
     }
     radix16_inv(x);
     tmem_wait_ld();
-    __syncwarp();  // the half-warp has consumed its row: reuse it as the B->C tile
+    b = tw2[7];
+    __syncwarp();  // the half-warp has consumed its row: reuse it as the B->C tile, element (n1, c) at 17 n1 + c
+#if ACQ_PADDED_ROWS
     {
-        row[c] = x[r16(0)];  // (n1 = 0, c) at 0 + (c ^ 0)
+        float2 *dst = row + c;
+        dst[0] = x[r16(0)];
 #pragma unroll
-        for (int i = 0; i < 8; i++) row[16 * (i + 1) + (c ^ (i + 1))] = cmul(x[r16(i + 1)], tw[i]);
+        for (int i = 0; i < 8; i++) dst[(i + 1) * 17] = cmul(x[r16(i + 1)], tw[i]);
 #pragma unroll
-        for (int i = 0; i < 7; i++) row[16 * (i + 9) + (c ^ (i + 9))] = cmul(x[r16(i + 9)], tw2[i]);
+        for (int i = 0; i < 7; i++) dst[(i + 9) * 17] = cmul(x[r16(i + 9)], tw2[i]);
     }
     __syncwarp();
     {
-        const float2 *src = row + 16 * c;  // this thread is now (n0, n1 = c)
+        const float2 *src = row + 17 * c;  // this thread is now (n0, n1 = c)
 #pragma unroll
-        for (int cc = 0; cc < 16; cc++) x[cc] = src[cc ^ c];
+        for (int cc = 0; cc < 16; cc++) x[cc] = src[cc];
     }
+#else
+    {   // unpadded row: element (n1, c) at 16 n1 + (c ^ n1); on byte addresses (row is 128-byte aligned) the XOR
+        // touches bits 3..6 only: address = ((row + 8 c) ^ (8 n1)) + 128 n1
+        const uint32_t wb = smem_u32(row + c);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wb), "f"(x[r16(0)].x), "f"(x[r16(0)].y) : "memory");
+#pragma unroll
+        for (int i = 0; i < 15; i++) {
+            const int n1 = i + 1;
+            const float2 v = cmul(x[r16(n1)], i < 8 ? tw[i] : tw2[i - 8]);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
+        }
+    }
+    __syncwarp();
+    {   // this thread is now (n0, n1 = c): element (c, cc) at 16 c + (cc ^ c) -> ((row + 136 c) ^ (8 cc))
+        const uint32_t rb = smem_u32(row + 17 * c);
+#pragma unroll
+        for (int cc = 0; cc < 16; cc++)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x[cc].x), "=f"(x[cc].y) : "r"(rb ^ (8u * cc)) : "memory");
+    }
+#endif
     radix16_inv(x);
 }
 

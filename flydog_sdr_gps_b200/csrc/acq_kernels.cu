@@ -586,6 +586,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
 // issued one sub-FFT ahead (see subfft4096_inv4): D into the idle half of the exchange buffer, E into its own
 // 32 KiB buffer; the B->C tiles live inside the exchange rows.  The L2 round trip (the LDG of the _ldg form sits
 // at the head of every warp's dependent chain) is off the critical path; 98.6 KiB of shared memory per CTA.
+constexpr int kIssueLanes = ACQ_PADDED_ROWS ? 16 : 1;  // threads of warp 0 that issue the operand copies
+
 template <bool MULTI>
 __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 {
@@ -597,23 +599,31 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     constexpr int L = ACQ_LAGS_L1;
     const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
     const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
-    subfft3_park_twiddles(p.tables, tw_taddr, t);
-    const float2 *base = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
+    subfft4_park_twiddles(p.tables, tw_taddr, t);
+    float2 bw = __ldg(p.tables + kT2Elems + t);  // W16384^{4t}: base of residue 0; later bases come from TMEM
     const uint32_t bar = smem_u32(s.bar);
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
-    // thread 0: stage the operands of sub-FFT (tn, bn, k2n) -- D into S1 half `half`, E into the E buffer
+    // lanes 0..15 of warp 0: stage the operands of sub-FFT (tn, bn, k2n) -- D row by row into S1 half `half`,
+    // E into the E buffer (lane 0)
     auto issue = [&](const TileIdx &tn, int bn, int k2n, int half) {
         const int r = (k2n - tn.dop) & 3;
         const int q = (k2n - tn.dop - r) >> 2;
         const float2 *Dk = p.Dp + ((size_t)((size_t)tn.cap * p.K + bn) * p.nvar + tn.v) * kN + k2n * kSub;
         const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
         fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
-        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
-        tma_load_1d(smem_u32(s.S1 + half * kS1Elems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
-        tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+        if (t == 0) {
+            mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
+            tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+        }
+#if ACQ_PADDED_ROWS
+        __syncwarp(0xffffu);
+        tma_load_1d(smem_u32(s.S1 + half * kS1pElems + t * kRowElems), Dk + 256 * t, (uint32_t)(sizeof(float2) * 256), bar);
+#else
+        if (t == 0) tma_load_1d(smem_u32(s.S1 + half * kS1pElems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+#endif
     };
-    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+    if (t < kIssueLanes && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
     auto flush = [&](int q) {
@@ -634,7 +644,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
             float2 x[16];
 #pragma unroll 1
             for (int k2 = 0; k2 < 4; k2++) {
-                float2 *S1b = s.S1 + (it & 1) * kS1Elems;
+                float2 *S1b = s.S1 + (it & 1) * kS1pElems;
                 {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471), operands from smem
                     const int r = (k2 - ti.dop) & 3;
                     const int q = (k2 - ti.dop - r) >> 2;
@@ -642,10 +652,10 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                     const float2 *Ek = s.E + ((p.Q + q) & 1) + t;
                     mbar_wait(bar, (uint32_t)(it & 1));
 #pragma unroll
-                    for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], Ek[256 * a]);
+                    for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
                 }
-                subfft4096_inv4(x, k2, __ldg(base + k2 * 256), S1b, t, tw_taddr, [&]() {
-                    if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                subfft4096_inv4(x, k2, bw, S1b, t, tw_taddr, [&]() {
+                    if (t < kIssueLanes) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
                         if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
                         else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
                         else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
