@@ -87,6 +87,9 @@ __device__ __forceinline__ void radix4_inv(float2 &a, float2 &b, float2 &c, floa
 // Input x[a] in natural order.  Output X[n] is left at register index  r16(n) = (n >> 2) | ((n & 3) << 2).
 __host__ __device__ constexpr int r16(int n) { return (n >> 2) | ((n & 3) << 2); }
 
+#ifndef ACQ_R16_FUSED
+#define ACQ_R16_FUSED 1
+#endif
 __device__ __forceinline__ void radix16_inv(float2 (&x)[16])
 {
     constexpr float C1 = 0.92387953251128675613f;  // cos(pi/8)
@@ -95,6 +98,41 @@ __device__ __forceinline__ void radix16_inv(float2 (&x)[16])
     // layer 1: for each a0, radix-4 over a = a0 + 4*a1  ->  u[a0][nl] at index a0 + 4*nl
 #pragma unroll
     for (int a0 = 0; a0 < 4; a0++) radix4_inv(x[a0], x[a0 + 4], x[a0 + 8], x[a0 + 12]);
+#if ACQ_R16_FUSED
+    // Twiddles u[a0][nl] *= W16^{a0*nl} folded into layer 2 where they are (+-1 +- j)/sqrt2: the 1/sqrt2 rides
+    // on the fused multiply-add of the following butterfly (4 packed instructions fewer than twiddle-then-add).
+    // nl = 0: no twiddles
+    radix4_inv(x[0], x[1], x[2], x[3]);
+    {   // nl = 1: b = x5 W^1, c = x6 W^2 = R2 (x6 + j x6), d = x7 W^3
+        const float2 s6 = cadd(x[6], jmul(x[6]));
+        const float2 b = cmul(x[5], make_float2(C1, S1)), d = cmul(x[7], make_float2(S1, C1));
+        const float2 apc = __ffma2_rn(s6, bc(R2), x[4]), amc = __ffma2_rn(s6, bc(-R2), x[4]);
+        const float2 bpd = cadd(b, d), bmd = csub(b, d);
+        x[4] = cadd(apc, bpd);
+        x[5] = cadd_jb(amc, bmd);
+        x[6] = csub(apc, bpd);
+        x[7] = csub_jb(amc, bmd);
+    }
+    {   // nl = 2: b = x9 W^2 = R2 (x9 + j x9), c = j x10, d = x11 W^6 = R2 (j x11 - x11)
+        const float2 s9 = cadd(x[9], jmul(x[9])), s11 = csub(jmul(x[11]), x[11]);
+        const float2 apc = cadd_jb(x[8], x[10]), amc = csub_jb(x[8], x[10]);
+        const float2 bpd = cadd(s9, s11), bmd = csub(s9, s11);  // both still to be scaled by R2
+        x[8] = __ffma2_rn(bpd, bc(R2), apc);
+        x[9] = __ffma2_rn(jmul(bmd), bc(R2), amc);
+        x[10] = __ffma2_rn(bpd, bc(-R2), apc);
+        x[11] = __ffma2_rn(jmul(bmd), bc(-R2), amc);
+    }
+    {   // nl = 3: b = x13 W^3, c = x14 W^6 = R2 (j x14 - x14), d = x15 W^9
+        const float2 s14 = csub(jmul(x[14]), x[14]);
+        const float2 b = cmul(x[13], make_float2(S1, C1)), d = cmul(x[15], make_float2(-C1, -S1));
+        const float2 apc = __ffma2_rn(s14, bc(R2), x[12]), amc = __ffma2_rn(s14, bc(-R2), x[12]);
+        const float2 bpd = cadd(b, d), bmd = csub(b, d);
+        x[12] = cadd(apc, bpd);
+        x[13] = cadd_jb(amc, bmd);
+        x[14] = csub(apc, bpd);
+        x[15] = csub_jb(amc, bmd);
+    }
+#else
     // twiddle u[a0][nl] *= W16^{a0*nl}
     x[5] = cmul(x[5], make_float2(C1, S1));                           // W16^1
     x[9] = __fmul2_rn(cadd(x[9], jmul(x[9])), bc(R2));               // W16^2 = (1+j)/sqrt2
@@ -108,6 +146,7 @@ __device__ __forceinline__ void radix16_inv(float2 (&x)[16])
     // layer 2: for each nl, radix-4 over a0  ->  X[nl + 4*nh] at index nh + 4*nl
 #pragma unroll
     for (int nl = 0; nl < 4; nl++) radix4_inv(x[4 * nl], x[4 * nl + 1], x[4 * nl + 2], x[4 * nl + 3]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
