@@ -554,4 +554,80 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
     radix16_inv(x);
 }
 
+// Form of subfft4096_inv4 for kernels whose tensor memory is taken by parked data (k_search_e1b: 96 of a thread's
+// 128 columns hold three residues): the stage-B twiddles W1024^{(4c+k2)*n1} come from a 7.5 KiB shared-memory
+// table T2s (read before the barrier / during stage B, broadcast between the two half-warps), the stage-A base
+// of the next residue from two TMEM columns at base_taddr + 2*((k2+1)&3).  Operand staging, exchange rows and
+// the B->C swizzle are those of subfft4096_inv4.
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float2 &v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, const float2 v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+template <class PostBarrier>
+__device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
+                                                 const float2 *T2s, const uint32_t base_taddr, PostBarrier &&post_barrier)
+{
+    radix16_inv(x);
+    {
+        float2 *dst = S1b + t;
+        float2 tw = b;
+        dst[0] = x[r16(0)];
+#pragma unroll
+        for (int n0 = 1; n0 < 16; n0++) {
+            dst[n0 * 256] = cmul(x[r16(n0)], tw);
+            if (n0 < 15) tw = cmul(tw, b);
+        }
+    }
+    float2 tw[8];
+    const float2 *twp = T2s + k2 * (15 * 16) + (t & 15);
+#pragma unroll
+    for (int i = 0; i < 8; i++) tw[i] = twp[i * 16];  // n1 = 1..8
+    float2 bn;
+    tmem_ld1(base_taddr + 2 * ((k2 + 1) & 3), bn);
+    __syncthreads();
+    post_barrier();
+    float2 *row = S1b + (t >> 4) * 256;  // row n0 = t >> 4
+    const int c = t & 15;
+    {
+        const float2 *src = row + c;
+#pragma unroll
+        for (int bb = 0; bb < 16; bb++) x[bb] = src[16 * bb];
+    }
+    radix16_inv(x);
+    tmem_wait_ld();
+    b = bn;
+    __syncwarp();  // the half-warp has consumed its row: reuse it as the B->C tile, element (n1, c) at 16 n1 + (c ^ n1)
+    {
+        const uint32_t wb = smem_u32(row + c);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wb), "f"(x[r16(0)].x), "f"(x[r16(0)].y) : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int n1 = i + 1;
+            const float2 v = cmul(x[r16(n1)], tw[i]);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < 7; i++) tw[i] = twp[(i + 8) * 16];  // n1 = 9..15
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            const int n1 = i + 9;
+            const float2 v = cmul(x[r16(n1)], tw[i]);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
+        }
+    }
+    __syncwarp();
+    {
+        const uint32_t rb = smem_u32(row + 17 * c);
+#pragma unroll
+        for (int cc = 0; cc < 16; cc++)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x[cc].x), "=f"(x[cc].y) : "r"(rb ^ (8u * cc)) : "memory");
+    }
+    radix16_inv(x);
+}
+
 }  // namespace acq

@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 // use disjoint column ranges; a CTA allocates 256 columns, so two CTAs fill the SM's 512.
 constexpr int kE1bTmemCols = 256;  // 2 warp sets x 96 columns, rounded up to a power of two
 
-__global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
+__global__ void __launch_bounds__(256, 2) k_search_e1b_ldg(const SearchArgs p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const FftSmem3 s = fft_smem3_carve(smem);
@@ -771,6 +771,155 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
         const Peak tot = block_reduce_peak(best, red_f, red_i, t);
         if (t == 0) store_cell(p, ti, tot, L);
     }
+    tmem_free_cta<kE1bTmemCols>(tmem_base, t);
+}
+
+// k_search_e1b: as k_search_e1b_ldg, with the operand staging of k_search_l1 -- both operands of a sub-FFT land in
+// shared memory by TMA bulk copies issued one sub-FFT ahead (D into the idle half of the exchange buffer, E into
+// its own buffer), the B->C tiles live inside the exchange rows, and the cross-warp peak merge is deferred to the
+// next tile (no reduction barrier).  A thread's 128 TMEM columns hold the three parked residues (96) and the four
+// stage-A bases (8), so the stage-B twiddles stay in a 7.5 KiB shared-memory table.  106 KiB of shared memory per
+// CTA, two CTAs per SM.
+constexpr int kE1bBaseCol = 96;  // TMEM columns [96, 104): W16384^{4t+k2}, k2 = 0..3
+struct E1bSmem {
+    float2 *S1;  // [2][4096]
+    float2 *E;   // [4098]
+    unsigned long long *bar;
+    float2 *T2;  // [4][15][16]
+    float *red_f;
+    int *red_i;
+};
+__host__ __device__ constexpr size_t e1b_smem_bytes()
+{
+    return sizeof(float2) * (size_t)(2 * kSub + kEBufElems) + 16 + sizeof(float2) * kT2Elems + 64 * sizeof(float);
+}
+__device__ __forceinline__ E1bSmem e1b_smem_carve(unsigned char *base)
+{
+    E1bSmem s;
+    s.S1 = reinterpret_cast<float2 *>(base);
+    s.E = s.S1 + 2 * kSub;
+    s.bar = reinterpret_cast<unsigned long long *>(s.E + kEBufElems);
+    s.T2 = reinterpret_cast<float2 *>(s.bar + 2);
+    s.red_f = reinterpret_cast<float *>(s.T2 + kT2Elems);  // [2 parities][16], then the TMEM slot at [48]
+    s.red_i = reinterpret_cast<int *>(s.red_f + 32);        // [2 parities][8]
+    return s;
+}
+
+__global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const E1bSmem s = e1b_smem_carve(smem);
+    float *red_f = s.red_f;
+    int *red_i = s.red_i;
+    const int t = threadIdx.x;
+    constexpr int L = ACQ_LAGS_E1B;
+    const uint32_t tmem_base = tmem_alloc_cta<kE1bTmemCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
+    {   // stage-B twiddle table into shared memory
+        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
+        float4 *dst = reinterpret_cast<float4 *>(s.T2);
+        for (int i = t; i < kT2Elems / 2; i += 256) dst[i] = __ldg(src + i);
+    }
+    // this thread's TMEM: lane 32*(warp%4) + (t%32), columns [128*(warp/4), +128): [k2][n2] parked, then the bases
+    const uint32_t zaddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * 128);
+    float2 bw = __ldg(p.tables + kT2Elems + t);  // W16384^{4t}: base of residue 0
+    tmem_st1(zaddr + kE1bBaseCol, bw);
+#pragma unroll
+    for (int k2 = 1; k2 < 4; k2++) tmem_st1(zaddr + kE1bBaseCol + 2 * k2, __ldg(p.tables + kT2Elems + k2 * 256 + t));
+    tmem_wait_st();
+    const uint32_t bar = smem_u32(s.bar);
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    auto issue = [&](const TileIdx &tn, int k2n, int half) {  // thread 0: stage the operands of sub-FFT (tn, k2n)
+        const int r = (k2n - tn.dop) & 3;
+        const int q = (k2n - tn.dop - r) >> 2;
+        const float2 *Dk = p.Dp + ((size_t)((size_t)tn.cap * p.K) * p.nvar + tn.v) * kN + k2n * kSub;
+        const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
+        fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
+        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
+        tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+        tma_load_1d(smem_u32(s.S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+    };
+    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0);
+    int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
+    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
+    auto flush = [&](int q) {
+        const Peak tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
+        acq_cell c;
+        c.peak = tot.p;
+        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
+        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
+        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
+        p.cells[((size_t)pend_cap * p.n_slots + pend_slot) * p.n_dop + pend_d] = c;
+    };
+
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileIdx ti(p, tile);
+        float2 x[16];
+#pragma unroll 1
+        for (int k2 = 0; k2 < 4; k2++) {
+            float2 *S1b = s.S1 + (it & 1) * kSub;
+            {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471), operands from smem
+                const int r = (k2 - ti.dop) & 3;
+                const int q = (k2 - ti.dop - r) >> 2;
+                const float2 *Dk = S1b + t;
+                const float2 *Ek = s.E + ((p.Q + q) & 1) + t;
+                mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+                for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], Ek[256 * a]);
+            }
+            subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, zaddr + kE1bBaseCol, [&]() {
+                if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                    if (k2 < 3) issue(ti, k2 + 1, (it + 1) & 1);
+                    else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, (it + 1) & 1);
+                }
+            });
+            it++;
+            if (t == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
+            if (k2 < 3) {
+                float2 z[16];
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) z[n2] = (k2 == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[k2][n2]);
+                tmem_st16(zaddr + 32 * k2, z);
+                tmem_wait_st();
+            }
+        }
+        // radix-4 combine over k2, lags n = lag_of3(t, n2) + 4096 m < 16368.  Lags are not visited in
+        // increasing order here, so ties compare the index explicitly (first index wins, search.cpp:488).
+        Peak best;
+        best.p = 0.0f;
+        best.n = 0x7fffffff;
+        best.sum = 0.0f;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+            float2 za[4], zb[4], zc[4];
+            tmem_ld4(zaddr + 0 * 32 + 8 * c4, za);
+            tmem_ld4(zaddr + 1 * 32 + 8 * c4, zb);
+            tmem_ld4(zaddr + 2 * 32 + 8 * c4, zc);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int n2 = 4 * c4 + i;
+                float2 z0 = za[i], z1 = zb[i], z2 = zc[i];
+                float2 z3 = cmul(x[r16(n2)], c_cC[3][n2]);
+                radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
+                const float2 zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const int n = lag_of3(t, n2) + 4096 * m;
+                    const float pw = cpower(zz[m]);
+                    if (n < L) peak_merge(best, pw, n, pw);
+                }
+            }
+        }
+        // parity slot `par` was last read (flush) during the previous tile, before >= 3 CTA barriers
+        warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
+        pend_cap = ti.cap;
+        pend_slot = ti.slot;
+        pend_d = ti.d;
+        par ^= 1;
+    }
+    __syncthreads();
+    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);
 }
 
@@ -928,7 +1077,13 @@ static bool use_ldg_kernel()
     static const bool v = [] { const char *k = getenv("ACQ_L1_KERNEL"); return k && !strcmp(k, "ldg"); }();  // A/B runs
     return v;
 }
-static size_t search_e1b_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
+static size_t search_e1b_ldg_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
+static size_t search_e1b_smem_bytes() { return e1b_smem_bytes(); }
+static bool use_e1b_ldg_kernel()
+{
+    const char *k = getenv("ACQ_E1B_CTA_KERNEL");  // A/B runs and the kernel-equivalence test
+    return k && !strcmp(k, "ldg");
+}
 static size_t search_e1b_cluster_smem_bytes() { return fft_smem3_bytes() + 2 * sizeof(float2) * kSub + 64 * sizeof(float); }
 static size_t fwd_smem_bytes() { return fft_smem3_bytes() + kZBytes; }
 
@@ -942,6 +1097,8 @@ cudaError_t search_kernels_configure()
     if ((e = cudaFuncSetAttribute(k_search_l1_ldg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1g))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1_ldg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1g))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
+    const int e1g = (int)search_e1b_ldg_smem_bytes();
+    if ((e = cudaFuncSetAttribute(k_search_e1b_ldg, cudaFuncAttributeMaxDynamicSharedMemorySize, e1g))) return e;
     const int ec = (int)search_e1b_cluster_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
@@ -1008,7 +1165,10 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st)
     if (a.n_tiles <= 0) return 0;
     const long long max_ctas = (long long)sm_count * 2;
     const int grid = (int)(a.n_tiles < max_ctas ? a.n_tiles : max_ctas);
-    if (e1b) k_search_e1b<<<grid, 256, search_e1b_smem_bytes(), st>>>(a);
+    if (e1b) {
+        if (use_e1b_ldg_kernel()) k_search_e1b_ldg<<<grid, 256, search_e1b_ldg_smem_bytes(), st>>>(a);
+        else k_search_e1b<<<grid, 256, search_e1b_smem_bytes(), st>>>(a);
+    }
     else if (use_ldg_kernel()) {
         if (a.K > 1) k_search_l1_ldg<true><<<grid, 256, search_l1_ldg_smem_bytes(), st>>>(a);
         else k_search_l1_ldg<false><<<grid, 256, search_l1_ldg_smem_bytes(), st>>>(a);

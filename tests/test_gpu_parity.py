@@ -370,6 +370,28 @@ def test_e1b_cluster_kernel_equals_single_cta_kernel(gpu_required, oracle, monke
     assert {int(r["sat"]) for r in rb[0] if r["snr"] >= 16} >= {1, 7, 11}
 
 
+def test_e1b_tma_staged_kernel_equals_ldg_kernel(gpu_required, oracle, monkeypatch):
+    """The operand-staging E1B kernel (TMA bulk copies one sub-FFT ahead, deferred peak merge) against the earlier
+    load-from-L2 form: the arithmetic is the same instruction for instruction, so the whole grid is bitwise equal.
+    More tiles than resident CTAs, so the deferred merge and the cross-tile prefetch are exercised."""
+    table = scenarios.table("cfg3")[:9]
+    kw = scenarios.params_kw("cfg3")
+    cap = synth.make_capture(37, 1, table, [(0, 12345, 17 * F.BIN_HZ, 47, 0.4), (8, 64000, -39 * F.BIN_HZ, 46, 1.4)])
+    out = {}
+    for kind in ("tma", "ldg"):
+        monkeypatch.setenv("ACQ_E1B_KERNEL", "cta")
+        monkeypatch.setenv("ACQ_E1B_CTA_KERNEL", kind)
+        with F.AcqEngine(table, F.default_params(**kw)) as eng:
+            out[kind] = eng.search(cap, want_grid=True)
+    (ra, ga), (rb, gb) = out["tma"], out["ldg"]
+    for f in ("peak", "lag", "noise", "snr"):
+        assert np.array_equal(ga[f], gb[f]), f
+    assert np.array_equal(ra, rb)
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
+    compare_records(ra[0], orec, ogrid, kw["dop_lo"], 16.0, ggrid=ga[0], max_ties=1)
+    assert {int(r["sat"]) for r in ra[0] if r["snr"] >= 16} >= {0, 8}
+
+
 def test_e1b_noncoherent_blocks(gpu_required, oracle):
     """Galileo E1B with K = 4 non-coherent blocks and half-bin Doppler (cluster kernel, block powers summed in
     registers per lag quarter) against the oracle's extension of search.cpp."""
