@@ -285,29 +285,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng.set_profiling(True)
     for _ in range(args.warmup):
         step_device()
     barrier()
 
-    # ---- device-resident timing: K steps, L2 flushed between steps (flush outside the event pairs)
+    # ---- device-resident timing: K steps of the product path, L2 flushed between steps (flush outside the
+    # event pairs).  No events between the kernels here: the four launches of a step are chained by
+    # programmatic dependent launch, which an event record in between would switch off.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms = []
     barrier()
     for a, b in evs:
         flush.fill_(1)
         a.record()
         step_device()
         b.record()
-        kern_ms.append(None)
-        kern_ms[-1] = eng.kernel_ms()  # waits for this step (the flush of the next step is not timed anyway)
     barrier()
     launches = eng.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- the same K steps once more with CUDA events between the kernels (on the launching stream): per-kernel
+    # durations for the roofline.  Still inside the clock-sampling window.
+    eng.set_profiling(True)
+    step_device()
+    barrier()
+    kern_ms = []
+    evs_p = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs_p:
+        flush.fill_(1)
+        a.record()
+        step_device()
+        b.record()
+        kern_ms.append(eng.kernel_ms())  # waits for this step (the flush of the next step is not timed anyway)
+    barrier()
+    eng.set_profiling(False)
+    prof_ms = sum(a.elapsed_time(b) for a, b in evs_p) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -399,6 +413,9 @@ def main():
                 "api": "acq_search (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches),
         "kernel_ms": {k: statistics.mean(x[k] for x in kern_ms) for k in kern_ms[0]},
+        "kernel_ms_pass": {"what": "second pass of the same K steps with CUDA events between the kernels "
+                                   "(which disables programmatic dependent launch between them)",
+                           "ms_per_step": prof_ms},
         "device_equals_host_path": same,
         "clocks": clocks,
         "roofline": roofline,

@@ -98,6 +98,7 @@ struct acq_engine {
     bool profiling = false, prof_valid = false;
     cudaEvent_t prof[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
+    int pdl = -1;        // programmatic dependent launch between the kernels of a search: -1 = by size, ACQ_PDL=0|1 forces
     int e1b_kernel = 0;  // 0 = by tile count, 1 = one CTA per tile, 2 = cluster of four CTAs per tile (ACQ_E1B_KERNEL)
     // persistent device data
     float2 *d_tables = nullptr, *d_rot = nullptr, *d_C = nullptr, *d_Ep = nullptr;
@@ -235,10 +236,16 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const int K = e->prm.k_noncoh;
     const int blocks = n_captures * K;
     const bool prof = e->profiling;
+    // Programmatic dependent launch between the kernels of a search: a gain where the search is a few waves of tiles
+    // (single captures: 85 -> 77 us for the reference's 32-PRN cold start), a measured 3 % loss on long searches
+    // (the search CTAs are placed while the forward FFT still holds SMs), so by default only up to 64 tiles per SM.
+    // Event records between the kernels (profiling) would serialise them anyway.
+    const long long tiles_total = (long long)n_captures * e->n_slots * e->n_dop * K;
+    const bool pdl = !prof && (e->pdl == 1 || (e->pdl < 0 && tiles_total <= 64LL * e->sm_count));
     if (prof) CU(cudaEventRecord(e->prof[0], st));
     e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, st);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
-    e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar, true, e->sm_count, st);
+    e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar, true, e->sm_count, st, pdl);
     if (prof) CU(cudaEventRecord(e->prof[2], st));
     SearchArgs a{};
     a.Dp = e->d_Dp;
@@ -257,7 +264,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         a.work = e->d_work;
         a.n_work = e->n_l1;
         a.n_tiles = (long long)n_captures * e->n_l1 * e->n_dop;
-        e->launches += launch_search(a, false, e->sm_count, st);
+        e->launches += launch_search(a, false, e->sm_count, st, pdl);
     }
     if (e->n_e1b > 0) {
         a.work = e->d_work + e->n_l1;
@@ -268,12 +275,12 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         // (its threads keep the block powers of their 16 lags in registers).  With more tiles than that the
         // one-CTA-per-tile form has 2.9x the throughput (profiles/r1_e1b_cluster_ab.json).
         const bool use_cluster = K > 1 || e->e1b_kernel == 2 || (e->e1b_kernel == 0 && a.n_tiles <= e->sm_count / 4);
-        if (use_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st);
-        else e->launches += launch_search(a, true, e->sm_count, st);
+        if (use_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st, pdl);
+        else e->launches += launch_search(a, true, e->sm_count, st, pdl);
     }
     if (prof) CU(cudaEventRecord(e->prof[3], st));
     e->launches += launch_best_dop(e->d_cells, e->d_slot_sat, out_dev, n_captures, e->n_slots, e->n_dop,
-                                   e->prm.dop_lo, st);
+                                   e->prm.dop_lo, st, pdl);
     if (prof) {
         CU(cudaEventRecord(e->prof[4], st));
         e->prof_valid = true;
@@ -400,6 +407,7 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
         }                                                                                           \
     } while (0)
 
+    if (const char *kv = getenv("ACQ_PDL")) e->pdl = strcmp(kv, "0") != 0 ? 1 : 0;
     if (const char *kv = getenv("ACQ_E1B_KERNEL")) e->e1b_kernel = !strcmp(kv, "cta") ? 1 : !strcmp(kv, "cluster") ? 2 : 0;
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUE(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));

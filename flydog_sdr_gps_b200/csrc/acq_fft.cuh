@@ -427,6 +427,26 @@ __device__ __forceinline__ FftSmem4 fft_smem4_carve(unsigned char *base)
     return s;
 }
 
+// Programmatic dependent launch (PDL): the kernels of one search are launched back to back with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs become resident and run their prologue
+// (tensor-memory allocation, twiddle parking, barrier init -- nothing that reads or writes search data) while its
+// predecessor drains.  pdl_wait() returns once every prerequisite grid has completed and its writes are visible;
+// every thread of every kernel in the chain calls it before touching search data, so completion is transitive.
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// experiment switches (tools/build_variants.py): drop the trigger of one kernel class
+#ifdef ACQ_PDL_NO_TRIGGER_SEARCH
+__device__ __forceinline__ void pdl_trigger_search() {}
+#else
+__device__ __forceinline__ void pdl_trigger_search() { pdl_launch_dependents(); }
+#endif
+#ifdef ACQ_PDL_NO_TRIGGER_FFT
+__device__ __forceinline__ void pdl_trigger_fft() {}
+#else
+__device__ __forceinline__ void pdl_trigger_fft() { pdl_launch_dependents(); }
+#endif
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -583,10 +603,13 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
             if (n0 < 15) tw = cmul(tw, b);
         }
     }
-    float2 tw[8];
+#ifndef ACQ_E1B_TW15
+#define ACQ_E1B_TW15 0
+#endif
+    float2 tw[ACQ_E1B_TW15 ? 15 : 8];
     const float2 *twp = T2s + k2 * (15 * 16) + (t & 15);
 #pragma unroll
-    for (int i = 0; i < 8; i++) tw[i] = twp[i * 16];  // n1 = 1..8
+    for (int i = 0; i < (ACQ_E1B_TW15 ? 15 : 8); i++) tw[i] = twp[i * 16];  // n1 = 1..8 (or all 15)
     float2 bn;
     tmem_ld1(base_taddr + 2 * ((k2 + 1) & 3), bn);
     __syncthreads();
@@ -611,12 +634,14 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
             const float2 v = cmul(x[r16(n1)], tw[i]);
             asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
         }
+#if !ACQ_E1B_TW15
 #pragma unroll
         for (int i = 0; i < 7; i++) tw[i] = twp[(i + 8) * 16];  // n1 = 9..15
+#endif
 #pragma unroll
         for (int i = 0; i < 7; i++) {
             const int n1 = i + 9;
-            const float2 v = cmul(x[r16(n1)], tw[i]);
+            const float2 v = cmul(x[r16(n1)], tw[ACQ_E1B_TW15 ? i + 8 : i]);
             asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
         }
     }

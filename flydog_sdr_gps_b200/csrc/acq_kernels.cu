@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
     __shared__ __align__(8) unsigned long long bar;
     __shared__ float2 x1s[kFeX1 + 2];
     const int t = threadIdx.x;
+    pdl_launch_dependents();
     const int chunk = blockIdx.x;                      // 16 chunks per block
     const uint8_t *pk = packed + (size_t)blockIdx.y * ACQ_BLOCK_BYTES + 512 * chunk;
     const int avail = ACQ_BLOCK_BYTES - 512 * chunk;   // bytes of this block from the chunk start
@@ -249,9 +250,11 @@ __global__ void __launch_bounds__(256, 1) k_fwd_fft(const float2 *__restrict__ x
     const FftSmem3 s = fft_smem3_carve(smem);
     float2 *Z = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());
     const int t = threadIdx.x;
+    pdl_trigger_fft();
     load_t2(s, tables, t);
     const float2 *base = tables + kT2Elems + t;
     int buf = 0;
+    pdl_wait();
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
         const float2 *in = x2 + (size_t)row * kN;
         float2 *o = out + (size_t)row * kN;
@@ -308,6 +311,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1)
     float2 *Y = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());  // [2][16][256]
     const int t = threadIdx.x;
     const int rank = (int)cluster.block_rank();
+    pdl_trigger_fft();
     load_t2(s, tables, t);
     const float2 bw = __ldg(tables + kT2Elems + rank * 256 + t);
     const float2 *Yr[4];
@@ -315,6 +319,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1)
     for (int k = 0; k < 4; k++) Yr[k] = cluster.map_shared_rank(Y, k);
     const int n_clusters = gridDim.x >> 2;
     int buf = 0, yb = 0;
+    pdl_wait();
     for (int row = blockIdx.x >> 2; row < n_rows; row += n_clusters) {
         const float2 *in = x2 + (size_t)row * kN;
         float2 *o = out + (size_t)row * kN;
@@ -513,9 +518,11 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
     // stage-B twiddles live in tensor memory: 128 columns per thread, warps w and w+4 share lanes
     const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
     const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
+    pdl_trigger_search();
     subfft3_park_twiddles(p.tables, tw_taddr, t);
     const float2 *base = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
     int buf = 0;
+    pdl_wait();
     // The cross-warp merge of a tile's peak is deferred to the next tile: the warp partials are left in a
     // parity slot and thread 0 merges them after the next tile's first sub-FFT barrier, so the reduction
     // costs no CTA barrier of its own (it matters at K = 1, where a tile is only four sub-FFTs).
@@ -599,18 +606,25 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     constexpr int L = ACQ_LAGS_L1;
     const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
     const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
+    pdl_trigger_search();
     subfft4_park_twiddles(p.tables, tw_taddr, t);
     float2 bw = __ldg(p.tables + kT2Elems + t);  // W16384^{4t}: base of residue 0; later bases come from TMEM
     const uint32_t bar = smem_u32(s.bar);
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
+    pdl_wait();
     // lanes 0..15 of warp 0: stage the operands of sub-FFT (tn, bn, k2n) -- D row by row into S1 half `half`,
     // E into the E buffer (lane 0)
     auto issue = [&](const TileIdx &tn, int bn, int k2n, int half) {
         const int r = (k2n - tn.dop) & 3;
         const int q = (k2n - tn.dop - r) >> 2;
+#ifdef ACQ_KO_SAME_OPERANDS  // knock-out experiment (wrong results): every tile reads the same 64 KiB of operands
+        const float2 *Dk = p.Dp + k2n * kSub;
+        const float2 *Ek = p.Ep + (size_t)r * p.ext_len + ((p.Q + q) & ~1);
+#else
         const float2 *Dk = p.Dp + ((size_t)((size_t)tn.cap * p.K + bn) * p.nvar + tn.v) * kN + k2n * kSub;
         const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
+#endif
         fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
         if (t == 0) {
             mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
@@ -718,11 +732,13 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_ldg(const SearchArgs p)
     const int t = threadIdx.x;
     constexpr int L = ACQ_LAGS_E1B;
     const uint32_t tmem_base = tmem_alloc_cta<kE1bTmemCols>(reinterpret_cast<uint32_t *>(red_f + 32), t);
+    pdl_trigger_search();
     load_t2(s, p.tables, t);
     // this thread's scratch: lane 32*(warp%4) + (t%32), columns [96*(warp/4), +96): [k2][n2] complex
     const uint32_t zaddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * 96);
     const float2 *base = p.tables + kT2Elems + t;
     int buf = 0;
+    pdl_wait();
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileIdx ti(p, tile);
@@ -780,6 +796,9 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_ldg(const SearchArgs p)
 // next tile (no reduction barrier).  A thread's 128 TMEM columns hold the three parked residues (96) and the four
 // stage-A bases (8), so the stage-B twiddles stay in a 7.5 KiB shared-memory table.  106 KiB of shared memory per
 // CTA, two CTAs per SM.
+#ifndef ACQ_E1B_BEST4
+#define ACQ_E1B_BEST4 1
+#endif
 constexpr int kE1bBaseCol = 96;  // TMEM columns [96, 104): W16384^{4t+k2}, k2 = 0..3
 struct E1bSmem {
     float2 *S1;  // [2][4096]
@@ -814,6 +833,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     const int t = threadIdx.x;
     constexpr int L = ACQ_LAGS_E1B;
     const uint32_t tmem_base = tmem_alloc_cta<kE1bTmemCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
+    pdl_trigger_search();
     {   // stage-B twiddle table into shared memory
         const float4 *src = reinterpret_cast<const float4 *>(p.tables);
         float4 *dst = reinterpret_cast<float4 *>(s.T2);
@@ -829,6 +849,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     const uint32_t bar = smem_u32(s.bar);
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
+    pdl_wait();
     auto issue = [&](const TileIdx &tn, int k2n, int half) {  // thread 0: stage the operands of sub-FFT (tn, k2n)
         const int r = (k2n - tn.dop) & 3;
         const int q = (k2n - tn.dop - r) >> 2;
@@ -885,6 +906,46 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
         }
         // radix-4 combine over k2, lags n = lag_of3(t, n2) + 4096 m < 16368.  Lags are not visited in
         // increasing order here, so ties compare the index explicitly (first index wins, search.cpp:488).
+#if ACQ_E1B_BEST4
+        // A thread's lags grow with n2 inside a quarter m and with m across quarters: one running (max, n2) per
+        // quarter with a strict >, merged in the order m = 0..3 with a strict >, keeps the first maximum
+        // (search.cpp:488) without comparing indices.
+        float bp[4] = {0.0f, 0.0f, 0.0f, 0.0f}, bsum = 0.0f;
+        int bn2[4] = {0, 0, 0, 0};
+        const int lag0 = lag_of3(t, 0);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+            float2 za[4], zb[4], zc[4];
+            tmem_ld4(zaddr + 0 * 32 + 8 * c4, za);
+            tmem_ld4(zaddr + 1 * 32 + 8 * c4, zb);
+            tmem_ld4(zaddr + 2 * 32 + 8 * c4, zc);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int n2 = 4 * c4 + i;
+                float2 z0 = za[i], z1 = zb[i], z2 = zc[i];
+                float2 z3 = cmul(x[r16(n2)], c_cC[3][n2]);
+                radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
+                const float2 zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const float pw = cpower(zz[m]);
+                    // only the last 16 lags of the transform (m = 3, n2 = 15, t & 15 == 15) lie beyond L = 16368
+                    if (m < 3 || n2 < 15 || lag0 + 256 * 15 + 4096 * 3 < L) {
+                        if (pw > bp[m]) bp[m] = pw, bn2[m] = n2;
+                        bsum += pw;
+                    }
+                }
+            }
+        }
+        Peak best;
+        best.p = 0.0f;
+        best.n = 0x7fffffff;
+        best.sum = bsum;
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+            if (bp[m] > best.p) best.p = bp[m], best.n = lag0 + 256 * bn2[m] + 4096 * m;
+#else
         Peak best;
         best.p = 0.0f;
         best.n = 0x7fffffff;
@@ -911,6 +972,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
                 }
             }
         }
+#endif
         // parity slot `par` was last read (flush) during the previous tile, before >= 3 CTA barriers
         warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
         pend_cap = ti.cap;
@@ -953,6 +1015,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b
     const int t = threadIdx.x;
     const int rank = (int)cluster.block_rank();  // = k2 in the sub-FFT phase, = n2 slice in the combine phase
     constexpr int L = ACQ_LAGS_E1B;
+    pdl_trigger_search();
     load_t2(s, p.tables, t);
     const float2 bw = __ldg(p.tables + kT2Elems + rank * 256 + t);
     const float2 *Yr[4];
@@ -962,6 +1025,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b
     int *peaks_i0 = cluster.map_shared_rank(peaks_i, 0);
     const int n_clusters = gridDim.x >> 2;
     int buf = 0, yb = 0;
+    pdl_wait();
 
     for (long long tile = blockIdx.x >> 2; tile < p.n_tiles; tile += n_clusters) {
         const TileIdx ti(p, tile);
@@ -1031,6 +1095,7 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
                                                   acq_record *__restrict__ out, int n_rows, int n_slots, int n_dop,
                                                   int dop_lo)
 {
+    pdl_wait();  // before the early exit: completion of this grid must imply completion of its predecessors
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
@@ -1070,6 +1135,24 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+// Launch with (pdl) or without programmatic stream serialization: with it the grid may become resident while the
+// preceding kernel of the stream is still running; its threads block in pdl_wait() until that kernel has completed.
+template <class... KArgs, class... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);  // errors surface through cudaGetLastError() in the caller
+}
+
 static size_t search_l1_ldg_smem_bytes() { return fft_smem3t_bytes() + 64 * sizeof(float); }
 static size_t search_l1_smem_bytes() { return fft_smem4_bytes() + 64 * sizeof(float); }
 static bool use_ldg_kernel()
@@ -1140,17 +1223,16 @@ int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int 
 }
 
 int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_rows, bool polyphase, int sm_count,
-                   cudaStream_t st)
+                   cudaStream_t st, bool pdl)
 {
     if (n_rows <= sm_count / 4) {  // few rows: four CTAs per row (cluster + DSMEM), 2.5x shorter than the serial chain
         const size_t smem = fft_smem3_bytes() + 2 * sizeof(float2) * kSub;
-        if (polyphase) k_fwd_fft_cluster<true><<<4 * n_rows, 256, smem, st>>>(x2, out, tables, n_rows);
-        else k_fwd_fft_cluster<false><<<4 * n_rows, 256, smem, st>>>(x2, out, tables, n_rows);
+        launch_k(polyphase ? k_fwd_fft_cluster<true> : k_fwd_fft_cluster<false>, 4 * n_rows, 256, smem, st, pdl, x2, out,
+                 tables, n_rows);
         return 1;
     }
     const int grid = n_rows < sm_count ? n_rows : sm_count;
-    if (polyphase) k_fwd_fft<true><<<grid, 256, fwd_smem_bytes(), st>>>(x2, out, tables, n_rows);
-    else k_fwd_fft<false><<<grid, 256, fwd_smem_bytes(), st>>>(x2, out, tables, n_rows);
+    launch_k(polyphase ? k_fwd_fft<true> : k_fwd_fft<false>, grid, 256, fwd_smem_bytes(), st, pdl, x2, out, tables, n_rows);
     return 1;
 }
 
@@ -1160,38 +1242,37 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
     return 1;
 }
 
-int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st)
+int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, bool pdl)
 {
     if (a.n_tiles <= 0) return 0;
     const long long max_ctas = (long long)sm_count * 2;
     const int grid = (int)(a.n_tiles < max_ctas ? a.n_tiles : max_ctas);
     if (e1b) {
-        if (use_e1b_ldg_kernel()) k_search_e1b_ldg<<<grid, 256, search_e1b_ldg_smem_bytes(), st>>>(a);
-        else k_search_e1b<<<grid, 256, search_e1b_smem_bytes(), st>>>(a);
+        if (use_e1b_ldg_kernel()) launch_k(k_search_e1b_ldg, grid, 256, search_e1b_ldg_smem_bytes(), st, pdl, a);
+        else launch_k(k_search_e1b, grid, 256, search_e1b_smem_bytes(), st, pdl, a);
+    } else if (use_ldg_kernel()) {
+        launch_k(a.K > 1 ? k_search_l1_ldg<true> : k_search_l1_ldg<false>, grid, 256, search_l1_ldg_smem_bytes(), st, pdl, a);
+    } else {
+        launch_k(a.K > 1 ? k_search_l1<true> : k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
     }
-    else if (use_ldg_kernel()) {
-        if (a.K > 1) k_search_l1_ldg<true><<<grid, 256, search_l1_ldg_smem_bytes(), st>>>(a);
-        else k_search_l1_ldg<false><<<grid, 256, search_l1_ldg_smem_bytes(), st>>>(a);
-    } else if (a.K > 1) k_search_l1<true><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
-    else k_search_l1<false><<<grid, 256, search_l1_smem_bytes(), st>>>(a);
     return 1;
 }
 
-int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st)
+int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st, bool pdl)
 {
     if (a.n_tiles <= 0) return 0;
     const long long max_clusters = sm_count / 4;
     const int n_clusters = (int)(a.n_tiles < max_clusters ? a.n_tiles : max_clusters);
-    if (a.K > 1) k_search_e1b_cluster<true><<<4 * n_clusters, 256, search_e1b_cluster_smem_bytes(), st>>>(a);
-    else k_search_e1b_cluster<false><<<4 * n_clusters, 256, search_e1b_cluster_smem_bytes(), st>>>(a);
+    launch_k(a.K > 1 ? k_search_e1b_cluster<true> : k_search_e1b_cluster<false>, 4 * n_clusters, 256,
+             search_e1b_cluster_smem_bytes(), st, pdl, a);
     return 1;
 }
 
 int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
-                    int dop_lo, cudaStream_t st)
+                    int dop_lo, cudaStream_t st, bool pdl)
 {
     const int n_rows = n_cap * n_slots;
-    k_best_dop<<<(n_rows + 3) / 4, 128, 0, st>>>(cells, slot_sat, out, n_rows, n_slots, n_dop, dop_lo);
+    launch_k(k_best_dop, (n_rows + 3) / 4, 128, 0, st, pdl, cells, slot_sat, out, n_rows, n_slots, n_dop, dop_lo);
     return 1;
 }
 

@@ -25,13 +25,15 @@ int launch_tables_init(const float2 *h_cC, const float *h_hb);
 int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, cudaStream_t st);
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
 int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st);
+// pdl: launch with programmatic stream serialization (the grid may become resident while the previous kernel of
+// the stream drains; see pdl_wait() in acq_fft.cuh)
 int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_rows, bool polyphase, int sm_count,
-                   cudaStream_t st);
+                   cudaStream_t st, bool pdl = false);
 int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len, int wrap_mode, cudaStream_t st);
-int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st);
-int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st);
+int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, bool pdl = false);
+int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st, bool pdl = false);
 int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
-                    int dop_lo, cudaStream_t st);
+                    int dop_lo, cudaStream_t st, bool pdl = false);
 cudaError_t search_kernels_configure();
 
 }  // namespace acq
