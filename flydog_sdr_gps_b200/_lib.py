@@ -31,6 +31,7 @@ _SIGNATURES = [
     ("acq_submit", C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     ("acq_poll", C.c_int, [_P]),
     ("acq_wait", C.c_int, [_P]),
+    ("acq_refine", C.c_int, [_P, _P, C.c_int, _P]),
     ("acq_detected", C.c_int, [_P, _P]),
     ("acq_get_code_spectrum", C.c_int, [_P, C.c_int, _P]),
     ("acq_get_capture_spectrum", C.c_int, [_P, _P, C.c_int, _P, _P]),

@@ -115,6 +115,12 @@ struct acq_engine {
     int2 *d_work = nullptr;   // [n_slots]: L1 entries first, then E1B
     int *d_slot_sat = nullptr;
     size_t cap_slots = 0;
+    // refinement (acq_refine): satellite types on the device, record/output scratch, shape of the last host-path search
+    int *d_sat_type = nullptr;
+    acq_record *d_ref_rec = nullptr;
+    acq_fine *d_fine = nullptr;
+    size_t cap_ref_rec = 0, cap_fine = 0;
+    int last_captures = 0;  // 0: no search whose spectra are still on the device
 };
 
 namespace {
@@ -137,6 +143,9 @@ int free_engine(acq_engine *e)
     cudaFree(e->d_records);
     cudaFree(e->d_work);
     cudaFree(e->d_slot_sat);
+    cudaFree(e->d_sat_type);
+    cudaFree(e->d_ref_rec);
+    cudaFree(e->d_fine);
     if (e->done) cudaEventDestroy(e->done);
     for (cudaEvent_t ev : e->prof)
         if (ev) cudaEventDestroy(ev);
@@ -309,7 +318,9 @@ int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int3
     if ((rc = ensure_scratch(e, n_captures, e->n_slots, true))) return rc;
     const size_t bytes = (size_t)n_captures * e->prm.k_noncoh * ACQ_BLOCK_BYTES;
     CU(cudaMemcpyAsync(e->d_packed, packed, bytes, cudaMemcpyHostToDevice, e->stream));
+    e->last_captures = 0;
     if ((rc = enqueue_search(e, e->d_packed, n_captures, e->d_records, e->stream))) return rc;
+    e->last_captures = n_captures;
     const size_t rows = (size_t)n_captures * e->n_slots;
     CU(cudaMemcpyAsync(out, e->d_records, rows * sizeof(acq_record), cudaMemcpyDeviceToHost, e->stream));
     if (grid)
@@ -445,6 +456,12 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     CUE(cudaGetLastError());
     CUE(cudaMalloc(&e->d_tables, tables.size() * sizeof(float2)));
     CUE(cudaMemcpy(e->d_tables, tables.data(), tables.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    {
+        std::vector<int> types(n_sats);
+        for (int i = 0; i < n_sats; i++) types[i] = sats[i].type;
+        CUE(cudaMalloc(&e->d_sat_type, n_sats * sizeof(int)));
+        CUE(cudaMemcpy(e->d_sat_type, types.data(), n_sats * sizeof(int), cudaMemcpyHostToDevice));
+    }
     if (e->nvar == 2) {
         const double pi = 3.14159265358979323846264338327950288;
         std::vector<float2> rot(kN);
@@ -526,6 +543,7 @@ int acq_search_device(acq_engine *e, const uint8_t *packed_dev, int n_captures, 
     if ((rc = set_selection(e, sel, n_sel))) return rc;
     if ((rc = ensure_scratch(e, n_captures, e->n_slots, false))) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    e->last_captures = 0;  // spectra now belong to a search on the caller's stream: acq_refine does not apply
     return enqueue_search(e, packed_dev, n_captures, out_dev, st);
 }
 
@@ -556,6 +574,38 @@ int acq_wait(acq_engine *e)
     DeviceGuard g(e->device);
     e->pending = false;
     CU(cudaEventSynchronize(e->done));
+    return ACQ_OK;
+}
+
+int acq_refine(acq_engine *e, const acq_record *rec, int n_records, acq_fine *out)
+{
+    if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");
+    if (!rec || !out) return fail(ACQ_ERR_ARG, "rec/out must not be NULL");
+    if (e->pending) return fail(ACQ_ERR_ARG, "a submitted search is still pending: call acq_wait first");
+    if (e->last_captures <= 0) return fail(ACQ_ERR_ARG, "no completed host-path search to refine");
+    const long long rows = (long long)e->last_captures * e->n_slots;
+    if (n_records != rows)
+        return fail(ACQ_ERR_ARG, "n_records=%d but the last search produced %lld records", n_records, rows);
+    for (int i = 0; i < n_records; i++) {
+        const acq_record &r = rec[i];
+        if (r.sat != e->sel_cache[i % e->n_slots])
+            return fail(ACQ_ERR_ARG, "record %d: sat %d is not the satellite searched in that slot", i, r.sat);
+        const int L = (e->sats[r.sat].type == ACQ_E1B) ? ACQ_LAGS_E1B : ACQ_LAGS_L1;
+        if (r.lag < 0 || r.lag >= L) return fail(ACQ_ERR_ARG, "record %d: lag %d outside 0..%d", i, r.lag, L - 1);
+        // a row that never exceeded snr 0 carries dop 0 (k_best_dop), which may lie outside an asymmetric range
+        if ((r.dop < e->prm.dop_lo || r.dop > e->prm.dop_hi) && !(r.dop == 0 && r.snr == 0.0f))
+            return fail(ACQ_ERR_ARG, "record %d: Doppler index %d outside %d..%d", i, r.dop, e->prm.dop_lo, e->prm.dop_hi);
+    }
+    DeviceGuard g(e->device);
+    int rc = grow(e->d_ref_rec, e->cap_ref_rec, (size_t)n_records);
+    if (rc) return rc;
+    if ((rc = grow(e->d_fine, e->cap_fine, (size_t)n_records))) return rc;
+    CU(cudaMemcpyAsync(e->d_ref_rec, rec, (size_t)n_records * sizeof(acq_record), cudaMemcpyHostToDevice, e->stream));
+    e->launches += launch_refine(e->d_Dp, e->d_Ep, e->d_ref_rec, e->d_sat_type, e->d_fine, n_records, e->n_slots,
+                                 e->prm.k_noncoh, e->nvar, e->prm.half_bin, e->ext_len, e->Q, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, e->d_fine, (size_t)n_records * sizeof(acq_fine), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     return ACQ_OK;
 }
 

@@ -1133,6 +1133,126 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6.  Acquisition refinement for the hand-off to tracking.  The search reports the code phase
+// in /DECIM samples and the Doppler in bins of 249.76 Hz (search.cpp:574-575); the tracking loops then need a 5 s
+// settle to pull in the LO (gps/channel.cpp:345-372) because +-125 Hz exceeds the Costas pull-in range.  For each
+// record this kernel evaluates the correlation r_d[n] = sum_k conj(D[k]) C[k-d] e^{+j 2 pi k n / N} (the very sum
+// the inverse FFT computes, search.cpp:471-481) at five points around the peak -- (d-1, n) (d, n-1) (d, n)
+// (d, n+1) (d+1, n) -- straight from the spectra the search left in HBM, and forms
+//   Doppler: delta = Re[(Xm - Xp) conj(2 X0 - Xm - Xp)] / |2 X0 - Xm - Xp|^2   (three-bin interpolation of a
+//            rectangular-window DFT; X_d = r_d[n] e^{-j 2 pi d n / N} puts the three bins on a common phase),
+//   code   : eps = slope (l - e) / (l + e),  e/l = Re(r[n-+1] conj(r[n]))       (early-minus-late over the
+//            correlation triangle: 4 samples per chip -> slope 3; BOC(1,1) main peak -> slope 1/3),
+// each summed over the K blocks.  One CTA per record; thread t owns k1 = t + 256 i for all four residues.
+// ---------------------------------------------------------------------------------------------
+struct RefineArgs {
+    const float2 *Dp;
+    const float2 *Ep;
+    const acq_record *rec;   // [n_rows], row = cap * n_slots + slot
+    const int *sat_type;     // [n_sats]
+    acq_fine *out;
+    int n_slots, K, nvar, half_bin, ext_len, Q;
+};
+
+__global__ void __launch_bounds__(256) k_refine(const RefineArgs p)
+{
+    __shared__ float red[8][10];
+    const int row = blockIdx.x, t = threadIdx.x;
+    const acq_record rc = p.rec[row];
+    const int cap = row / p.n_slots;
+    const bool e1b = p.sat_type[rc.sat] == ACQ_E1B;
+    const int v = p.half_bin ? (rc.dop & 1) : 0;
+    const int dop = p.half_bin ? ((rc.dop - v) >> 1) : rc.dop;
+    const int n = rc.lag;
+    float num = 0.0f, den = 0.0f, early = 0.0f, late = 0.0f, peak = 0.0f;  // thread 0 only
+    for (int b = 0; b < p.K; b++) {
+        const float2 *D = p.Dp + ((size_t)((size_t)cap * p.K + b) * p.nvar + v) * kN;
+        float2 acc[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) acc[j] = make_float2(0.0f, 0.0f);
+        for (int k2 = 0; k2 < 4; k2++) {
+            const float2 *Er[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {  // code rows for Doppler dop-1, dop, dop+1
+                const int dd = dop - 1 + j;
+                const int r = (k2 - dd) & 3;
+                const int q = (k2 - dd - r) >> 2;
+                Er[j] = p.Ep + (size_t)(rc.sat * 4 + r) * p.ext_len + p.Q + q;
+            }
+            for (int k1 = t; k1 < kSub; k1 += 256) {
+                const int k = 4 * k1 + k2;
+                const float2 d = D[k2 * kSub + k1];
+                float sn, cs, s1, c1;
+                sincospif((float)((k * n) & (kN - 1)) * (1.0f / 8192.0f), &sn, &cs);  // e^{+j 2 pi k n / N}
+                sincospif((float)k * (1.0f / 8192.0f), &s1, &c1);                      // e^{+j 2 pi k / N}
+                const float2 w0 = make_float2(cs, sn), wk = make_float2(c1, s1);
+                const float2 pm = cmul(cmul_conj_a(d, Er[0][k1]), w0);
+                const float2 pc = cmul(cmul_conj_a(d, Er[1][k1]), w0);
+                const float2 pp = cmul(cmul_conj_a(d, Er[2][k1]), w0);
+                acc[0] = cadd(acc[0], pm);
+                acc[1] = cadd(acc[1], cmul(pc, make_float2(c1, -s1)));  // lag n-1
+                acc[2] = cadd(acc[2], pc);
+                acc[3] = cadd(acc[3], cmul(pc, wk));                    // lag n+1
+                acc[4] = cadd(acc[4], pp);
+            }
+        }
+        // CTA reduction of the five complex sums
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, off);
+                acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, off);
+            }
+        }
+        __syncthreads();  // red[] of the previous block has been consumed
+        if ((t & 31) == 0) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                red[t >> 5][2 * j] = acc[j].x;
+                red[t >> 5][2 * j + 1] = acc[j].y;
+            }
+        }
+        __syncthreads();
+        if (t == 0) {
+            float2 R[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                R[j] = make_float2(0.0f, 0.0f);
+                for (int w = 0; w < 8; w++) R[j].x += red[w][2 * j], R[j].y += red[w][2 * j + 1];
+            }
+            float sn, cs;
+            // w1 = e^{+j 2 pi n_b / N}, n_b = n + 16 b: the front end delayed block b by 16 b samples, so lag n of
+            // its spectrum is lag n + 16 b of the block itself -- the lag the Doppler phase term refers to
+            sincospif((float)((n + 16 * b) & (kN - 1)) * (1.0f / 8192.0f), &sn, &cs);
+            const float2 Xm = cmul(R[0], make_float2(cs, sn)), Xp = cmul(R[4], make_float2(cs, -sn)), X0 = R[2];
+            const float2 a = csub(Xm, Xp);
+            const float2 g = csub(csub(cadd(X0, X0), Xm), Xp);
+            num += a.x * g.x + a.y * g.y;
+            den += g.x * g.x + g.y * g.y;
+            early += R[1].x * R[2].x + R[1].y * R[2].y;
+            late += R[3].x * R[2].x + R[3].y * R[2].y;
+            peak += R[2].x * R[2].x + R[2].y * R[2].y;
+        }
+    }
+    if (t == 0) {
+        float delta = den > 0.0f ? num / den : 0.0f;
+        delta = fminf(1.0f, fmaxf(-1.0f, delta));
+        float eps = (early + late) > 0.0f ? (e1b ? (1.0f / 3.0f) : 3.0f) * (late - early) / (early + late) : 0.0f;
+        eps = fminf(1.0f, fmaxf(-1.0f, eps));
+        const int L = e1b ? ACQ_LAGS_E1B : ACQ_LAGS_L1;
+        acq_fine o;
+        o.dop_hz = ((p.half_bin ? 0.5f * (float)rc.dop : (float)rc.dop) + delta) * (float)ACQ_BIN_HZ;
+        o.code_fs = (float)ACQ_DECIM * ((float)n + eps);
+        o.peak = peak;
+        int cs = (int)lrintf(o.code_fs) % (L * ACQ_DECIM);
+        if (cs < 0) cs += L * ACQ_DECIM;
+        o.ca_shift = cs;
+        p.out[row] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 // Launch with (pdl) or without programmatic stream serialization: with it the grid may become resident while the
@@ -1265,6 +1385,15 @@ int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st
     const int n_clusters = (int)(a.n_tiles < max_clusters ? a.n_tiles : max_clusters);
     launch_k(a.K > 1 ? k_search_e1b_cluster<true> : k_search_e1b_cluster<false>, 4 * n_clusters, 256,
              search_e1b_cluster_smem_bytes(), st, pdl, a);
+    return 1;
+}
+
+int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
+                  int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, cudaStream_t st)
+{
+    if (n_rows <= 0) return 0;
+    RefineArgs a{Dp, Ep, rec, sat_type, out, n_slots, K, nvar, half_bin, ext_len, Q};
+    k_refine<<<n_rows, 256, 0, st>>>(a);
     return 1;
 }
 

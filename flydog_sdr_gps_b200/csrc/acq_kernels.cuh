@@ -34,6 +34,9 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st, bool pdl = false);
 int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
                     int dop_lo, cudaStream_t st, bool pdl = false);
+// refinement of the records of the most recent search (one CTA per record)
+int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
+                  int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, cudaStream_t st);
 cudaError_t search_kernels_configure();
 
 }  // namespace acq

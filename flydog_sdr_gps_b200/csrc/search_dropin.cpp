@@ -1,6 +1,7 @@
 // search_dropin.cpp -- see search_dropin.h.  Host C++ above the C ABI; no CUDA types here.
 #include "../../include/search_dropin.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,6 +15,7 @@ struct acq_dropin {
     std::vector<char> busy;
     int minimum_sig = 16;  // MIN_SIG (gps/gps.h:60), overridable with -gsig (search.cpp:82-84)
     int test_mode = 0;
+    int refine = 0;  // acq_dropin_set_refine: hand ChanStart the interpolated code phase / nearest Doppler bin
     int acq_navstar = 1, acq_qzss = 1, acq_galileo = 1;
     // state that SearchTask keeps across satellites and passes (search.cpp:513-515)
     int last_ch = -1, lo_shift = 0, ca_shift = 0;
@@ -111,6 +113,13 @@ int acq_dropin_set_acq(acq_dropin *d, int navstar, int qzss, int galileo)
     return ACQ_OK;
 }
 
+int acq_dropin_set_refine(acq_dropin *d, int on)
+{
+    if (!d) return ACQ_ERR_ARG;
+    d->refine = on ? 1 : 0;
+    return ACQ_OK;
+}
+
 int acq_dropin_enable(acq_dropin *d, int sat)
 {
     if (!d || sat < 0 || sat >= (int)d->sats.size()) return ACQ_ERR_ARG;
@@ -157,6 +166,13 @@ static int pass_literal(acq_dropin *d)
         if (h.stat_sat) h.stat_sat(h.user, d->snr, ch, sat, d->snr < msig, us);  // :580
         d->last_ch = ch;
         if (d->snr < msig) continue;  // :591
+        if (d->refine && rec.snr > 0) {  // extension (off by default): FS-sample code phase, nearest Doppler bin
+            acq_fine fine;
+            const int rr = acq_refine(d->eng, &rec, 1, &fine);
+            if (rr != ACQ_OK) return rr;
+            d->ca_shift = fine.ca_shift;
+            d->lo_shift = (int)lrintf(fine.dop_hz / (float)ACQ_BIN_HZ);
+        }
         if (h.stat_dop) h.stat_dop(h.user, ch, (int)(d->lo_shift * (float)ACQ_BIN_HZ), d->ca_shift);  // :595
         d->busy[sat] = 1;  // :597
         h.chan_start(h.user, ch, sat, (int)t0, d->lo_shift, d->ca_shift, (int)d->snr);  // :601
@@ -180,6 +196,12 @@ static int pass_batch(acq_dropin *d)
     std::vector<acq_record> rec(sel.size());
     const int rc = acq_search(d->eng, d->capture.data(), 1, sel.data(), (int)sel.size(), rec.data());
     if (rc != ACQ_OK) return rc;
+    std::vector<acq_fine> fine;
+    if (d->refine) {
+        fine.resize(sel.size());
+        const int rr = acq_refine(d->eng, rec.data(), (int)rec.size(), fine.data());
+        if (rr != ACQ_OK) return rr;
+    }
     const int us = (int)(h.timer_us(h.user) - t0);
     int started = 0;
     for (size_t i = 0; i < sel.size(); i++) {
@@ -191,11 +213,12 @@ static int pass_batch(acq_dropin *d)
         }
         const int ch = h.chan_reset(h.user, sat, codegen_init(d->sats[sat]));
         if (ch < 0) break;  // no free tracking channel left
-        const int ca_shift = rec[i].lag * ACQ_DECIM;
+        const int ca_shift = d->refine ? fine[i].ca_shift : rec[i].lag * ACQ_DECIM;
+        const int lo_shift = d->refine ? (int)lrintf(fine[i].dop_hz / (float)ACQ_BIN_HZ) : rec[i].dop;
         if (h.stat_sat) h.stat_sat(h.user, rec[i].snr, ch, sat, 0, us);
-        if (h.stat_dop) h.stat_dop(h.user, ch, (int)(rec[i].dop * (float)ACQ_BIN_HZ), ca_shift);
+        if (h.stat_dop) h.stat_dop(h.user, ch, (int)(lo_shift * (float)ACQ_BIN_HZ), ca_shift);
         d->busy[sat] = 1;
-        h.chan_start(h.user, ch, sat, (int)t0, rec[i].dop, ca_shift, (int)rec[i].snr);
+        h.chan_start(h.user, ch, sat, (int)t0, lo_shift, ca_shift, (int)rec[i].snr);
         started++;
     }
     return started;

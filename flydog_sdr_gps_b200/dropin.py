@@ -75,6 +75,7 @@ class Dropin:
         L.acq_dropin_enable.argtypes = [C.c_void_p, C.c_int]
         L.acq_dropin_is_busy.argtypes = [C.c_void_p, C.c_int]
         L.acq_dropin_set_acq.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.acq_dropin_set_refine.argtypes = [C.c_void_p, C.c_int]
         L.acq_dropin_params.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
         self.rx = receiver
         self._cbs = HostIface(None, _CHAN_RESET(receiver.chan_reset), _CHAN_START(receiver.chan_start),
@@ -95,6 +96,10 @@ class Dropin:
 
     def set_acq(self, navstar=1, qzss=1, galileo=1):
         return self._L.acq_dropin_set_acq(self._h, navstar, qzss, galileo)
+
+    def set_refine(self, on=True):
+        """Hand ChanStart the acq_refine values (FS-sample ca_shift, nearest Doppler bin); off by default."""
+        return self._L.acq_dropin_set_refine(self._h, int(bool(on)))
 
     def search_pass(self, mode=LITERAL):
         rc = self._L.acq_dropin_pass(self._h, mode)

@@ -19,7 +19,8 @@ WRAP_REFERENCE, WRAP_CIRCULAR = 0, 1
 RECORD_DTYPE = np.dtype([("sat", "<i4"), ("lag", "<i4"), ("dop", "<i4"),
                          ("peak", "<f4"), ("noise", "<f4"), ("snr", "<f4")])
 CELL_DTYPE = np.dtype([("peak", "<f4"), ("noise", "<f4"), ("snr", "<f4"), ("lag", "<i4")])
-assert RECORD_DTYPE.itemsize == 24 and CELL_DTYPE.itemsize == 16
+FINE_DTYPE = np.dtype([("dop_hz", "<f4"), ("code_fs", "<f4"), ("peak", "<f4"), ("ca_shift", "<i4")])
+assert RECORD_DTYPE.itemsize == 24 and CELL_DTYPE.itemsize == 16 and FINE_DTYPE.itemsize == 16
 
 
 class AcqError(RuntimeError):
@@ -173,6 +174,14 @@ class AcqEngine:
         """packed_dev / out_dev: device pointers (ints).  Enqueues on stream_ptr (None = engine stream)."""
         sp, n_sel, keep = self._sel(sel)
         _check(self._L.acq_search_device(self._h, packed_dev, n_cap, sp, n_sel, out_dev, stream_ptr))
+
+    def refine(self, records):
+        """acq_refine: hand-off refinement of the records of the most recent search()/wait() -- FINE_DTYPE array of
+        the same shape (Doppler in Hz from a three-bin interpolation, code phase in FS samples from early/late)."""
+        r = np.ascontiguousarray(records, RECORD_DTYPE)
+        out = np.zeros(r.shape, FINE_DTYPE)
+        _check(self._L.acq_refine(self._h, r.ctypes.data, r.size, out.ctypes.data))
+        return out
 
     def detected(self, records):
         """Detection rule of SearchTask (search.cpp:549,591) applied to a record array."""

@@ -101,6 +101,17 @@ typedef struct acq_cell {
     int32_t lag;
 } acq_cell;
 
+/* Refined hand-off values for one record (acq_refine; SURVEY 8(f) rank 4 -- an extension, the reference hands
+ * over whole bins and whole /DECIM samples, gps/search.cpp:574-575).  16 bytes. */
+typedef struct acq_fine {
+    float dop_hz;     /* Doppler in Hz: (bin + three-bin interpolation) * ACQ_BIN_HZ */
+    float code_fs;    /* code phase in FS samples: ACQ_DECIM * (lag + early/late interpolation) */
+    float peak;       /* |r|^2 at (lag, dop) evaluated directly from the spectra, summed over the K blocks: equals
+                         acq_record.peak up to rounding */
+    int32_t ca_shift; /* round(code_fs) modulo the code period in FS samples: ChanStart's ca_shift at FS-sample
+                         resolution (gps/channel.cpp:925-934) */
+} acq_fine;
+
 typedef struct acq_engine acq_engine;
 
 /* Thread-local text of the last error returned on this thread ("" if none). */
@@ -149,6 +160,16 @@ int acq_submit(acq_engine *e, const uint8_t *packed, int n_captures, const int32
                acq_record *out);
 int acq_poll(acq_engine *e);
 int acq_wait(acq_engine *e);
+
+/* Acquisition refinement for the hand-off to tracking.  `rec` (HOST) are the n_captures * n_sel records of the MOST
+ * RECENT host-path search on this engine (acq_search, acq_search_grid, or acq_submit after acq_wait), in the same
+ * order; the capture spectra that search left on the device are reused, so no capture is passed again.  For each
+ * record the correlation is evaluated at the five points (dop-1..dop+1 at lag; lag-1..lag+1 at dop), a three-bin
+ * Doppler interpolation and an early/late code-phase interpolation are formed, and `out` (HOST, same count) is
+ * filled.  Records of undetected satellites are refined like any other (their values are noise).  Returns
+ * ACQ_ERR_ARG when there is no completed search, the count differs, or a record does not belong to this engine's
+ * table / Doppler range. */
+int acq_refine(acq_engine *e, const acq_record *rec, int n_records, acq_fine *out);
 
 /* Detection rule of SearchTask (gps/search.cpp:549,591): snr >= threshold of the sat's type. */
 int acq_detected(const acq_engine *e, const acq_record *r);

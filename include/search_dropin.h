@@ -60,6 +60,10 @@ int acq_dropin_destroy(acq_dropin *d);
 int acq_dropin_params(acq_dropin *d, int argc, char *argv[]);
 /* gps.acq_Navstar / acq_QZSS / acq_Galileo (search.cpp:525,533-535) */
 int acq_dropin_set_acq(acq_dropin *d, int navstar, int qzss, int galileo);
+/* Extension, off by default: hand ChanStart the acq_refine values -- ca_shift at FS-sample
+ * resolution instead of lag * DECIM, lo_shift = the bin nearest to the interpolated Doppler.  Units and call
+ * order are unchanged, so gps/channel.cpp needs no edit. */
+int acq_dropin_set_refine(acq_dropin *d, int on);
 /* SearchEnable(sat): sat is no longer tracked, search it again (search.cpp:504-506) */
 int acq_dropin_enable(acq_dropin *d, int sat);
 int acq_dropin_is_busy(const acq_dropin *d, int sat);

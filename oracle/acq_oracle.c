@@ -383,6 +383,121 @@ int orc_search(const uint8_t *packed, const orc_sat *sats, int n_sats, const int
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Acquisition refinement (extension; see acq_oracle.h).  Direct evaluation of the correlation sum of
+ * search.cpp:471-481 at five points around a record's peak, in double precision.
+ * ---------------------------------------------------------------------------------------- */
+static void code_bin(const float *C, const float *Cnext, int wrap_mode, int i, int dop, double *cr, double *ci)
+{
+    /* same row addressing as correlate_one (search.cpp:471 with the doubled rows) */
+    int j = i - dop;
+    const float *row = C;
+    if (j < 0) j += N;
+    else if (j >= N) {
+        j -= N;
+        if (wrap_mode == ORC_WRAP_REFERENCE) row = Cnext;
+    }
+    *cr = row ? row[2 * j] : 0.0;
+    *ci = row ? row[2 * j + 1] : 0.0;
+}
+
+int orc_refine(const uint8_t *packed, const orc_sat *sats, int n_sats, const orc_params *prm,
+               const orc_record *rec, int n_rec, orc_fine *out, int nthreads)
+{
+    if (!packed || !sats || !prm || !rec || !out || n_sats <= 0 || n_rec < 0) return -1;
+    for (int s = 0; s < n_rec; s++)
+        if (rec[s].sat < 0 || rec[s].sat >= n_sats) return -2;
+    plans_init();
+    const int K = prm->k_noncoh;
+    const int nvar = prm->half_bin ? 2 : 1;
+    float *D = (float *)malloc(sizeof(float) * 2 * N * (size_t)K * nvar);
+    double *tw = (double *)malloc(sizeof(double) * 2 * N);
+    if (!D || !tw) return -3;
+    for (int i = 0; i < N; i++) {
+        tw[2 * i] = cos(2.0 * M_PI * i / N);
+        tw[2 * i + 1] = sin(2.0 * M_PI * i / N);
+    }
+#pragma omp parallel for schedule(dynamic) num_threads(orc_threads(nthreads))
+    for (int bv = 0; bv < K * nvar; bv++) {
+        float *scratch = (float *)malloc(sizeof(float) * 2 * N);
+        float *d = D + (size_t)bv * 2 * N;
+        orc_capture_baseband(packed + (size_t)(bv / nvar) * ORC_BLOCK_BYTES, bv % nvar, d);
+        orc_fft_execute(g_fwd, d, scratch);
+        free(scratch);
+    }
+#pragma omp parallel for schedule(dynamic) num_threads(orc_threads(nthreads))
+    for (int s = 0; s < n_rec; s++) {
+        const int sat = rec[s].sat;
+        float *C = (float *)malloc(sizeof(float) * 4 * N), *scratch = (float *)malloc(sizeof(float) * 2 * N);
+        const float *Cnext = NULL;
+        orc_code_baseband(&sats[sat], C);
+        orc_fft_execute(g_fwd, C, scratch);
+        if (sat + 1 < n_sats && prm->wrap_mode == ORC_WRAP_REFERENCE) {
+            orc_code_baseband(&sats[sat + 1], C + 2 * N);
+            orc_fft_execute(g_fwd, C + 2 * N, scratch);
+            Cnext = C + 2 * N;
+        }
+        const int e1b = sats[sat].type == ORC_E1B;
+        const int L = e1b ? 16368 : 4092;
+        const int var = prm->half_bin ? (rec[s].dop & 1) : 0;
+        const int dop = prm->half_bin ? (rec[s].dop - var) / 2 : rec[s].dop;
+        const int n = rec[s].lag;
+        double num = 0, den = 0, early = 0, late = 0, peak = 0;
+        for (int b = 0; b < K; b++) {
+            const float *data = D + (size_t)(b * nvar + var) * 2 * N;
+            const int nb = (n + 16 * b) % N; /* lag n of block 0 is lag n + 16 b of block b (see correlate_one) */
+            double R[5][2] = {{0}};
+            for (int i = 0; i < N; i++) {
+                const double dr = data[2 * i], di = data[2 * i + 1];
+                double c[3][2];
+                for (int j = 0; j < 3; j++) code_bin(C, Cnext, prm->wrap_mode, i, dop - 1 + j, &c[j][0], &c[j][1]);
+                double pr[3][2];
+                for (int j = 0; j < 3; j++) { /* conj(data) * code, support/simd.cpp:38-39 */
+                    pr[j][0] = dr * c[j][0] + di * c[j][1];
+                    pr[j][1] = dr * c[j][1] - di * c[j][0];
+                }
+                const int lag[5] = {nb, (nb + N - 1) % N, nb, (nb + 1) % N, nb};
+                const int which[5] = {0, 1, 1, 1, 2};
+                for (int j = 0; j < 5; j++) {
+                    const int m = (int)(((long long)i * lag[j]) % N);
+                    const double wr = tw[2 * m], wi = tw[2 * m + 1];
+                    R[j][0] += pr[which[j]][0] * wr - pr[which[j]][1] * wi;
+                    R[j][1] += pr[which[j]][0] * wi + pr[which[j]][1] * wr;
+                }
+            }
+            /* X_d = r_d e^{-j 2 pi d n/N}: relative to the centre bin, r_{d-1} gets e^{+j 2 pi n/N}, r_{d+1} its conjugate */
+            const double wr = tw[2 * nb], wi = tw[2 * nb + 1];
+            const double Xm[2] = {R[0][0] * wr - R[0][1] * wi, R[0][0] * wi + R[0][1] * wr};
+            const double Xp[2] = {R[4][0] * wr + R[4][1] * wi, -R[4][0] * wi + R[4][1] * wr};
+            const double a[2] = {Xm[0] - Xp[0], Xm[1] - Xp[1]};
+            const double g[2] = {2 * R[2][0] - Xm[0] - Xp[0], 2 * R[2][1] - Xm[1] - Xp[1]};
+            num += a[0] * g[0] + a[1] * g[1];
+            den += g[0] * g[0] + g[1] * g[1];
+            early += R[1][0] * R[2][0] + R[1][1] * R[2][1];
+            late += R[3][0] * R[2][0] + R[3][1] * R[2][1];
+            peak += R[2][0] * R[2][0] + R[2][1] * R[2][1];
+        }
+        double delta = den > 0 ? num / den : 0.0;
+        if (delta > 1) delta = 1;
+        if (delta < -1) delta = -1;
+        double eps = (early + late) > 0 ? (e1b ? 1.0 / 3.0 : 3.0) * (late - early) / (early + late) : 0.0;
+        if (eps > 1) eps = 1;
+        if (eps < -1) eps = -1;
+        orc_fine *o = &out[s];
+        o->dop_hz = (float)(((prm->half_bin ? 0.5 * rec[s].dop : (double)rec[s].dop) + delta) * (16.368e6 / 65536.0));
+        o->code_fs = (float)(ORC_DECIM * ((double)n + eps));
+        o->peak = (float)peak;
+        int cs = (int)lrintf(o->code_fs) % (L * ORC_DECIM);
+        if (cs < 0) cs += L * ORC_DECIM;
+        o->ca_shift = cs;
+        free(C);
+        free(scratch);
+    }
+    free(D);
+    free(tw);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Synthetic capture generator (test fixture; not a reference function).
  *   s[i] = sum_k A_k * c_k(i + tau_k) * cos(2*pi*(FC + f_k)*i/FS + phi_k) + n[i],  n ~ N(0,1)
  *   A_k  = sqrt(4 * 10^(CN0/10) / FS);  bit = (s < 0);  packed LSB-first (search.cpp:408-411).

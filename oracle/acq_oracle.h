@@ -120,6 +120,22 @@ int orc_search_pre(const uint8_t *packed, const orc_sat *sats, int n_sats, const
                    const int32_t *sel, int n_sel, const orc_params *prm, orc_record *out,
                    orc_cell *grid, int nthreads);
 
+/* --- acquisition refinement (extension; no reference counterpart) ---
+ * For each record: the correlation r_d[n] = sum_k conj(D[k]) C[k-d] e^{+j 2 pi k n/N} (search.cpp:471-481 written as
+ * a direct sum, double precision here) at (d-1,n) (d,n-1) (d,n) (d,n+1) (d+1,n), summed over the K blocks as
+ *   num += Re[(Xm-Xp) conj(2X0-Xm-Xp)], den += |2X0-Xm-Xp|^2, X_d = r_d[n] e^{-j 2 pi d n/N}   -> delta = num/den
+ *   e   += Re(r[n-1] conj r[n]),  l += Re(r[n+1] conj r[n])   -> eps = slope (l-e)/(l+e), slope 3 (C/A) | 1/3 (E1B)
+ * both clamped to [-1,1].  Block b of a K-block capture is evaluated at lag n + 16 b (its code phase advance). */
+typedef struct {
+    float dop_hz;     /* (bin + delta) * BIN_SIZE */
+    float code_fs;    /* DECIM * (lag + eps), FS samples */
+    float peak;       /* sum_b |r_d[n]|^2 : the record's peak power, recomputed directly */
+    int32_t ca_shift; /* round(code_fs) mod (L * DECIM) */
+} orc_fine;
+
+int orc_refine(const uint8_t *packed, const orc_sat *sats, int n_sats, const orc_params *prm,
+               const orc_record *rec, int n_rec, orc_fine *out, int nthreads);
+
 /* --- deterministic synthetic capture generator (SURVEY.md 8(d) "Value distributions") --- */
 typedef struct {
     int32_t sat;       /* index into the sat table */

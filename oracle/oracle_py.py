@@ -37,6 +37,7 @@ class OrcSignal(C.Structure):
 
 RECORD_DTYPE = np.dtype([("sat", "<i4"), ("lag", "<i4"), ("dop", "<i4"),
                          ("peak", "<f4"), ("noise", "<f4"), ("snr", "<f4")])
+FINE_DTYPE = np.dtype([("dop_hz", "<f4"), ("code_fs", "<f4"), ("peak", "<f4"), ("ca_shift", "<i4")])
 CELL_DTYPE = np.dtype([("peak", "<f4"), ("noise", "<f4"), ("snr", "<f4"), ("lag", "<i4")])
 EVENT_DTYPE = np.dtype([("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4"), ("d", "<i4"),
                         ("e", "<i4"), ("x", "<f8"), ("y", "<f8")])
@@ -74,6 +75,9 @@ def lib():
         L.orc_search_pre.argtypes = [u8, C.POINTER(OrcSat), C.c_int, fp, C.POINTER(C.c_int32), C.c_int,
                                      C.POINTER(OrcParams), C.c_void_p, C.c_void_p, C.c_int]
         L.orc_search_pre.restype = C.c_int
+        L.orc_refine.argtypes = [u8, C.POINTER(OrcSat), C.c_int, C.POINTER(OrcParams), C.c_void_p, C.c_int, C.c_void_p,
+                                 C.c_int]
+        L.orc_refine.restype = C.c_int
         L.orc_gen_capture.argtypes = [C.c_uint64, C.c_int, C.POINTER(OrcSat), C.c_int,
                                       C.POINTER(OrcSignal), C.c_int, u8]
         L.orc_gen_capture.restype = C.c_int
@@ -208,6 +212,20 @@ def search(packed, sats, sel=None, params=None, spectra=None, want_grid=False, n
     if rc != 0:
         raise RuntimeError("orc_search_pre failed: %d" % rc)
     return (out, grid) if want_grid else out
+
+
+def refine(packed, sats, records, params=None, nthreads=0):
+    """Oracle refinement of `records` (from search() on the same capture): FINE_DTYPE array, one per record."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    p = params or default_params()
+    assert packed.size == p.k_noncoh * BLOCK_BYTES, (packed.size, p.k_noncoh)
+    rec = np.ascontiguousarray(records, RECORD_DTYPE)
+    out = np.zeros(rec.size, FINE_DTYPE)
+    rc = lib().orc_refine(_u8(packed), sat_array(sats), len(sats), C.byref(p), rec.ctypes.data, rec.size,
+                          out.ctypes.data, nthreads)
+    if rc != 0:
+        raise RuntimeError("orc_refine failed: %d" % rc)
+    return out
 
 
 def gen_capture(seed, n_blocks, sats, signals):

@@ -26,7 +26,7 @@ def test_library_builds_and_exports_header_symbols():
     assert os.path.exists(path)
     L = C.CDLL(path)
     names = declared_functions()
-    assert len(names) >= 18
+    assert len(names) >= 19
     for n in names:
         assert hasattr(L, n), "libacq_b200.so does not export %s" % n
     # the ctypes binding covers the same set
@@ -41,6 +41,7 @@ def test_library_builds_and_exports_header_symbols():
 def test_struct_layouts_match_header():
     assert engine.RECORD_DTYPE.itemsize == 24  # acq_record
     assert engine.CELL_DTYPE.itemsize == 16    # acq_cell
+    assert engine.FINE_DTYPE.itemsize == 16    # acq_fine
     assert C.sizeof(_lib.AcqSat) == 16
     assert C.sizeof(_lib.AcqParams) == 32
 

@@ -441,3 +441,94 @@ def test_dropin_with_capture_file_source(gpu_required, golden_search, tmp_path):
     assert rx.samples == 2
     d.close()
     src.close()
+
+
+# ---------------------------------------------------------------- acquisition refinement
+def _compare_fine(gfine, ofine, rec):
+    g, o, r = np.asarray(gfine).reshape(-1), np.asarray(ofine).reshape(-1), np.asarray(rec).reshape(-1)
+    assert np.allclose(g["peak"], o["peak"], rtol=RTOL)
+    assert np.allclose(g["peak"], r["peak"], rtol=RTOL)  # the direct sum reproduces the FFT search's peak cell
+    # interpolation offsets: 2e-3 of a bin / of a /4 sample (fp32 sums of 16384 terms against the oracle's doubles)
+    assert np.abs(g["dop_hz"] - o["dop_hz"]).max() < 2e-3 * F.BIN_HZ, np.abs(g["dop_hz"] - o["dop_hz"]).max()
+    assert np.abs(g["code_fs"] - o["code_fs"]).max() < 8e-3, np.abs(g["code_fs"] - o["code_fs"]).max()
+    away = np.abs((o["code_fs"] % 1.0) - 0.5) > 0.02  # rounding to whole FS samples, away from the .5 boundary
+    assert np.array_equal(g["ca_shift"][away], o["ca_shift"][away])
+
+
+def test_refine_matches_oracle_and_injected_values(ref_engine, oracle):
+    table = S.reference_table()
+    sig = [(2, 4001, 3.3 * F.BIN_HZ, 50, 1.0), (10, 12346, -7.45 * F.BIN_HZ, 48, 2.0), (44, 30003, -6.2 * F.BIN_HZ, 50, 0.4)]
+    cap = synth.make_capture(77, 1, table, sig)
+    sel = np.array([2, 10, 44, 20, 58], np.int32)
+    rec = ref_engine.search(cap, sel=sel)
+    fine = ref_engine.refine(rec)
+    assert fine.shape == rec.shape
+    _compare_fine(fine, oracle.refine(cap, table, rec[0]), rec)
+    for i, (sat, tau, fd, _, _) in enumerate(sig):
+        period = 4 * (F.LAGS_E1B if table[sat][3] == S.E1B else F.LAGS_L1)
+        err = (float(fine["code_fs"][0, i]) - tau) % period
+        err = err - period if err > period / 2 else err
+        assert abs(fine["dop_hz"][0, i] - fd) < 0.25 * F.BIN_HZ and abs(err) < 2.0
+
+
+def test_refine_half_bins_noncoherent_and_batches(gpu_required, oracle):
+    table = S.navstar()
+    kw = dict(k_noncoh=4, half_bin=1, dop_lo=-20, dop_hi=20)
+    caps = [synth.make_capture(78 + c, 4, table, [(7, 8002 + c, (4.5 - c) * F.BIN_HZ, 46, 0.5), (12, 100, -3.1 * F.BIN_HZ, 46, 0.1)])
+            for c in range(3)]
+    sel = np.array([7, 12, 30], np.int32)
+    with F.AcqEngine(table, F.default_params(**kw)) as eng:
+        rec = eng.search(np.concatenate(caps), sel=sel)
+        fine = eng.refine(rec)
+        for c in range(3):
+            _compare_fine(fine[c], oracle.refine(caps[c], table, rec[c], params=oracle.default_params(**kw)), rec[c])
+        assert abs(fine["dop_hz"][0, 0] - 4.5 * F.BIN_HZ) < 0.25 * F.BIN_HZ
+        # refining again gives the same bytes (no state is consumed)
+        assert eng.refine(rec).tobytes() == fine.tobytes()
+
+
+def test_refine_error_paths(gpu_required):
+    table = S.navstar()
+    cap = synth.make_capture(5, 1, table, [(3, 400, 0.0, 50, 0.0)])
+    with F.AcqEngine(table) as eng:
+        with pytest.raises(F.AcqError):  # nothing searched yet
+            eng.refine(np.zeros(32, F.RECORD_DTYPE))
+        rec = eng.search(cap)
+        with pytest.raises(F.AcqError):  # wrong count
+            eng.refine(rec[0, :5])
+        bad = rec.copy()
+        bad["sat"][0, 0] = 7             # not the satellite of that slot
+        with pytest.raises(F.AcqError):
+            eng.refine(bad)
+        bad = rec.copy()
+        bad["lag"][0, 1] = 5000          # outside the 1 ms window
+        with pytest.raises(F.AcqError):
+            eng.refine(bad)
+        assert eng.refine(rec).shape == rec.shape
+
+
+def test_dropin_refined_handoff(gpu_required, golden_search):
+    """With acq_dropin_set_refine the shim hands ChanStart a ca_shift at FS-sample resolution (within one /4 sample of
+    lag * DECIM) and the bin nearest to the interpolated Doppler (at most one bin from the search's); the started
+    set, call order and units are those of the unrefined pass.  Literal and batch mode agree."""
+    from flydog_sdr_gps_b200 import dropin
+    cap = golden_search["captures"][0]
+    table = S.reference_table()
+    runs = {}
+    for mode in (dropin.LITERAL, dropin.BATCH):
+        for refine in (0, 1):
+            rx = dropin.MockReceiver(cap, free_chans=59)
+            d = dropin.Dropin(table, rx)
+            d.set_refine(refine)
+            d.search_pass(mode)
+            runs[mode, refine] = {e[2]: (e[3], e[4]) for e in rx.events if e[0] == "chan_start"}
+            d.close()
+    for mode in (dropin.LITERAL, dropin.BATCH):
+        plain, fine = runs[mode, 0], runs[mode, 1]
+        assert plain.keys() == fine.keys() and len(plain) >= 5
+        for sat in plain:
+            period = 4 * (F.LAGS_E1B if table[sat][3] == S.E1B else F.LAGS_L1)
+            dca = (fine[sat][1] - plain[sat][1] + period // 2) % period - period // 2
+            assert abs(dca) <= 4 and 0 <= fine[sat][1] < period
+            assert abs(fine[sat][0] - plain[sat][0]) <= 1
+    assert runs[dropin.LITERAL, 1] == runs[dropin.BATCH, 1]

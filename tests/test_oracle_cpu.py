@@ -229,3 +229,46 @@ def test_synth_capture_format():
     assert cap.dtype == np.uint8 and cap.size == 2 * 8192
     assert 0.48 < np.unpackbits(cap).mean() < 0.52
     assert np.array_equal(cap, synth.make_capture(1, 2, table, scenarios.signals("cfg1", 1)))
+
+
+def _code_err(code_fs, tau, period_fs):
+    e = (float(code_fs) - tau) % period_fs
+    return e - period_fs if e > period_fs / 2 else e
+
+
+def test_refinement_recovers_injected_doppler_and_code_phase(oracle):
+    """orc_refine: the directly evaluated peak equals the FFT search's peak, the interpolated
+    Doppler lands within a quarter bin and the code phase within 2 FS samples of what was injected (the search
+    alone is good to half a bin = 125 Hz and 4 FS samples)."""
+    table = S.reference_table()
+    bin_hz = 16.368e6 / 65536
+    sig = [(2, 4001, 3.3 * bin_hz, 50, 1.0), (10, 12346, -7.45 * bin_hz, 48, 2.0), (44, 30003, -6.2 * bin_hz, 50, 0.4)]
+    cap = synth.make_capture(77, 1, table, sig)
+    sel = np.array([2, 10, 44, 20], np.int32)
+    rec = oracle.search(cap, table, sel=sel)
+    fine = oracle.refine(cap, table, rec)
+    assert np.allclose(fine["peak"], rec["peak"], rtol=1e-4)  # same cell, direct sum against the inverse FFT
+    for i, (sat, tau, fd, _, _) in enumerate(sig):
+        L = 16368 if table[sat][3] == S.E1B else 4092
+        assert rec["snr"][i] >= 16
+        assert abs(fine["dop_hz"][i] - fd) < 0.25 * bin_hz, (sat, fine["dop_hz"][i], fd)
+        assert abs(_code_err(fine["code_fs"][i], tau, 4 * L)) < 2.0, (sat, fine["code_fs"][i], tau)
+        assert abs(fine["dop_hz"][i] - rec["dop"][i] * bin_hz) <= bin_hz          # stays inside the neighbour bins
+        assert abs(fine["code_fs"][i] - 4 * rec["lag"][i]) <= 4.0                  # and the neighbour lags
+        assert fine["ca_shift"][i] == int(np.rint(fine["code_fs"][i])) % (4 * L)
+
+
+def test_refinement_with_half_bins_and_noncoherent_blocks(oracle):
+    """K = 4 blocks, half-bin Doppler indices: the peak identity and the Doppler estimate hold with the per-block lag
+    advance (n + 16 b) and the pre-rotated capture spectrum of odd indices."""
+    table = S.navstar()
+    bin_hz = 16.368e6 / 65536
+    prm = oracle.default_params(k_noncoh=4, half_bin=1, dop_lo=-20, dop_hi=20)
+    cap = synth.make_capture(78, 4, table, [(7, 8002, 4.5 * bin_hz, 46, 0.5), (12, 100, -3.1 * bin_hz, 46, 0.1)])
+    rec = oracle.search(cap, table, sel=[7, 12], params=prm)
+    fine = oracle.refine(cap, table, rec, params=prm)
+    assert np.allclose(fine["peak"], rec["peak"], rtol=1e-4)
+    assert rec["dop"][0] == 9 and rec["dop"][1] in (-6, -7)
+    assert abs(fine["dop_hz"][0] - 4.5 * bin_hz) < 0.25 * bin_hz
+    assert abs(fine["dop_hz"][1] + 3.1 * bin_hz) < 0.25 * bin_hz
+    assert abs(_code_err(fine["code_fs"][0], 8002, 4 * 4092)) < 2.0
