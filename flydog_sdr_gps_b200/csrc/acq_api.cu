@@ -308,6 +308,14 @@ int check_search_args(acq_engine *e, const void *packed, int n_captures, const v
     return ACQ_OK;
 }
 
+// after set_selection: a search kernel launch indexes its tiles with 32 bits
+int check_tile_count(acq_engine *e, int n_captures)
+{
+    if ((double)n_captures * (double)e->n_slots * (double)e->n_dop > (double)acq::kMaxTilesPerLaunch)
+        return fail(ACQ_ERR_UNSUPPORTED, "search too large for one call (more than 2^31 - 1 tiles): split the captures");
+    return ACQ_OK;
+}
+
 int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel, acq_record *out,
                 acq_cell *grid, bool sync)
 {
@@ -315,6 +323,7 @@ int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int3
     if (rc) return rc;
     DeviceGuard g(e->device);
     if ((rc = set_selection(e, sel, n_sel))) return rc;
+    if ((rc = check_tile_count(e, n_captures))) return rc;
     if ((rc = ensure_scratch(e, n_captures, e->n_slots, true))) return rc;
     const size_t bytes = (size_t)n_captures * e->prm.k_noncoh * ACQ_BLOCK_BYTES;
     CU(cudaMemcpyAsync(e->d_packed, packed, bytes, cudaMemcpyHostToDevice, e->stream));
@@ -541,6 +550,7 @@ int acq_search_device(acq_engine *e, const uint8_t *packed_dev, int n_captures, 
         return fail(ACQ_ERR_ARG, "packed_dev must be 16-byte aligned (the front end stages it with bulk async copies)");
     DeviceGuard g(e->device);
     if ((rc = set_selection(e, sel, n_sel))) return rc;
+    if ((rc = check_tile_count(e, n_captures))) return rc;
     if ((rc = ensure_scratch(e, n_captures, e->n_slots, false))) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     e->last_captures = 0;  // spectra now belong to a search on the caller's stream: acq_refine does not apply

@@ -432,12 +432,15 @@ __device__ __forceinline__ Peak block_reduce_peak(Peak v, float *red_f, int *red
 
 struct TileIdx {
     int sat, slot, cap, d, dop, v;
+    // The host keeps a launch below 2^31 tiles (launch_search), so the decomposition runs on 32-bit unsigned
+    // divisions: every warp pays it once per tile, and a K = 1 tile is only four sub-FFTs long.
     __device__ __forceinline__ TileIdx(const SearchArgs &p, long long tile)
     {
-        d = (int)(tile % p.n_dop);
-        const long long cw = tile / p.n_dop;
-        const int wi = (int)(cw % p.n_work);
-        cap = (int)(cw / p.n_work);
+        const unsigned tl = (unsigned)tile, nd = (unsigned)p.n_dop, nw = (unsigned)p.n_work;
+        const unsigned cw = tl / nd;
+        d = (int)(tl - cw * nd);
+        cap = (int)(cw / nw);
+        const int wi = (int)(cw - (unsigned)cap * nw);
         const int2 wk = p.work[wi];
         sat = wk.x;
         slot = wk.y;
@@ -1364,7 +1367,7 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
 
 int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, bool pdl)
 {
-    if (a.n_tiles <= 0) return 0;
+    if (a.n_tiles <= 0 || a.n_tiles > kMaxTilesPerLaunch) return 0;
     const long long max_ctas = (long long)sm_count * 2;
     const int grid = (int)(a.n_tiles < max_ctas ? a.n_tiles : max_ctas);
     if (e1b) {
@@ -1380,7 +1383,7 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 
 int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st, bool pdl)
 {
-    if (a.n_tiles <= 0) return 0;
+    if (a.n_tiles <= 0 || a.n_tiles > kMaxTilesPerLaunch) return 0;
     const long long max_clusters = sm_count / 4;
     const int n_clusters = (int)(a.n_tiles < max_clusters ? a.n_tiles : max_clusters);
     launch_k(a.K > 1 ? k_search_e1b_cluster<true> : k_search_e1b_cluster<false>, 4 * n_clusters, 256,

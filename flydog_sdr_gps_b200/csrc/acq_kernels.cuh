@@ -20,6 +20,9 @@ struct SearchArgs {
     int n_work, n_slots, n_dop, dop_lo, half_bin, K, nvar, ext_len, Q;
 };
 
+// A search launch decomposes its tile index with 32-bit arithmetic; acq_api.cu refuses larger searches.
+constexpr long long kMaxTilesPerLaunch = 0x7fffffffLL;
+
 // host-side launchers (all asynchronous on `st`; each returns the number of kernels it launched)
 int launch_tables_init(const float2 *h_cC, const float *h_hb);
 int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, cudaStream_t st);
