@@ -91,6 +91,8 @@ struct acq_engine {
     acq_params prm{};
     std::vector<acq_sat> sats;
     int n_dop = 0, nvar = 1, Q = 0, ext_len = 0;
+    int sample_bits = 1;       // capture format: 1 = sign only (reference), 2 = sign plane + magnitude plane
+    size_t block_bytes = ACQ_BLOCK_BYTES;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     bool pending = false;
@@ -181,7 +183,7 @@ int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool own_packed)
         e->cap_blocks = blocks;
     }
     if (own_packed) {
-        int rc = grow(e->d_packed, e->cap_packed, blocks * ACQ_BLOCK_BYTES);
+        int rc = grow(e->d_packed, e->cap_packed, blocks * e->block_bytes);
         if (rc) return rc;
     }
     const size_t rows = (size_t)n_captures * n_slots;
@@ -252,7 +254,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const long long tiles_total = (long long)n_captures * e->n_slots * e->n_dop * K;
     const bool pdl = !prof && (e->pdl == 1 || (e->pdl < 0 && tiles_total <= 64LL * e->sm_count));
     if (prof) CU(cudaEventRecord(e->prof[0], st));
-    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, st);
+    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, st);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
     e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar, true, e->sm_count, st, pdl);
     if (prof) CU(cudaEventRecord(e->prof[2], st));
@@ -325,7 +327,7 @@ int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int3
     if ((rc = set_selection(e, sel, n_sel))) return rc;
     if ((rc = check_tile_count(e, n_captures))) return rc;
     if ((rc = ensure_scratch(e, n_captures, e->n_slots, true))) return rc;
-    const size_t bytes = (size_t)n_captures * e->prm.k_noncoh * ACQ_BLOCK_BYTES;
+    const size_t bytes = (size_t)n_captures * e->prm.k_noncoh * e->block_bytes;
     CU(cudaMemcpyAsync(e->d_packed, packed, bytes, cudaMemcpyHostToDevice, e->stream));
     e->last_captures = 0;
     if ((rc = enqueue_search(e, e->d_packed, n_captures, e->d_records, e->stream))) return rc;
@@ -360,7 +362,7 @@ int acq_params_default(acq_params *p)
     p->thr_l1 = 16.0f;   // MIN_SIG, gps/gps.h:60
     p->thr_e1b = 16.0f;  // gps/search.cpp:549
     p->wrap_mode = ACQ_WRAP_REFERENCE;
-    p->reserved = 0;
+    p->sample_bits = 1;  // the sampler's I_sign stream, gps/search.cpp:408-411
     return ACQ_OK;
 }
 
@@ -377,6 +379,8 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     if (prm.half_bin != 0 && prm.half_bin != 1) return fail(ACQ_ERR_ARG, "half_bin must be 0 or 1");
     if (prm.wrap_mode != ACQ_WRAP_REFERENCE && prm.wrap_mode != ACQ_WRAP_CIRCULAR)
         return fail(ACQ_ERR_ARG, "bad wrap_mode");
+    if (prm.sample_bits < 0 || prm.sample_bits > 2) return fail(ACQ_ERR_ARG, "sample_bits must be 1 or 2 (0 = 1)");
+    if (prm.sample_bits == 0) prm.sample_bits = 1;  // the member used to be "reserved, must be 0"
     const int max_idx = std::max(std::abs(prm.dop_lo), std::abs(prm.dop_hi));
     const int max_bins = prm.half_bin ? (max_idx + 1) / 2 + 1 : max_idx;
     if (max_bins > 2048) return fail(ACQ_ERR_ARG, "Doppler span too large (|bins| <= 2048)");
@@ -414,6 +418,8 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     e->sats.assign(sats, sats + n_sats);
     e->n_dop = prm.dop_hi - prm.dop_lo + 1;
     e->nvar = prm.half_bin ? 2 : 1;
+    e->sample_bits = prm.sample_bits;
+    e->block_bytes = ACQ_CAPTURE_BLOCK_BYTES(prm.sample_bits);
     e->Q = max_bins / 4 + 2;
     e->ext_len = kSub + 2 * e->Q;
 
@@ -647,10 +653,10 @@ int acq_get_capture_spectrum(acq_engine *e, const uint8_t *packed, int half_rot,
     int rc = ACQ_OK;
     cudaError_t ce = cudaSuccess;
     do {
-        if ((ce = cudaMalloc(&d_pk, ACQ_BLOCK_BYTES))) break;
+        if ((ce = cudaMalloc(&d_pk, e->block_bytes))) break;
         if ((ce = cudaMalloc(&d_x2, 2 * kN * sizeof(float2)))) break;
         if ((ce = cudaMalloc(&d_D, kN * sizeof(float2)))) break;
-        if ((ce = cudaMemcpy(d_pk, packed, ACQ_BLOCK_BYTES, cudaMemcpyHostToDevice))) break;
+        if ((ce = cudaMemcpy(d_pk, packed, e->block_bytes, cudaMemcpyHostToDevice))) break;
         const float2 *rotp = e->d_rot;
         if (half_rot && !rotp) {
             const double pi = 3.14159265358979323846264338327950288;
@@ -663,7 +669,7 @@ int acq_get_capture_spectrum(acq_engine *e, const uint8_t *packed, int half_rot,
             if ((ce = cudaMemcpy(d_rot, rot.data(), kN * sizeof(float2), cudaMemcpyHostToDevice))) break;
             rotp = d_rot;
         }
-        e->launches += launch_front_end(d_pk, d_x2, rotp, 1, half_rot ? 2 : 1, 1, e->stream);
+        e->launches += launch_front_end(d_pk, d_x2, rotp, 1, half_rot ? 2 : 1, 1, e->sample_bits, e->stream);
         const float2 *sel_x2 = d_x2 + (half_rot ? kN : 0);
         e->launches += launch_fwd_fft(sel_x2, d_D, e->d_tables, 1, false, e->sm_count, e->stream);
         if ((ce = cudaGetLastError())) break;

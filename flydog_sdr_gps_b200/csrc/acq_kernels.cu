@@ -1,6 +1,6 @@
 // acq_kernels.cu -- sm_100a kernels of the acquisition engine.
 //
-//   K1  k_front_end  : unpack 1-bit capture (TMA-staged), fs/4 XOR mix, both half-band /2 stages
+//   K1  k_front_end  : unpack 1-bit (or 2-bit sign/magnitude) capture (TMA-staged), fs/4 XOR mix, both half-band /2 stages
 //                      (+ optional half-bin pre-rotation, block delay)              (search.cpp:408-441)
 //   K6a k_hb1_code   : C/A / E1B(BOC) replica samples, first half-band /2            (search.cpp:250-275,315-337)
 //   K6a' k_hb2       : second half-band /2 of the replica                            (search.cpp:273-275)
@@ -62,16 +62,24 @@ constexpr int kFeOut = 1024;                   // x2 samples per CTA
 constexpr int kFeX1 = 2 * kFeOut + 30;         // x1 samples needed (2078)
 constexpr int kFeBytes = 544;                  // staged capture bytes (>= 524, multiple of 16)
 
+//
+// MAG (2-bit sign/magnitude capture, acq_params.sample_bits = 2 -- the MAX2769's native output, of which the
+// reference's FPGA keeps the sign only, verilog/gps/gps.v:50): a block is the sign plane (the 1-bit format above)
+// followed by a magnitude plane of the same layout; the mixed sample is (bit ? -1 : +1) * (mag ? 3 : 1).  Both
+// planes are staged by bulk copies on the same mbarrier.  The products with the taps stay exact roundings of
+// (+-1 | +-3) * c in the reference's summation order.
+template <bool MAG>
 __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ packed, float2 *__restrict__ x2,
                                                    const float2 *__restrict__ rot, int nvar, int K, int row0)
 {
     __shared__ __align__(16) uint8_t sbits[kFeBytes + 16];
+    __shared__ __align__(16) uint8_t mbits[MAG ? kFeBytes + 16 : 16];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ float2 x1s[kFeX1 + 2];
     const int t = threadIdx.x;
     pdl_launch_dependents();
     const int chunk = blockIdx.x;                      // 16 chunks per block
-    const uint8_t *pk = packed + (size_t)blockIdx.y * ACQ_BLOCK_BYTES + 512 * chunk;
+    const uint8_t *pk = packed + (size_t)blockIdx.y * (MAG ? 2 : 1) * ACQ_BLOCK_BYTES + 512 * chunk;
     const int avail = ACQ_BLOCK_BYTES - 512 * chunk;   // bytes of this block from the chunk start
     const int nbytes = avail < kFeBytes ? avail : kFeBytes;  // 512 for the last chunk: never read past the block
     const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
@@ -80,25 +88,24 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = nbytes + t; i < kFeBytes + 16; i += 256) sbits[i] = 0;  // zero tail (samples past the block)
+    for (int i = nbytes + t; i < kFeBytes + 16; i += 256) {  // zero tail (samples past the block)
+        sbits[i] = 0;
+        if (MAG) mbits[i] = 0;
+    }
     __syncthreads();
     if (t == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(nbytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((MAG ? 2 : 1) * nbytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
                      "l"(pk), "r"(nbytes), "r"(bar_a)
                      : "memory");
+        if (MAG)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(mbits)),
+                         "l"(pk + ACQ_BLOCK_BYTES), "r"(nbytes), "r"(bar_a)
+                         : "memory");
     }
     {   // every thread waits for the bytes to land (phase 0)
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "FE_WAIT:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
-            "@P1 bra FE_DONE;\n"
-            "bra FE_WAIT;\n"
-            "FE_DONE:\n"
-            "}\n" ::"r"(bar_a)
-            : "memory");
+        mbar_wait(bar_a, 0);
     }
     // ---- first half-band stage into shared memory: x1s[m] = x1[2*o0 + m]
     const int i_base = 4 * kFeOut * chunk;  // first capture sample of this chunk (= bit 0 of sbits)
@@ -108,6 +115,12 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
 #pragma unroll
         for (int k = 0; k < 5; k++) win |= (unsigned long long)sbits[(r0 >> 3) + k] << (8 * k);
         win >>= (r0 & 7);
+        unsigned long long mwin = 0;
+        if (MAG) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) mwin |= (unsigned long long)mbits[(r0 >> 3) + k] << (8 * k);
+            mwin >>= (r0 & 7);
+        }
         auto sample = [&](int j, float &xr, float &xi) {
             const int i = i_base + r0 + j;
             if (i < ACQ_NSAMPLES) {
@@ -115,8 +128,9 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
                 const unsigned ph = i & 3;
                 const unsigned lsin = (ph < 2) ? 1u : 0u;             // {1,1,0,0}
                 const unsigned lcos = (ph == 0 || ph == 3) ? 1u : 0u; // {1,0,0,1}
-                xr = (bit ^ lsin) ? -1.0f : 1.0f;
-                xi = (bit ^ lcos) ? -1.0f : 1.0f;
+                const float w = (MAG && ((unsigned)(mwin >> j) & 1u)) ? 3.0f : 1.0f;
+                xr = (bit ^ lsin) ? -w : w;
+                xi = (bit ^ lcos) ? -w : w;
             } else {  // zero padding past the end of the block (search.cpp:145)
                 xr = 0.0f;
                 xi = 0.0f;
@@ -1316,13 +1330,19 @@ cudaError_t search_kernels_configure()
     return cudaSuccess;
 }
 
-int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, cudaStream_t st)
+int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, int sample_bits,
+                     cudaStream_t st)
 {
     int launched = 0;
     for (int b0 = 0; b0 < n_blocks; b0 += 32768) {  // gridDim.y <= 65535
         const int nb = (n_blocks - b0 < 32768) ? (n_blocks - b0) : 32768;
-        k_front_end<<<dim3(kN / kFeOut, nb), 256, 0, st>>>(packed + (size_t)b0 * ACQ_BLOCK_BYTES,
-                                                          x2 + (size_t)b0 * nvar * kN, rot, nvar, K, b0);
+        const dim3 grid(kN / kFeOut, nb);
+        if (sample_bits == 2)
+            k_front_end<true><<<grid, 256, 0, st>>>(packed + (size_t)b0 * 2 * ACQ_BLOCK_BYTES, x2 + (size_t)b0 * nvar * kN,
+                                                    rot, nvar, K, b0);
+        else
+            k_front_end<false><<<grid, 256, 0, st>>>(packed + (size_t)b0 * ACQ_BLOCK_BYTES, x2 + (size_t)b0 * nvar * kN,
+                                                     rot, nvar, K, b0);
         launched++;
     }
     return launched;

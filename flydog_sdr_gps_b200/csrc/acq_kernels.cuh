@@ -25,7 +25,9 @@ constexpr long long kMaxTilesPerLaunch = 0x7fffffffLL;
 
 // host-side launchers (all asynchronous on `st`; each returns the number of kernels it launched)
 int launch_tables_init(const float2 *h_cC, const float *h_hb);
-int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, cudaStream_t st);
+// sample_bits: 1 = the reference's sign-only capture, 2 = sign plane + magnitude plane per block
+int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, int sample_bits,
+                     cudaStream_t st);
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
 int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st);
 // pdl: launch with programmatic stream serialization (the grid may become resident while the previous kernel of

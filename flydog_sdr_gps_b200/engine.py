@@ -95,6 +95,11 @@ class AcqEngine:
         return self.params.k_noncoh
 
     @property
+    def block_bytes(self):
+        """Bytes of one 65536-sample block in this engine's capture format (ACQ_CAPTURE_BLOCK_BYTES)."""
+        return 2 * BLOCK_BYTES if self.params.sample_bits == 2 else BLOCK_BYTES
+
+    @property
     def launch_count(self):
         return int(self._L.acq_launch_count(self._h))
 
@@ -130,7 +135,7 @@ class AcqEngine:
 
     def _packed(self, packed):
         a = np.ascontiguousarray(packed, np.uint8).reshape(-1)
-        per = self.k_noncoh * BLOCK_BYTES
+        per = self.k_noncoh * self.block_bytes
         if a.size == 0 or a.size % per:
             raise ValueError("packed must hold a whole number of captures of %d bytes" % per)
         return a, a.size // per
@@ -198,7 +203,7 @@ class AcqEngine:
 
     def capture_spectrum(self, packed_block, half_rot=0):
         a = np.ascontiguousarray(packed_block, np.uint8).reshape(-1)
-        assert a.size == BLOCK_BYTES
+        assert a.size == self.block_bytes
         x2 = np.zeros(2 * N, np.float32)
         D = np.zeros(2 * N, np.float32)
         _check(self._L.acq_get_capture_spectrum(self._h, a.ctypes.data, half_rot, x2.ctypes.data, D.ctypes.data))

@@ -1,4 +1,4 @@
-"""Synthetic 1-bit IF captures in the receiver's wire format (bench / smoke input data).
+"""Synthetic 1-bit (optionally 2-bit sign/magnitude) IF captures in the receiver's wire format (bench / smoke input data).
 
     s[i] = sum_k A_k * c_k(i + tau_k) * cos(2*pi*(FC + f_k)*i/FS + phi_k) + n[i],   n ~ N(0, 1)
     A_k  = sqrt(4 * 10^(CN0_k/10) / FS);   bit = (s < 0);   sample i -> bit (i & 7) of byte i >> 3
@@ -59,8 +59,21 @@ def sat_chips(row):
     return ca_chips(t1, t2), False
 
 
-def make_capture(seed, n_blocks, sats, signals):
-    """numpy generator.  signals: iterable of (sat, tau, doppler_hz, cn0_dbhz, phase).  Returns uint8[n_blocks*8192]."""
+def _planes(s, sample_bits, mag_thr):
+    """Quantise real samples s (noise sigma 1) to the capture wire format: sign bits, LSB first; with
+    sample_bits == 2 every 65536-sample block is its sign plane followed by its magnitude plane
+    (mag = |s| > mag_thr; include/acq_b200.h ACQ_CAPTURE_BLOCK_BYTES)."""
+    sign = np.packbits(s < 0, bitorder="little")
+    if sample_bits != 2:
+        return sign
+    mag = np.packbits(np.abs(s) > mag_thr, bitorder="little")
+    return np.concatenate([sign.reshape(-1, 1, BLOCK_BYTES), mag.reshape(-1, 1, BLOCK_BYTES)], axis=1).reshape(-1)
+
+
+def make_capture(seed, n_blocks, sats, signals, sample_bits=1, mag_thr=0.98):
+    """numpy generator.  signals: iterable of (sat, tau, doppler_hz, cn0_dbhz, phase).  Returns uint8[n_blocks*8192]
+    (sample_bits=2: uint8[n_blocks*16384], 2-bit sign/magnitude with the same sign bits; mag_thr in noise sigmas --
+    0.98 is the optimum of a 4-level quantiser with levels +-1, +-3, a magnitude duty cycle of about 1/3)."""
     rng = np.random.Generator(np.random.Philox(int(seed)))
     n = n_blocks * BLOCK_SAMPLES
     i = np.arange(n, dtype=np.int64)
@@ -74,7 +87,7 @@ def make_capture(seed, n_blocks, sats, signals):
         amp = np.sqrt(4.0 * 10.0 ** (cn0 / 10.0) / FS)
         cyc = (dop / FS * i) % 1.0 + 0.25 * (i & 3)
         s += amp * (1.0 - 2.0 * c) * np.cos(2.0 * np.pi * cyc + phase)
-    return np.packbits(s < 0, bitorder="little")
+    return _planes(s, sample_bits, mag_thr)
 
 
 def make_captures_torch(seed, n_captures, n_blocks, sats, signals_per_capture, device):

@@ -79,8 +79,20 @@ typedef struct acq_params {
     float thr_l1;       /* detection threshold, Navstar/QZSS. default 16 = MIN_SIG / -gsig (search.cpp:70,82-84) */
     float thr_e1b;      /* detection threshold, E1B.          default 16 (search.cpp:549) */
     int32_t wrap_mode;  /* ACQ_WRAP_REFERENCE (default) or ACQ_WRAP_CIRCULAR */
-    int32_t reserved;   /* must be 0 */
+    int32_t sample_bits; /* capture format (this member was "reserved, must be 0"): 0 or 1 = the reference's 1-bit
+                            sign-only capture; 2 = 2-bit sign/magnitude (extension, see ACQ_CAPTURE_BLOCK_BYTES) */
 } acq_params;
+
+/* Bytes of one 65536-sample capture block in the format `sample_bits` selects.
+ *   1 bit : ACQ_BLOCK_BYTES.  Sample i = bit i&7 of byte i>>3 -- the I_sign stream the reference's sampler
+ *           delivers (gps/search.cpp:408-411, verilog/gps/gps.v:50,156).
+ *   2 bits: 2 * ACQ_BLOCK_BYTES = the sign plane above followed by a MAGNITUDE plane of the same layout
+ *           (I_mag of the MAX2769, which the front end is already configured to produce -- dev/gps_fe.cpp:104 --
+ *           and the reference's FPGA drops).  A sample is (sign ? -1 : +1) * (mag ? 3 : 1), the MAX2769's
+ *           sign/magnitude levels, before the same fs/4 XOR mix.  With an all-zero magnitude plane the results
+ *           are bit-identical to the 1-bit format.  No reference counterpart; the oracle carries the same
+ *           definition (orc_params.sample_bits). */
+#define ACQ_CAPTURE_BLOCK_BYTES(sample_bits) ((sample_bits) == 2 ? 2 * ACQ_BLOCK_BYTES : ACQ_BLOCK_BYTES)
 
 /* One record per (capture, searched satellite): what Correlate() returns (gps/search.cpp:453,495-498)
  * plus the two powers its snr is made of.  24 bytes. */
@@ -118,7 +130,7 @@ typedef struct acq_engine acq_engine;
 const char *acq_last_error(void);
 int acq_abi_version(void);
 
-/* Reference defaults: -20..+20 bins, full bins, K=1, thresholds 16, reference wrap. */
+/* Reference defaults: -20..+20 bins, full bins, K=1, thresholds 16, reference wrap, 1-bit captures. */
 int acq_params_default(acq_params *p);
 
 /* Replaces SearchInit()'s spectrum build (gps/search.cpp:183-346): generates the C/A (LFSR,
@@ -132,8 +144,9 @@ int acq_destroy(acq_engine *e);
 
 /* Replaces the DSP of Sample() (everything after the SPI reads, gps/search.cpp:408-447) and
  * Correlate() (gps/search.cpp:453-499) for n_sel satellites on n_captures captures in one call.
- *   packed : HOST memory, n_captures * k_noncoh * ACQ_BLOCK_BYTES bytes; capture c occupies
- *            k_noncoh consecutive blocks.  (Pinned memory avoids a staging copy.)
+ *   packed : HOST memory, n_captures * k_noncoh * ACQ_CAPTURE_BLOCK_BYTES(sample_bits) bytes (ACQ_BLOCK_BYTES per
+ *            block in the reference's 1-bit format); capture c occupies k_noncoh consecutive blocks.
+ *            (Pinned memory avoids a staging copy.)
  *   sel    : n_sel table indices to search, or NULL for the whole table (then n_sel is ignored).
  *   out    : HOST memory, n_captures * n_sel records, record [c*n_sel + s].
  * Synchronous: returns when `out` is filled. */
@@ -178,7 +191,7 @@ int acq_detected(const acq_engine *e, const acq_record *r);
 /* Code spectrum of table entry `sat` as the reference stores it (first copy of code[sat],
  * gps/search.cpp:283): ACQ_FFT_LEN interleaved complex floats to HOST memory. */
 int acq_get_code_spectrum(acq_engine *e, int sat, float *out);
-/* Front end of one block: packed (HOST, ACQ_BLOCK_BYTES) -> decimated baseband `x2` (the forward
+/* Front end of one block: packed (HOST, one block in the engine's capture format) -> decimated baseband `x2` (the forward
  * FFT's input, gps/search.cpp:437-445) and spectrum `D` (fwd_buf after search.cpp:447), each
  * ACQ_FFT_LEN interleaved complex floats, either may be NULL.  half_rot=1 selects the
  * half-bin pre-rotated variant. */

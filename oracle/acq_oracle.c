@@ -48,6 +48,7 @@ void orc_params_default(orc_params *p)
     p->thr_l1 = 16.0f;  /* MIN_SIG, gps/gps.h:60, search.cpp:70 */
     p->thr_e1b = 16.0f; /* search.cpp:549 */
     p->wrap_mode = ORC_WRAP_REFERENCE;
+    p->sample_bits = 1; /* I_sign only, search.cpp:408-411 */
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -190,13 +191,23 @@ void orc_code_spectrum(const orc_sat *sat, float *out)
  * ---------------------------------------------------------------------------------------- */
 void orc_capture_baseband(const uint8_t *packed, int half_rot, float *out)
 {
+    orc_capture_baseband_sm(packed, 1, half_rot, out);
+}
+
+/* sample_bits == 2 (extension, no reference counterpart): the magnitude plane follows the sign plane; the mixed
+ * +-1 of the reference is scaled by 3 where the magnitude bit is set (x * 1.0f is exact, so sample_bits == 1 and
+ * an all-zero magnitude plane give the reference's values bit for bit). */
+void orc_capture_baseband_sm(const uint8_t *packed, int sample_bits, int half_rot, float *out)
+{
     static const int lo_sin[4] = {1, 1, 0, 0};
     static const int lo_cos[4] = {1, 0, 0, 1};
     float *buf = (float *)malloc(sizeof(float) * 2 * (NS + 2 * NTAPS));
+    const uint8_t *mag = (sample_bits == 2) ? packed + ORC_BLOCK_BYTES : NULL;
     for (int i = 0; i < NS; i++) {
         const int bit = (packed[i >> 3] >> (i & 7)) & 1;
-        buf[2 * i] = bipolar(bit ^ lo_sin[i & 3]);
-        buf[2 * i + 1] = bipolar(bit ^ lo_cos[i & 3]);
+        const float w = (mag && ((mag[i >> 3] >> (i & 7)) & 1)) ? 3.0f : 1.0f;
+        buf[2 * i] = w * bipolar(bit ^ lo_sin[i & 3]);
+        buf[2 * i + 1] = w * bipolar(bit ^ lo_cos[i & 3]);
     }
     int n = NS;
     n = orc_hb_decimate(n, buf);
@@ -334,7 +345,7 @@ int orc_search_pre(const uint8_t *packed, const orc_sat *sats, int n_sats, const
         const int b = bv / nvar, v = bv % nvar;
         float *scratch = (float *)malloc(sizeof(float) * 2 * N);
         float *d = D + (size_t)bv * 2 * N;
-        orc_capture_baseband(packed + (size_t)b * ORC_BLOCK_BYTES, v, d);
+        orc_capture_baseband_sm(packed + (size_t)b * ORC_CAPTURE_BLOCK_BYTES(prm->sample_bits), prm->sample_bits, v, d);
         orc_fft_execute(g_fwd, d, scratch);
         free(scratch);
     }
@@ -420,7 +431,8 @@ int orc_refine(const uint8_t *packed, const orc_sat *sats, int n_sats, const orc
     for (int bv = 0; bv < K * nvar; bv++) {
         float *scratch = (float *)malloc(sizeof(float) * 2 * N);
         float *d = D + (size_t)bv * 2 * N;
-        orc_capture_baseband(packed + (size_t)(bv / nvar) * ORC_BLOCK_BYTES, bv % nvar, d);
+        orc_capture_baseband_sm(packed + (size_t)(bv / nvar) * ORC_CAPTURE_BLOCK_BYTES(prm->sample_bits), prm->sample_bits,
+                                bv % nvar, d);
         orc_fft_execute(g_fwd, d, scratch);
         free(scratch);
     }
@@ -514,7 +526,13 @@ static inline uint64_t splitmix64(uint64_t x)
 int orc_gen_capture(uint64_t seed, int n_blocks, const orc_sat *sats, int n_sats, const orc_signal *sig,
                     int n_sig, uint8_t *packed)
 {
-    if (n_blocks < 1 || n_sig < 0 || !packed) return -1;
+    return orc_gen_capture_sm(seed, n_blocks, sats, n_sats, sig, n_sig, 1, 0.0, packed);
+}
+
+int orc_gen_capture_sm(uint64_t seed, int n_blocks, const orc_sat *sats, int n_sats, const orc_signal *sig,
+                       int n_sig, int sample_bits, double mag_thr, uint8_t *packed)
+{
+    if (n_blocks < 1 || n_sig < 0 || !packed || (sample_bits != 1 && sample_bits != 2)) return -1;
     const double FS = 16.368e6, two_pi = 6.283185307179586476925286766559;
     uint8_t *chips = (uint8_t *)malloc((size_t)(n_sig > 0 ? n_sig : 1) * 4092);
     int *codelen = (int *)malloc(sizeof(int) * (n_sig > 0 ? n_sig : 1));
@@ -538,7 +556,7 @@ int orc_gen_capture(uint64_t seed, int n_blocks, const orc_sat *sats, int n_sats
     const uint64_t key = splitmix64(seed ^ 0xA5A5A5A55A5A5A5Aull);
 #pragma omp parallel for schedule(static)
     for (long by = 0; by < total_bytes; by++) {
-        unsigned byte = 0;
+        unsigned byte = 0, mbyte = 0;
         for (int bb = 0; bb < 8; bb++) {
             const long i = by * 8 + bb;
             const uint64_t z1 = splitmix64(key + 2 * (uint64_t)i);
@@ -558,8 +576,15 @@ int orc_gen_capture(uint64_t seed, int n_blocks, const orc_sat *sats, int n_sats
                 s += amp[k] * sgn * cos(two_pi * cyc + sig[k].phase);
             }
             byte |= (unsigned)(s < 0.0) << bb;
+            mbyte |= (unsigned)(fabs(s) > mag_thr) << bb;
         }
-        packed[by] = (uint8_t)byte;
+        if (sample_bits == 2) { /* block = [sign plane][magnitude plane] */
+            const long blk = by / ORC_BLOCK_BYTES, off = by % ORC_BLOCK_BYTES;
+            packed[blk * 2 * ORC_BLOCK_BYTES + off] = (uint8_t)byte;
+            packed[blk * 2 * ORC_BLOCK_BYTES + ORC_BLOCK_BYTES + off] = (uint8_t)mbyte;
+        } else {
+            packed[by] = (uint8_t)byte;
+        }
     }
     free(chips);
     free(codelen);

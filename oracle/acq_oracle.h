@@ -48,7 +48,15 @@ typedef struct {
     float thr_l1;           /* detection threshold for Navstar/QZSS (minimum_sig, search.cpp:70,549) */
     float thr_e1b;          /* detection threshold for E1B (16, search.cpp:549) */
     int32_t wrap_mode;      /* ORC_WRAP_REFERENCE (default) or ORC_WRAP_CIRCULAR, see below */
+    int32_t sample_bits;    /* 1 = reference capture format (sign only, search.cpp:408-411).  2 = extension: each
+                               65536-sample block is its sign plane (that format) followed by a magnitude plane of
+                               the same layout; sample value (sign ? -1 : +1) * (mag ? 3 : 1) -- the MAX2769's
+                               sign/magnitude levels (dev/gps_fe.cpp:104; the reference FPGA drops I_mag,
+                               verilog/gps/gps.v:50).  0 is read as 1. */
 } orc_params;
+
+/* bytes of one capture block in the format `sample_bits` selects */
+#define ORC_CAPTURE_BLOCK_BYTES(sample_bits) ((sample_bits) == 2 ? 2 * ORC_BLOCK_BYTES : ORC_BLOCK_BYTES)
 
 /* How code-spectrum bins beyond the end of a satellite's row are fetched for NEGATIVE Doppler.
  *
@@ -100,6 +108,8 @@ void orc_code_spectrum(const orc_sat *sat, float *out);
 /* 8192 packed bytes -> mixed, /4 decimated baseband (search.cpp:398-442). out: 2*16384 floats.
  * half_rot=1 additionally multiplies sample n by exp(-j*pi*n/16384) (half-bin extension). */
 void orc_capture_baseband(const uint8_t *packed, int half_rot, float *out);
+/* Same for one block in the `sample_bits` format (1: identical to orc_capture_baseband). */
+void orc_capture_baseband_sm(const uint8_t *block, int sample_bits, int half_rot, float *out);
 /* capture_baseband + forward FFT (search.cpp:447). */
 void orc_capture_spectrum(const uint8_t *packed, int half_rot, float *out);
 /* forward / backward 16384-point FFT, in place (sign -1 / +1). */
@@ -149,6 +159,12 @@ typedef struct {
 /* Fills n_blocks*8192 bytes. */
 int orc_gen_capture(uint64_t seed, int n_blocks, const orc_sat *sats, int n_sats, const orc_signal *sig,
                     int n_sig, uint8_t *packed);
+/* Same signal and noise (the sign planes equal orc_gen_capture's output for the same seed) quantised to
+ * `sample_bits`: with 2, block b is [sign plane 8192 B][magnitude plane 8192 B], mag = (|s| > mag_thr) with s in
+ * units of the noise sigma (an AGC holding the magnitude duty cycle near 1/3 corresponds to mag_thr ~ 0.98).
+ * Fills n_blocks * ORC_CAPTURE_BLOCK_BYTES(sample_bits) bytes. */
+int orc_gen_capture_sm(uint64_t seed, int n_blocks, const orc_sat *sats, int n_sats, const orc_signal *sig,
+                       int n_sig, int sample_bits, double mag_thr, uint8_t *packed);
 
 #ifdef __cplusplus
 }

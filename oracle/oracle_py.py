@@ -27,7 +27,7 @@ class OrcSat(C.Structure):
 class OrcParams(C.Structure):
     _fields_ = [("dop_lo", C.c_int32), ("dop_hi", C.c_int32), ("half_bin", C.c_int32),
                 ("k_noncoh", C.c_int32), ("thr_l1", C.c_float), ("thr_e1b", C.c_float),
-                ("wrap_mode", C.c_int32)]
+                ("wrap_mode", C.c_int32), ("sample_bits", C.c_int32)]
 
 
 class OrcSignal(C.Structure):
@@ -70,6 +70,7 @@ def lib():
         L.orc_code_baseband.argtypes = [C.POINTER(OrcSat), fp]
         L.orc_code_spectrum.argtypes = [C.POINTER(OrcSat), fp]
         L.orc_capture_baseband.argtypes = [u8, C.c_int, fp]
+        L.orc_capture_baseband_sm.argtypes = [u8, C.c_int, C.c_int, fp]
         L.orc_capture_spectrum.argtypes = [u8, C.c_int, fp]
         L.orc_fft16384.argtypes = [fp, C.c_int]
         L.orc_search_pre.argtypes = [u8, C.POINTER(OrcSat), C.c_int, fp, C.POINTER(C.c_int32), C.c_int,
@@ -81,6 +82,9 @@ def lib():
         L.orc_gen_capture.argtypes = [C.c_uint64, C.c_int, C.POINTER(OrcSat), C.c_int,
                                       C.POINTER(OrcSignal), C.c_int, u8]
         L.orc_gen_capture.restype = C.c_int
+        L.orc_gen_capture_sm.argtypes = [C.c_uint64, C.c_int, C.POINTER(OrcSat), C.c_int,
+                                         C.POINTER(OrcSignal), C.c_int, C.c_int, C.c_double, u8]
+        L.orc_gen_capture_sm.restype = C.c_int
         _lib = L
     return _lib
 
@@ -169,10 +173,16 @@ def code_spectrum(sat):
     return out.view(np.complex64)
 
 
-def capture_baseband(packed, half_rot=0):
+def block_bytes(sample_bits):
+    """Bytes of one 65536-sample block: 8192 (sign only) or 16384 (sign plane + magnitude plane)."""
+    return 2 * BLOCK_BYTES if sample_bits == 2 else BLOCK_BYTES
+
+
+def capture_baseband(packed, half_rot=0, sample_bits=1):
     packed = np.ascontiguousarray(packed, np.uint8)
+    assert packed.size == block_bytes(sample_bits)
     out = np.zeros(2 * N, np.float32)
-    lib().orc_capture_baseband(_u8(packed), half_rot, _fp(out))
+    lib().orc_capture_baseband_sm(_u8(packed), sample_bits, half_rot, _fp(out))
     return out.view(np.complex64)
 
 
@@ -194,7 +204,7 @@ def search(packed, sats, sel=None, params=None, spectra=None, want_grid=False, n
     Returns records (structured array, one per selected sat) and optionally the (n_sel, n_dop) grid."""
     packed = np.ascontiguousarray(packed, np.uint8)
     p = params or default_params()
-    assert packed.size == p.k_noncoh * BLOCK_BYTES, (packed.size, p.k_noncoh)
+    assert packed.size == p.k_noncoh * block_bytes(p.sample_bits), (packed.size, p.k_noncoh, p.sample_bits)
     arr = sat_array(sats)
     n_sel = len(sats) if sel is None else len(sel)
     sel_a = None if sel is None else np.ascontiguousarray(sel, np.int32)
@@ -218,7 +228,7 @@ def refine(packed, sats, records, params=None, nthreads=0):
     """Oracle refinement of `records` (from search() on the same capture): FINE_DTYPE array, one per record."""
     packed = np.ascontiguousarray(packed, np.uint8)
     p = params or default_params()
-    assert packed.size == p.k_noncoh * BLOCK_BYTES, (packed.size, p.k_noncoh)
+    assert packed.size == p.k_noncoh * block_bytes(p.sample_bits), (packed.size, p.k_noncoh, p.sample_bits)
     rec = np.ascontiguousarray(records, RECORD_DTYPE)
     out = np.zeros(rec.size, FINE_DTYPE)
     rc = lib().orc_refine(_u8(packed), sat_array(sats), len(sats), C.byref(p), rec.ctypes.data, rec.size,
@@ -228,8 +238,9 @@ def refine(packed, sats, records, params=None, nthreads=0):
     return out
 
 
-def gen_capture(seed, n_blocks, sats, signals):
-    """signals: iterable of dicts/tuples (sat, tau, doppler_hz, cn0_dbhz, phase[, flip_ms])."""
+def gen_capture(seed, n_blocks, sats, signals, sample_bits=1, mag_thr=0.98):
+    """signals: iterable of dicts/tuples (sat, tau, doppler_hz, cn0_dbhz, phase[, flip_ms]).
+    sample_bits=2: sign plane + magnitude plane per block, mag = |s| > mag_thr noise sigmas (same sign bits)."""
     arr = sat_array(sats)
     sig = (OrcSignal * max(1, len(signals)))()
     for i, s in enumerate(signals):
@@ -239,10 +250,11 @@ def gen_capture(seed, n_blocks, sats, signals):
         sig[i].sat, sig[i].tau = int(s[0]), int(s[1])
         sig[i].doppler_hz, sig[i].cn0_dbhz, sig[i].phase = float(s[2]), float(s[3]), float(s[4])
         sig[i].flip_ms = int(s[5])
-    out = np.zeros(n_blocks * BLOCK_BYTES, np.uint8)
-    rc = lib().orc_gen_capture(int(seed), n_blocks, arr, len(sats), sig, len(signals), _u8(out))
+    out = np.zeros(n_blocks * block_bytes(sample_bits), np.uint8)
+    rc = lib().orc_gen_capture_sm(int(seed), n_blocks, arr, len(sats), sig, len(signals), int(sample_bits),
+                                  float(mag_thr), _u8(out))
     if rc != 0:
-        raise RuntimeError("orc_gen_capture failed: %d" % rc)
+        raise RuntimeError("orc_gen_capture_sm failed: %d" % rc)
     return out
 
 

@@ -51,6 +51,7 @@ def test_defaults_are_the_reference_constants():
     assert (p.dop_lo, p.dop_hi, p.half_bin, p.k_noncoh) == (-20, 20, 0, 1)  # gps/search.cpp:465
     assert p.thr_l1 == 16.0 and p.thr_e1b == 16.0                            # gps/gps.h:60, search.cpp:549
     assert p.wrap_mode == engine.WRAP_REFERENCE
+    assert p.sample_bits == 1                                                # I_sign only, search.cpp:408-411
     assert _lib.load().acq_abi_version() == 1
 
 
@@ -76,6 +77,10 @@ def test_argument_errors_without_gpu():
     assert L.acq_create(C.byref(h), None, None, 0, 0) == -1
     assert b"satellite table" in L.acq_last_error()
     assert L.acq_destroy(None) == 0
+    # parameter validation precedes the device probe: an unknown capture format is an argument error everywhere
+    sat = _lib.AcqSat(1, 2, 6, 0)
+    assert L.acq_create(C.byref(h), C.byref(engine.default_params(sample_bits=3)), C.byref(sat), 1, 0) == -1
+    assert b"sample_bits" in L.acq_last_error()
 
 
 def test_product_never_imports_the_oracle():

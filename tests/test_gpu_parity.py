@@ -532,3 +532,46 @@ def test_dropin_refined_handoff(gpu_required, golden_search):
             assert abs(dca) <= 4 and 0 <= fine[sat][1] < period
             assert abs(fine[sat][0] - plain[sat][0]) <= 1
     assert runs[dropin.LITERAL, 1] == runs[dropin.BATCH, 1]
+
+
+def test_sign_magnitude_captures(gpu_required, oracle):
+    """2-bit sign/magnitude capture format (acq_params.sample_bits = 2, an extension: the MAX2769 produces I_mag,
+    the reference's FPGA drops it).  Front end bit-exact against the oracle's definition, search parity for K = 1
+    and for half-bin K = 3 sums, and an all-zero magnitude plane equals the 1-bit engine byte for byte."""
+    table = S.navstar()
+    sig = scenarios.signals("cfg1", 2)
+    c1 = synth.make_capture(2, 1, table, sig)
+    c2 = synth.make_capture(2, 1, table, sig, sample_bits=2)
+    with F.AcqEngine(table) as e1, F.AcqEngine(table, F.default_params(sample_bits=2)) as e2:
+        assert e2.block_bytes == 16384 and e1.block_bytes == 8192
+        x2, D = e2.capture_spectrum(c2)
+        assert np.array_equal(x2, oracle.capture_baseband(c2, 0, 2))
+        x2h, _ = e2.capture_spectrum(c2, 1)
+        assert np.array_equal(x2h, oracle.capture_baseband(c2, 1, 2))
+        rec, grid = e2.search(c2, want_grid=True)
+        orec, ogrid = oracle.search(c2, table, params=oracle.default_params(sample_bits=2), want_grid=True)
+        compare_records(rec[0], orec, ogrid, -20, 16.0, ggrid=grid[0])
+        one = e1.search(c1)
+        strong = one[0]["snr"] >= 30
+        assert strong.sum() >= 3 and (rec[0]["snr"][strong] > one[0]["snr"][strong]).all()  # less quantisation loss
+        assert np.array_equal(rec[0]["lag"][strong], one[0]["lag"][strong])
+        z = np.concatenate([c1, np.zeros(8192, np.uint8)])
+        assert e2.search(z).tobytes() == one.tobytes()
+        # two captures in one call: capture stride is 16384 bytes
+        both = e2.search(np.concatenate([z, c2]))
+        assert both[0].tobytes() == one[0].tobytes() and both[1].tobytes() == rec[0].tobytes()
+        with pytest.raises(ValueError):
+            e2.search(c1)  # a 1-bit capture is half a block in this engine's format
+    kw = dict(dop_lo=-12, dop_hi=12, half_bin=1, k_noncoh=3, thr_l1=8.0, sample_bits=2)
+    sig = [(4, 5000, 2.5 * F.BIN_HZ, 40, 0.2), (20, 16000, -1.0 * F.BIN_HZ, 41, 1.2)]
+    cap = synth.make_capture(12, 3, table, sig, sample_bits=2)
+    sel = np.array([4, 20, 7], np.int32)
+    with F.AcqEngine(table, F.default_params(**kw)) as eng:
+        rec, grid = eng.search(cap, sel=sel, want_grid=True)
+        fine = eng.refine(rec)
+    orec, ogrid = oracle.search(cap, table, sel=sel, params=oracle.default_params(**kw), want_grid=True)
+    compare_records(rec[0], orec, ogrid, kw["dop_lo"], kw["thr_l1"], ggrid=grid[0], max_ties=1)
+    assert rec[0]["dop"][0] == 5 and rec[0]["dop"][1] == -2
+    assert np.allclose(fine[0]["peak"], rec[0]["peak"], rtol=1e-4)
+    with pytest.raises(F.AcqError):
+        F.AcqEngine(table, F.default_params(sample_bits=3))

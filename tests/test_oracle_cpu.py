@@ -272,3 +272,79 @@ def test_refinement_with_half_bins_and_noncoherent_blocks(oracle):
     assert abs(fine["dop_hz"][0] - 4.5 * bin_hz) < 0.25 * bin_hz
     assert abs(fine["dop_hz"][1] + 3.1 * bin_hz) < 0.25 * bin_hz
     assert abs(_code_err(fine["code_fs"][0], 8002, 4 * 4092)) < 2.0
+
+
+def _half_band_f64(x):
+    """Half-band /2 of search.cpp:140-166 in double precision (zero padding past the end, float-narrowed taps)."""
+    taps = np.zeros(31)
+    taps[0::2] = [-0.010233, 0.010668, -0.016324, 0.024377, -0.036482, 0.056990, -0.101993, 0.316926,
+                  0.316926, -0.101993, 0.056990, -0.036482, 0.024377, -0.016324, 0.010668, -0.010233]
+    taps[15] = 0.500009
+    taps = taps.astype(np.float32).astype(np.float64)
+    xp = np.concatenate([x.astype(np.complex128), np.zeros(31, np.complex128)])
+    out = np.zeros(len(x) // 2, np.complex128)
+    for j in np.flatnonzero(taps):
+        out += taps[j] * xp[j:j + len(x):2]
+    return out
+
+
+def test_sign_magnitude_capture_format(oracle):
+    """2-bit sign/magnitude captures (extension; include/acq_b200.h ACQ_CAPTURE_BLOCK_BYTES): a block is the reference's
+    sign plane followed by a magnitude plane, sample = (sign ? -1 : +1) * (mag ? 3 : 1)."""
+    table = S.navstar()
+    sig = scenarios.signals("cfg1", 1)
+    c1 = synth.make_capture(1, 2, table, sig)
+    c2 = synth.make_capture(1, 2, table, sig, sample_bits=2)
+    assert c2.size == 2 * 16384
+    planes = c2.reshape(2, 2, 8192)
+    assert np.array_equal(planes[:, 0].reshape(-1), c1)                  # same sign bits as the 1-bit capture
+    assert 0.30 < np.unpackbits(planes[:, 1]).mean() < 0.36              # |s| > 0.98 sigma: about one third
+    g1 = oracle.gen_capture(5, 2, table, sig)
+    g2 = oracle.gen_capture(5, 2, table, sig, sample_bits=2)
+    assert np.array_equal(g2.reshape(2, 2, 8192)[:, 0].reshape(-1), g1)
+    # an all-zero magnitude plane reproduces the reference's 1-bit front end bit for bit
+    blk = c1[:8192]
+    z = np.concatenate([blk, np.zeros(8192, np.uint8)])
+    assert np.array_equal(oracle.capture_baseband(z, 0, 2), oracle.capture_baseband(blk))
+    assert np.array_equal(oracle.capture_baseband(z, 1, 2), oracle.capture_baseband(blk, 1))
+    # a set magnitude bit scales the mixed sample by 3: all-ones plane = 3 x the 1-bit baseband (exact in fp32: every
+    # product and partial sum scales by 3 only up to rounding, so compare to 1e-6)
+    o = np.concatenate([blk, np.full(8192, 0xFF, np.uint8)])
+    b3 = oracle.capture_baseband(o, 0, 2)
+    b1 = oracle.capture_baseband(blk)
+    assert np.abs(b3 - 3 * b1).max() < 1e-5 * np.abs(b1).max()
+    # independent restatement in double precision
+    blk2 = c2[:16384]
+    bits = np.unpackbits(blk2[:8192], bitorder="little").astype(np.int64)
+    mag = np.unpackbits(blk2[8192:], bitorder="little").astype(np.int64)
+    i = np.arange(65536)
+    w = 1.0 + 2.0 * mag
+    x0 = w * (1.0 - 2.0 * (bits ^ np.array([1, 1, 0, 0])[i & 3])) + 1j * w * (1.0 - 2.0 * (bits ^ np.array([1, 0, 0, 1])[i & 3]))
+    want = _half_band_f64(_half_band_f64(x0))
+    got = oracle.capture_baseband(blk2, 0, 2)
+    assert np.abs(got - want).max() < 2e-6 * np.abs(want).max()
+
+
+def test_sign_magnitude_search_gains_over_one_bit(oracle):
+    """Same signals, same noise: the 4-level capture loses 0.55 dB to quantisation, the sign-only one 1.96 dB, so
+    strong satellites come out with a visibly larger peak-to-noise ratio and identical decisions."""
+    table = S.navstar()
+    sig = [(3, 4000, 4 * 249.755859375, 47, 0.3), (17, 9000, -11 * 249.755859375, 46, 1.3), (25, 120, 0.0, 48, 2.0)]
+    gains = []
+    for seed in (1, 2, 3):
+        c1 = synth.make_capture(seed, 1, table, sig)
+        c2 = synth.make_capture(seed, 1, table, sig, sample_bits=2)
+        r1 = oracle.search(c1, table, sel=[3, 17, 25])
+        r2 = oracle.search(c2, table, sel=[3, 17, 25], params=oracle.default_params(sample_bits=2))
+        assert np.array_equal(r1["dop"], r2["dop"]) and np.array_equal(r1["lag"], r2["lag"])
+        assert np.array_equal(r2["dop"], [4, -11, 0]) and np.array_equal(r2["lag"], [1000, 2250, 30])
+        gains.append(r2["snr"] / r1["snr"])
+    g = np.mean(gains)
+    assert 1.15 < g < 1.7, g   # 1.41 dB in amplitude^2 terms ~ x1.38 on a peak-dominated max/mean ratio
+    # K = 2 blocks of a 2-bit capture: block stride is 16384 bytes
+    c2 = synth.make_capture(9, 2, table, sig, sample_bits=2)
+    prm = oracle.default_params(sample_bits=2, k_noncoh=2)
+    r = oracle.search(c2, table, sel=[3, 17, 25], params=prm)
+    assert np.array_equal(r["dop"], [4, -11, 0]) and np.array_equal(r["lag"], [1000, 2250, 30])
+    fine = oracle.refine(c2, table, r, params=prm)
+    assert np.allclose(fine["peak"], r["peak"], rtol=1e-4)
