@@ -14,7 +14,8 @@ class AcqSat(C.Structure):
 
 class AcqParams(C.Structure):
     _fields_ = [("dop_lo", C.c_int32), ("dop_hi", C.c_int32), ("half_bin", C.c_int32), ("k_noncoh", C.c_int32),
-                ("thr_l1", C.c_float), ("thr_e1b", C.c_float), ("wrap_mode", C.c_int32), ("sample_bits", C.c_int32)]
+                ("thr_l1", C.c_float), ("thr_e1b", C.c_float), ("wrap_mode", C.c_int32), ("sample_bits", C.c_int32),
+                ("code_doppler", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 # every symbol include/acq_b200.h declares: (name, restype, argtypes)

@@ -91,6 +91,7 @@ struct acq_engine {
     acq_params prm{};
     std::vector<acq_sat> sats;
     int n_dop = 0, nvar = 1, Q = 0, ext_len = 0;
+    int n_shift = 1, smax = 0, cd_div = 385;  // code-Doppler compensation: shifted copies per spectrum (1 = off)
     int sample_bits = 1;       // capture format: 1 = sign only (reference), 2 = sign plane + magnitude plane
     size_t block_bytes = ACQ_BLOCK_BYTES;
     cudaStream_t stream = nullptr;
@@ -178,8 +179,8 @@ int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool own_packed)
         if (e->d_Dp) CU(cudaFree(e->d_Dp));
         e->d_x2 = e->d_Dp = nullptr;
         e->cap_blocks = 0;
-        CU(cudaMalloc(&e->d_x2, blocks * e->nvar * kN * sizeof(float2)));
-        CU(cudaMalloc(&e->d_Dp, blocks * e->nvar * kN * sizeof(float2)));
+        CU(cudaMalloc(&e->d_x2, blocks * e->nvar * e->n_shift * kN * sizeof(float2)));
+        CU(cudaMalloc(&e->d_Dp, blocks * e->nvar * e->n_shift * kN * sizeof(float2)));
         e->cap_blocks = blocks;
     }
     if (own_packed) {
@@ -254,9 +255,9 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const long long tiles_total = (long long)n_captures * e->n_slots * e->n_dop * K;
     const bool pdl = !prof && (e->pdl == 1 || (e->pdl < 0 && tiles_total <= 64LL * e->sm_count));
     if (prof) CU(cudaEventRecord(e->prof[0], st));
-    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, st);
+    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
-    e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar, true, e->sm_count, st, pdl);
+    e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar * e->n_shift, true, e->sm_count, st, pdl);
     if (prof) CU(cudaEventRecord(e->prof[2], st));
     SearchArgs a{};
     a.Dp = e->d_Dp;
@@ -271,6 +272,9 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     a.nvar = e->nvar;
     a.ext_len = e->ext_len;
     a.Q = e->Q;
+    a.n_shift = e->n_shift;
+    a.smax = e->smax;
+    a.cd_div = e->cd_div;
     if (e->n_l1 > 0) {
         a.work = e->d_work;
         a.n_work = e->n_l1;
@@ -305,7 +309,7 @@ int check_search_args(acq_engine *e, const void *packed, int n_captures, const v
     if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");
     if (!packed || !out) return fail(ACQ_ERR_ARG, "packed/out must not be NULL");
     if (n_captures <= 0) return fail(ACQ_ERR_ARG, "n_captures must be > 0 (got %d)", n_captures);
-    if ((long long)n_captures * e->prm.k_noncoh > (1 << 24)) return fail(ACQ_ERR_ARG, "too many capture blocks");
+    if ((long long)n_captures * e->prm.k_noncoh * e->n_shift > (1 << 24)) return fail(ACQ_ERR_ARG, "too many capture blocks");
     if (e->pending) return fail(ACQ_ERR_ARG, "a submitted search is still pending: call acq_wait first");
     return ACQ_OK;
 }
@@ -363,6 +367,8 @@ int acq_params_default(acq_params *p)
     p->thr_e1b = 16.0f;  // gps/search.cpp:549
     p->wrap_mode = ACQ_WRAP_REFERENCE;
     p->sample_bits = 1;  // the sampler's I_sign stream, gps/search.cpp:408-411
+    p->code_doppler = 0;
+    p->reserved[0] = p->reserved[1] = p->reserved[2] = 0;
     return ACQ_OK;
 }
 
@@ -381,6 +387,17 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
         return fail(ACQ_ERR_ARG, "bad wrap_mode");
     if (prm.sample_bits < 0 || prm.sample_bits > 2) return fail(ACQ_ERR_ARG, "sample_bits must be 1 or 2 (0 = 1)");
     if (prm.sample_bits == 0) prm.sample_bits = 1;  // the member used to be "reserved, must be 0"
+    if (prm.code_doppler != 0 && prm.code_doppler != 1) return fail(ACQ_ERR_ARG, "code_doppler must be 0 or 1");
+    if (prm.reserved[0] || prm.reserved[1] || prm.reserved[2]) return fail(ACQ_ERR_ARG, "reserved members must be 0");
+    // code-Doppler compensation: largest lag shift over the Doppler range, reached in the last block
+    const int cd_div = 385 * (prm.half_bin ? 2 : 1);  // FS/DECIM/f_L1 = 4.092e6/1575.42e6 = 1/385 exactly
+    int smax = 0;
+    if (prm.code_doppler && prm.k_noncoh > 1)
+        smax = std::max(std::abs(acq::code_shift(prm.k_noncoh - 1, prm.dop_lo, cd_div)),
+                        std::abs(acq::code_shift(prm.k_noncoh - 1, prm.dop_hi, cd_div)));
+    if (2 * smax + 1 > ACQ_MAX_CODE_SHIFTS)
+        return fail(ACQ_ERR_UNSUPPORTED, "code_doppler needs %d shifted copies of every capture spectrum (limit %d): "
+                    "reduce k_noncoh or the Doppler span", 2 * smax + 1, ACQ_MAX_CODE_SHIFTS);
     const int max_idx = std::max(std::abs(prm.dop_lo), std::abs(prm.dop_hi));
     const int max_bins = prm.half_bin ? (max_idx + 1) / 2 + 1 : max_idx;
     if (max_bins > 2048) return fail(ACQ_ERR_ARG, "Doppler span too large (|bins| <= 2048)");
@@ -418,6 +435,9 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     e->sats.assign(sats, sats + n_sats);
     e->n_dop = prm.dop_hi - prm.dop_lo + 1;
     e->nvar = prm.half_bin ? 2 : 1;
+    e->smax = smax;
+    e->n_shift = 2 * smax + 1;
+    e->cd_div = cd_div;
     e->sample_bits = prm.sample_bits;
     e->block_bytes = ACQ_CAPTURE_BLOCK_BYTES(prm.sample_bits);
     e->Q = max_bins / 4 + 2;
@@ -618,7 +638,8 @@ int acq_refine(acq_engine *e, const acq_record *rec, int n_records, acq_fine *ou
     if ((rc = grow(e->d_fine, e->cap_fine, (size_t)n_records))) return rc;
     CU(cudaMemcpyAsync(e->d_ref_rec, rec, (size_t)n_records * sizeof(acq_record), cudaMemcpyHostToDevice, e->stream));
     e->launches += launch_refine(e->d_Dp, e->d_Ep, e->d_ref_rec, e->d_sat_type, e->d_fine, n_records, e->n_slots,
-                                 e->prm.k_noncoh, e->nvar, e->prm.half_bin, e->ext_len, e->Q, e->stream);
+                                 e->prm.k_noncoh, e->nvar, e->prm.half_bin, e->ext_len, e->Q, e->n_shift, e->smax,
+                                 e->cd_div, e->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, e->d_fine, (size_t)n_records * sizeof(acq_fine), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -669,7 +690,7 @@ int acq_get_capture_spectrum(acq_engine *e, const uint8_t *packed, int half_rot,
             if ((ce = cudaMemcpy(d_rot, rot.data(), kN * sizeof(float2), cudaMemcpyHostToDevice))) break;
             rotp = d_rot;
         }
-        e->launches += launch_front_end(d_pk, d_x2, rotp, 1, half_rot ? 2 : 1, 1, e->sample_bits, e->stream);
+        e->launches += launch_front_end(d_pk, d_x2, rotp, 1, half_rot ? 2 : 1, 1, e->sample_bits, 1, 0, e->stream);
         const float2 *sel_x2 = d_x2 + (half_rot ? kN : 0);
         e->launches += launch_fwd_fft(sel_x2, d_D, e->d_tables, 1, false, e->sm_count, e->stream);
         if ((ce = cudaGetLastError())) break;

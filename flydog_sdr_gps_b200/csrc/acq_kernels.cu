@@ -68,9 +68,12 @@ constexpr int kFeBytes = 544;                  // staged capture bytes (>= 524, 
 // followed by a magnitude plane of the same layout; the mixed sample is (bit ? -1 : +1) * (mag ? 3 : 1).  Both
 // planes are staged by bulk copies on the same mbarrier.  The products with the taps stay exact roundings of
 // (+-1 | +-3) * c in the reference's summation order.
+// Code-Doppler compensation (n_shift > 1): every output row is written n_shift times, copy i delayed by a further
+// i - smax samples (row layout [block][variant][copy][16384]); the search kernels pick the copy per (block, Doppler).
 template <bool MAG>
 __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ packed, float2 *__restrict__ x2,
-                                                   const float2 *__restrict__ rot, int nvar, int K, int row0)
+                                                   const float2 *__restrict__ rot, int nvar, int K, int row0,
+                                                   int n_shift, int smax)
 {
     __shared__ __align__(16) uint8_t sbits[kFeBytes + 16];
     __shared__ __align__(16) uint8_t mbits[MAG ? kFeBytes + 16 : 16];
@@ -152,8 +155,8 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
     }
     __syncthreads();
     // ---- second half-band stage: x2[o0 + oo] from x1s[2*oo + j]
-    float2 *out = x2 + (size_t)blockIdx.y * nvar * kN;
-    const int delay = 16 * (int)((row0 + blockIdx.y) % K);
+    float2 *out = x2 + (size_t)blockIdx.y * nvar * n_shift * kN;
+    const int delay = 16 * (int)((row0 + blockIdx.y) % K) - smax;
     for (int oo = t; oo < kFeOut; oo += 256) {
         const float2 *in = x1s + 2 * oo;
         HbAcc acc;
@@ -167,12 +170,13 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
         v = in[15];
         acc.add(v.x, v.y, c_hb[16]);
         const int o = kFeOut * chunk + oo;
-        const int od = (o + delay) & (kN - 1);
-        out[od] = make_float2(acc.re, acc.im);
+        const float2 y = make_float2(acc.re, acc.im);
+        for (int i = 0; i < n_shift; i++) out[(size_t)i * kN + ((o + delay + i) & (kN - 1))] = y;
         if (nvar == 2) {
             const float2 w = rot[o];
-            out[kN + od] = make_float2(__fsub_rn(__fmul_rn(acc.re, w.x), __fmul_rn(acc.im, w.y)),
-                                      __fadd_rn(__fmul_rn(acc.re, w.y), __fmul_rn(acc.im, w.x)));
+            const float2 yh = make_float2(__fsub_rn(__fmul_rn(acc.re, w.x), __fmul_rn(acc.im, w.y)),
+                                          __fadd_rn(__fmul_rn(acc.re, w.y), __fmul_rn(acc.im, w.x)));
+            for (int i = 0; i < n_shift; i++) out[(size_t)(n_shift + i) * kN + ((o + delay + i) & (kN - 1))] = yh;
         }
     }
 }
@@ -464,6 +468,15 @@ struct TileIdx {
     }
 };
 
+// Row of the capture-spectrum array for (capture, block b, variant) at this tile's Doppler index: with code-Doppler
+// compensation the copy delayed by s(b, h) more samples (SearchArgs::n_shift), otherwise the only one.
+__device__ __forceinline__ size_t d_row(const SearchArgs &p, const TileIdx &ti, int b)
+{
+    const size_t bv = (size_t)((size_t)ti.cap * p.K + b) * p.nvar + ti.v;
+    if (p.n_shift == 1) return bv;
+    return bv * p.n_shift + (size_t)(p.smax + code_shift(b, p.dop_lo + ti.d, p.cd_div));
+}
+
 __device__ __forceinline__ void store_cell(const SearchArgs &p, const TileIdx &ti, const Peak &tot, int L)
 {
     acq_cell c;
@@ -481,7 +494,7 @@ __device__ __forceinline__ void load_products(float2 (&x)[16], const SearchArgs 
 {
     const int r = (k2 - ti.dop) & 3;
     const int q = (k2 - ti.dop - r) >> 2;
-    const float2 *Dk = p.Dp + ((size_t)((size_t)ti.cap * p.K + b) * p.nvar + ti.v) * kN + k2 * kSub + t;
+    const float2 *Dk = p.Dp + d_row(p, ti, b) * kN + k2 * kSub + t;
     const float2 *Ek = p.Ep + (size_t)(ti.sat * 4 + r) * p.ext_len + p.Q + q + t;
 #pragma unroll
     for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(__ldg(Dk + 256 * a), __ldg(Ek + 256 * a));
@@ -639,7 +652,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         const float2 *Dk = p.Dp + k2n * kSub;
         const float2 *Ek = p.Ep + (size_t)r * p.ext_len + ((p.Q + q) & ~1);
 #else
-        const float2 *Dk = p.Dp + ((size_t)((size_t)tn.cap * p.K + bn) * p.nvar + tn.v) * kN + k2n * kSub;
+        const float2 *Dk = p.Dp + d_row(p, tn, bn) * kN + k2n * kSub;
         const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
 #endif
         fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
@@ -870,7 +883,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     auto issue = [&](const TileIdx &tn, int k2n, int half) {  // thread 0: stage the operands of sub-FFT (tn, k2n)
         const int r = (k2n - tn.dop) & 3;
         const int q = (k2n - tn.dop - r) >> 2;
-        const float2 *Dk = p.Dp + ((size_t)((size_t)tn.cap * p.K) * p.nvar + tn.v) * kN + k2n * kSub;
+        const float2 *Dk = p.Dp + d_row(p, tn, 0) * kN + k2n * kSub;
         const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
         fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
         mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
@@ -1168,7 +1181,7 @@ struct RefineArgs {
     const acq_record *rec;   // [n_rows], row = cap * n_slots + slot
     const int *sat_type;     // [n_sats]
     acq_fine *out;
-    int n_slots, K, nvar, half_bin, ext_len, Q;
+    int n_slots, K, nvar, half_bin, ext_len, Q, n_shift, smax, cd_div;
 };
 
 __global__ void __launch_bounds__(256) k_refine(const RefineArgs p)
@@ -1183,7 +1196,10 @@ __global__ void __launch_bounds__(256) k_refine(const RefineArgs p)
     const int n = rc.lag;
     float num = 0.0f, den = 0.0f, early = 0.0f, late = 0.0f, peak = 0.0f;  // thread 0 only
     for (int b = 0; b < p.K; b++) {
-        const float2 *D = p.Dp + ((size_t)((size_t)cap * p.K + b) * p.nvar + v) * kN;
+        // the copy of block b the search read at this record's Doppler index (code-Doppler compensation), delayed
+        // by 16 b + cshift samples in the front end
+        const int cshift = p.n_shift > 1 ? code_shift(b, rc.dop, p.cd_div) : 0;
+        const float2 *D = p.Dp + (((size_t)((size_t)cap * p.K + b) * p.nvar + v) * p.n_shift + (p.smax + cshift)) * kN;
         float2 acc[5];
 #pragma unroll
         for (int j = 0; j < 5; j++) acc[j] = make_float2(0.0f, 0.0f);
@@ -1241,7 +1257,7 @@ __global__ void __launch_bounds__(256) k_refine(const RefineArgs p)
             float sn, cs;
             // w1 = e^{+j 2 pi n_b / N}, n_b = n + 16 b: the front end delayed block b by 16 b samples, so lag n of
             // its spectrum is lag n + 16 b of the block itself -- the lag the Doppler phase term refers to
-            sincospif((float)((n + 16 * b) & (kN - 1)) * (1.0f / 8192.0f), &sn, &cs);
+            sincospif((float)((n + 16 * b + cshift) & (kN - 1)) * (1.0f / 8192.0f), &sn, &cs);
             const float2 Xm = cmul(R[0], make_float2(cs, sn)), Xp = cmul(R[4], make_float2(cs, -sn)), X0 = R[2];
             const float2 a = csub(Xm, Xp);
             const float2 g = csub(csub(cadd(X0, X0), Xm), Xp);
@@ -1331,18 +1347,18 @@ cudaError_t search_kernels_configure()
 }
 
 int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, int sample_bits,
-                     cudaStream_t st)
+                     int n_shift, int smax, cudaStream_t st)
 {
     int launched = 0;
     for (int b0 = 0; b0 < n_blocks; b0 += 32768) {  // gridDim.y <= 65535
         const int nb = (n_blocks - b0 < 32768) ? (n_blocks - b0) : 32768;
         const dim3 grid(kN / kFeOut, nb);
         if (sample_bits == 2)
-            k_front_end<true><<<grid, 256, 0, st>>>(packed + (size_t)b0 * 2 * ACQ_BLOCK_BYTES, x2 + (size_t)b0 * nvar * kN,
-                                                    rot, nvar, K, b0);
+            k_front_end<true><<<grid, 256, 0, st>>>(packed + (size_t)b0 * 2 * ACQ_BLOCK_BYTES,
+                                                    x2 + (size_t)b0 * nvar * n_shift * kN, rot, nvar, K, b0, n_shift, smax);
         else
-            k_front_end<false><<<grid, 256, 0, st>>>(packed + (size_t)b0 * ACQ_BLOCK_BYTES, x2 + (size_t)b0 * nvar * kN,
-                                                     rot, nvar, K, b0);
+            k_front_end<false><<<grid, 256, 0, st>>>(packed + (size_t)b0 * ACQ_BLOCK_BYTES,
+                                                     x2 + (size_t)b0 * nvar * n_shift * kN, rot, nvar, K, b0, n_shift, smax);
         launched++;
     }
     return launched;
@@ -1412,10 +1428,11 @@ int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st
 }
 
 int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
-                  int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, cudaStream_t st)
+                  int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, int n_shift, int smax, int cd_div,
+                  cudaStream_t st)
 {
     if (n_rows <= 0) return 0;
-    RefineArgs a{Dp, Ep, rec, sat_type, out, n_slots, K, nvar, half_bin, ext_len, Q};
+    RefineArgs a{Dp, Ep, rec, sat_type, out, n_slots, K, nvar, half_bin, ext_len, Q, n_shift, smax, cd_div};
     k_refine<<<n_rows, 256, 0, st>>>(a);
     return 1;
 }

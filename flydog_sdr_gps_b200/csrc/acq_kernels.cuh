@@ -18,7 +18,19 @@ struct SearchArgs {
     acq_cell *cells;       // [cap][n_slots][n_dop]
     long long n_tiles;
     int n_work, n_slots, n_dop, dop_lo, half_bin, K, nvar, ext_len, Q;
+    // code-Doppler compensation (acq_params.code_doppler): every (block, variant) spectrum exists in n_shift copies,
+    // copy i of a block delayed by a further i - smax samples; Doppler index h reads copy smax + s(b, h) of block b,
+    // s = round-half-away(b h / cd_div).  n_shift == 1: off.
+    int n_shift, smax, cd_div;
 };
+
+// s(b, h) of acq_params.code_doppler (same integer arithmetic as the oracle's orc_code_shift)
+__host__ __device__ inline int code_shift(int b, int h, int cd_div)
+{
+    const int a = b * h, m = a < 0 ? -a : a;
+    const int s = (2 * m + cd_div) / (2 * cd_div);
+    return a < 0 ? -s : s;
+}
 
 // A search launch decomposes its tile index with 32-bit arithmetic; acq_api.cu refuses larger searches.
 constexpr long long kMaxTilesPerLaunch = 0x7fffffffLL;
@@ -26,8 +38,9 @@ constexpr long long kMaxTilesPerLaunch = 0x7fffffffLL;
 // host-side launchers (all asynchronous on `st`; each returns the number of kernels it launched)
 int launch_tables_init(const float2 *h_cC, const float *h_hb);
 // sample_bits: 1 = the reference's sign-only capture, 2 = sign plane + magnitude plane per block
+// n_shift/smax: copies of each output row, copy i delayed by a further i - smax samples (code-Doppler compensation)
 int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, int sample_bits,
-                     cudaStream_t st);
+                     int n_shift, int smax, cudaStream_t st);
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
 int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st);
 // pdl: launch with programmatic stream serialization (the grid may become resident while the previous kernel of
@@ -41,7 +54,8 @@ int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out,
                     int dop_lo, cudaStream_t st, bool pdl = false);
 // refinement of the records of the most recent search (one CTA per record)
 int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
-                  int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, cudaStream_t st);
+                  int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, int n_shift, int smax, int cd_div,
+                  cudaStream_t st);
 cudaError_t search_kernels_configure();
 
 }  // namespace acq

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ACQ_ABI_VERSION 1
+#define ACQ_ABI_VERSION 2   /* 2: acq_params grew from 32 to 48 bytes (code_doppler) */
 
 /* Fixed geometry of the reference search (gps/gps.h:60-82, kiwi.config:259). */
 #define ACQ_FFT_LEN 16384      /* FFT_LEN */
@@ -81,7 +81,18 @@ typedef struct acq_params {
     int32_t wrap_mode;  /* ACQ_WRAP_REFERENCE (default) or ACQ_WRAP_CIRCULAR */
     int32_t sample_bits; /* capture format (this member was "reserved, must be 0"): 0 or 1 = the reference's 1-bit
                             sign-only capture; 2 = 2-bit sign/magnitude (extension, see ACQ_CAPTURE_BLOCK_BYTES) */
+    int32_t code_doppler; /* 0 (default): the K-block sum adds block powers at lag n + 16 b.  1: code-Doppler compensation
+                             (extension): a carrier offset f stretches the code by f/f_L1, so at
+                             Doppler index h block b has advanced a further b*h/385 /DECIM-samples (FS/DECIM/f_L1 =
+                             1/385 exactly; h/2 for half-bin indices) and its power is taken at lag
+                             n + 16 b + s(b,h), s = that quotient rounded half away from zero.  Recovers the
+                             correlation loss of long sums at high Doppler (0.52 chip over 80 ms at 10 kHz); costs
+                             (2 max|s| + 1) shifted copies of every capture spectrum (at most ACQ_MAX_CODE_SHIFTS),
+                             nothing in the search kernels.  No effect when k_noncoh = 1. */
+    int32_t reserved[3];  /* must be 0 */
 } acq_params;
+
+#define ACQ_MAX_CODE_SHIFTS 33 /* acq_create fails with ACQ_ERR_UNSUPPORTED when code_doppler needs more shifted copies */
 
 /* Bytes of one 65536-sample capture block in the format `sample_bits` selects.
  *   1 bit : ACQ_BLOCK_BYTES.  Sample i = bit i&7 of byte i>>3 -- the I_sign stream the reference's sampler

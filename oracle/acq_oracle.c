@@ -49,6 +49,7 @@ void orc_params_default(orc_params *p)
     p->thr_e1b = 16.0f; /* search.cpp:549 */
     p->wrap_mode = ORC_WRAP_REFERENCE;
     p->sample_bits = 1; /* I_sign only, search.cpp:408-411 */
+    p->code_doppler = 0;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -287,8 +288,11 @@ static void correlate_one(const float *Dall, int nvar, int K, const float *C, co
                  * (the transform's own circular lag axis), not modulo L: for the 1 ms codes lags
                  * L..L+16b-1 are the same code phases one period later, and this form is a plain
                  * circular time shift of the block (no scatter) -- see DESIGN.md "non-coherent sum". */
+                /* code-Doppler compensation (extension, acq_oracle.h): block b's code phase has advanced by a
+                 * further s(b, h) /4-samples at Doppler index h */
+                const int cs = prm->code_doppler ? orc_code_shift(b, h, prm->half_bin) : 0;
                 for (i = 0; i < L; i++) {
-                    const int m = (i + 16 * b) % N;
+                    const int m = (i + 16 * b + cs + N) % N;
                     const float pwr = prod[2 * m] * prod[2 * m] + prod[2 * m + 1] * prod[2 * m + 1];
                     if (b == 0) P[i] = pwr; else P[i] += pwr;
                 }
@@ -456,7 +460,8 @@ int orc_refine(const uint8_t *packed, const orc_sat *sats, int n_sats, const orc
         double num = 0, den = 0, early = 0, late = 0, peak = 0;
         for (int b = 0; b < K; b++) {
             const float *data = D + (size_t)(b * nvar + var) * 2 * N;
-            const int nb = (n + 16 * b) % N; /* lag n of block 0 is lag n + 16 b of block b (see correlate_one) */
+            /* lag n of block 0 is lag n + 16 b (+ the code-Doppler shift) of block b (see correlate_one) */
+            const int nb = (n + 16 * b + (prm->code_doppler ? orc_code_shift(b, rec[s].dop, prm->half_bin) : 0) + N) % N;
             double R[5][2] = {{0}};
             for (int i = 0; i < N; i++) {
                 const double dr = data[2 * i], di = data[2 * i + 1];
@@ -565,7 +570,8 @@ int orc_gen_capture_sm(uint64_t seed, int n_blocks, const orc_sat *sats, int n_s
             const double u2 = (double)(z2 >> 11) * (1.0 / 9007199254740992.0);
             double s = sqrt(-2.0 * log(u1)) * cos(two_pi * u2);
             for (int k = 0; k < n_sig; k++) {
-                const long idx = i + sig[k].tau;
+                const long idx = (sig[k].code_doppler ? (long)floor((double)i * (1.0 + sig[k].doppler_hz / 1575.42e6)) : i)
+                                 + sig[k].tau;
                 int c = chips[(size_t)k * 4092 + (idx >> 4) % codelen[k]];
                 if (boc[k]) c ^= ((idx & 15) >= 8);
                 double sgn = c ? -1.0 : 1.0;

@@ -53,7 +53,22 @@ typedef struct {
                                the same layout; sample value (sign ? -1 : +1) * (mag ? 3 : 1) -- the MAX2769's
                                sign/magnitude levels (dev/gps_fe.cpp:104; the reference FPGA drops I_mag,
                                verilog/gps/gps.v:50).  0 is read as 1. */
+    int32_t code_doppler;   /* 0 = off.  1 = extension: code-Doppler compensation
+                               of the K-block sum.  A carrier offset f stretches the code by f/f_L1, so block b starts
+                               65536 b f/f_L1 FS samples further along the code than 16 b /4-samples: with f = h BIN
+                               (BIN = FS/65536, FS/4/f_L1 = 1/385 exactly) that is b h/385 /4-samples (h/2 for
+                               half-bin indices).  The power of block b is then taken at lag
+                               n + 16 b + s(b,h),  s = round-half-away(b h / (385 hb)), hb = 2 for half-bins else 1. */
 } orc_params;
+
+/* s(b, h) above; exact integer arithmetic so that every implementation picks the same lag */
+static inline int orc_code_shift(int b, int h, int half_bin)
+{
+    const int d = 385 * (half_bin ? 2 : 1);
+    const int a = b * h, m = a < 0 ? -a : a;
+    const int s = (2 * m + d) / (2 * d);
+    return a < 0 ? -s : s;
+}
 
 /* bytes of one capture block in the format `sample_bits` selects */
 #define ORC_CAPTURE_BLOCK_BYTES(sample_bits) ((sample_bits) == 2 ? 2 * ORC_BLOCK_BYTES : ORC_BLOCK_BYTES)
@@ -154,6 +169,8 @@ typedef struct {
     double cn0_dbhz;
     double phase;      /* carrier phase at sample 0, radians */
     int32_t flip_ms;   /* >0: flip the sign every flip_ms milliseconds (data bits); 0: none */
+    int32_t code_doppler; /* 1: the code runs at (1 + doppler_hz/f_L1) chips per nominal chip (as a real signal's does):
+                             sample i carries chip floor(i (1 + f/f_L1)) + tau; 0: code Doppler ignored (v1 captures) */
 } orc_signal;
 
 /* Fills n_blocks*8192 bytes. */

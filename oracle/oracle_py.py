@@ -27,12 +27,12 @@ class OrcSat(C.Structure):
 class OrcParams(C.Structure):
     _fields_ = [("dop_lo", C.c_int32), ("dop_hi", C.c_int32), ("half_bin", C.c_int32),
                 ("k_noncoh", C.c_int32), ("thr_l1", C.c_float), ("thr_e1b", C.c_float),
-                ("wrap_mode", C.c_int32), ("sample_bits", C.c_int32)]
+                ("wrap_mode", C.c_int32), ("sample_bits", C.c_int32), ("code_doppler", C.c_int32)]
 
 
 class OrcSignal(C.Structure):
     _fields_ = [("sat", C.c_int32), ("tau", C.c_int32), ("doppler_hz", C.c_double),
-                ("cn0_dbhz", C.c_double), ("phase", C.c_double), ("flip_ms", C.c_int32)]
+                ("cn0_dbhz", C.c_double), ("phase", C.c_double), ("flip_ms", C.c_int32), ("code_doppler", C.c_int32)]
 
 
 RECORD_DTYPE = np.dtype([("sat", "<i4"), ("lag", "<i4"), ("dop", "<i4"),
@@ -238,7 +238,7 @@ def refine(packed, sats, records, params=None, nthreads=0):
     return out
 
 
-def gen_capture(seed, n_blocks, sats, signals, sample_bits=1, mag_thr=0.98):
+def gen_capture(seed, n_blocks, sats, signals, sample_bits=1, mag_thr=0.98, code_doppler=False):
     """signals: iterable of dicts/tuples (sat, tau, doppler_hz, cn0_dbhz, phase[, flip_ms]).
     sample_bits=2: sign plane + magnitude plane per block, mag = |s| > mag_thr noise sigmas (same sign bits)."""
     arr = sat_array(sats)
@@ -250,6 +250,7 @@ def gen_capture(seed, n_blocks, sats, signals, sample_bits=1, mag_thr=0.98):
         sig[i].sat, sig[i].tau = int(s[0]), int(s[1])
         sig[i].doppler_hz, sig[i].cn0_dbhz, sig[i].phase = float(s[2]), float(s[3]), float(s[4])
         sig[i].flip_ms = int(s[5])
+        sig[i].code_doppler = 1 if code_doppler else 0
     out = np.zeros(n_blocks * block_bytes(sample_bits), np.uint8)
     rc = lib().orc_gen_capture_sm(int(seed), n_blocks, arr, len(sats), sig, len(signals), int(sample_bits),
                                   float(mag_thr), _u8(out))

@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
     assert engine.CELL_DTYPE.itemsize == 16    # acq_cell
     assert engine.FINE_DTYPE.itemsize == 16    # acq_fine
     assert C.sizeof(_lib.AcqSat) == 16
-    assert C.sizeof(_lib.AcqParams) == 32
+    assert C.sizeof(_lib.AcqParams) == 48  # ABI version 2: + code_doppler, reserved[3]
 
 
 def test_defaults_are_the_reference_constants():
@@ -52,7 +52,8 @@ def test_defaults_are_the_reference_constants():
     assert p.thr_l1 == 16.0 and p.thr_e1b == 16.0                            # gps/gps.h:60, search.cpp:549
     assert p.wrap_mode == engine.WRAP_REFERENCE
     assert p.sample_bits == 1                                                # I_sign only, search.cpp:408-411
-    assert _lib.load().acq_abi_version() == 1
+    assert p.code_doppler == 0 and list(p.reserved) == [0, 0, 0]
+    assert _lib.load().acq_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -81,6 +82,11 @@ def test_argument_errors_without_gpu():
     sat = _lib.AcqSat(1, 2, 6, 0)
     assert L.acq_create(C.byref(h), C.byref(engine.default_params(sample_bits=3)), C.byref(sat), 1, 0) == -1
     assert b"sample_bits" in L.acq_last_error()
+    assert L.acq_create(C.byref(h), C.byref(engine.default_params(code_doppler=2)), C.byref(sat), 1, 0) == -1
+    # code-Doppler compensation is refused (not silently truncated) when it would need too many shifted spectra
+    big = engine.default_params(code_doppler=1, k_noncoh=255, dop_lo=-2048, dop_hi=2048)
+    assert L.acq_create(C.byref(h), C.byref(big), C.byref(sat), 1, 0) == -4  # ACQ_ERR_UNSUPPORTED
+    assert b"shifted copies" in L.acq_last_error()
 
 
 def test_product_never_imports_the_oracle():

@@ -575,3 +575,42 @@ def test_sign_magnitude_captures(gpu_required, oracle):
     assert np.allclose(fine[0]["peak"], rec[0]["peak"], rtol=1e-4)
     with pytest.raises(F.AcqError):
         F.AcqEngine(table, F.default_params(sample_bits=3))
+
+
+def test_code_doppler_compensation(gpu_required, oracle):
+    """acq_params.code_doppler: shifted copies of the capture spectra, selected per (block, Doppler index) in the
+    search kernels and in the refinement -- against the oracle's per-block lag shift on a capture whose codes are
+    stretched by their carrier offsets.  C/A (TMA-staged and LDG forms), half-bins, and E1B non-coherent sums."""
+    table = S.navstar()
+    BIN = F.BIN_HZ
+    K = 12
+    kw = dict(dop_lo=-80, dop_hi=80, half_bin=1, k_noncoh=K, thr_l1=3.0, code_doppler=1)
+    sig = [(4, 5000, 38.0 * BIN, 37, 0.2), (20, 16000, -37.5 * BIN, 37, 1.2), (9, 800, 1.0 * BIN, 37, 0.7)]
+    cap = synth.make_capture(5, K, table, sig, code_doppler=True)
+    sel = np.array([4, 20, 9, 11], np.int32)
+    orec, ogrid = oracle.search(cap, table, sel=sel, params=oracle.default_params(**kw), want_grid=True)
+    with F.AcqEngine(table, F.default_params(**kw)) as eng:
+        rec, grid = eng.search(cap, sel=sel, want_grid=True)
+        fine = eng.refine(rec)
+        two = eng.search(np.concatenate([cap, cap]), sel=sel)       # capture stride with shifted copies
+    compare_records(rec[0], orec, ogrid, kw["dop_lo"], kw["thr_l1"], ggrid=grid[0], max_ties=1)
+    assert np.array_equal(rec[0]["dop"][:3], [76, -75, 2]) and np.array_equal(rec[0]["lag"][:3], [1250, 4000, 200])
+    assert two[0].tobytes() == rec[0].tobytes() and two[1].tobytes() == rec[0].tobytes()
+    ofine = oracle.refine(cap, table, orec, params=oracle.default_params(**kw))
+    assert np.allclose(fine[0]["peak"], rec[0]["peak"], rtol=1e-4)
+    assert np.abs(fine[0]["dop_hz"][:3] - ofine["dop_hz"][:3]).max() < 2e-3 * BIN
+    kw0 = dict(kw, code_doppler=0)
+    with F.AcqEngine(table, F.default_params(**kw0)) as eng:
+        plain = eng.search(cap, sel=sel)
+    assert (rec[0]["snr"][:2] > 1.05 * plain[0]["snr"][:2]).all()    # the compensation recovers the smeared peaks
+    assert rec[0][2].tobytes() == plain[0][2].tobytes()              # |h| = 2: no shift in any block
+    # E1B, full bins, K = 6 (cluster kernel with block sums)
+    gal = S.e1b([3, 11, 19])
+    kwe = dict(dop_lo=-40, dop_hi=40, k_noncoh=6, thr_e1b=5.0, code_doppler=1)
+    sige = [(1, 30000, -39.0 * BIN, 40, 0.4)]
+    cape = synth.make_capture(8, 6, gal, sige, code_doppler=True)
+    orec, ogrid = oracle.search(cape, gal, params=oracle.default_params(**kwe), want_grid=True)
+    with F.AcqEngine(gal, F.default_params(**kwe)) as eng:
+        rec, grid = eng.search(cape, want_grid=True)
+    compare_records(rec[0], orec, ogrid, -40, 5.0, ggrid=grid[0], max_ties=1)
+    assert rec[0]["dop"][1] == -39 and rec[0]["snr"][1] >= 5.0
