@@ -236,6 +236,31 @@ __device__ __forceinline__ uint32_t tmem_lane_base(int t) { return (uint32_t)(((
 //     finishing its B(i-1) reads.
 // Stage-C thread t then owns lags n = (t >> 4) + 16*(t & 15) + 256*n2.
 // ---------------------------------------------------------------------------------------------
+// Stage-A output twiddles W16384^{(4t+k2) n0} = b^{n0}, n0 = 1..15, as ACQ_TW_CHAINS interleaved chains of powers
+// (chain i holds b^{i+1}, b^{i+1+C}, ...; every chain advances by b^C): always 14 complex multiplies, dependent
+// depth 14 with one chain, 8 with two, 6 with four (measured: two chains +0.5 % on cfg2/cfg5, +0.9 % on cfg3 over one;
+// four no better).  dst[n0 * STRIDE] = x[r16(n0)] * b^{n0}.
+#ifndef ACQ_TW_CHAINS
+#define ACQ_TW_CHAINS 2
+#endif
+template <int STRIDE>
+__device__ __forceinline__ void stage_a_store(const float2 (&x)[16], const float2 b, float2 *dst)
+{
+    constexpr int C = ACQ_TW_CHAINS;
+    float2 tw[C];
+    tw[0] = b;
+#pragma unroll
+    for (int i = 1; i < C; i++) tw[i] = cmul(tw[i - 1], b);
+    const float2 step = tw[C - 1];
+    dst[0] = x[r16(0)];
+#pragma unroll
+    for (int n0 = 1; n0 < 16; n0++) {
+        const int i = (n0 - 1) % C;
+        dst[n0 * STRIDE] = cmul(x[r16(n0)], tw[i]);
+        if (n0 + C <= 15) tw[i] = cmul(tw[i], step);
+    }
+}
+
 constexpr int kS2TileElems = 16 * 17;  // one padded 16x16 tile per half-warp
 
 struct FftSmem3 {
@@ -266,16 +291,7 @@ __device__ __forceinline__ void subfft4096_inv3(float2 (&x)[16], const int k2, c
                                                 const FftSmem3 &s, const int t)
 {
     radix16_inv(x);
-    {
-        float2 *dst = s.S1 + buf * kS1Elems + t;
-        float2 tw = b;
-        dst[0] = x[r16(0)];
-#pragma unroll
-        for (int n0 = 1; n0 < 16; n0++) {
-            dst[n0 * 256] = cmul(x[r16(n0)], tw);
-            if (n0 < 15) tw = cmul(tw, b);
-        }
-    }
+    stage_a_store<256>(x, b, s.S1 + buf * kS1Elems + t);
     // stage-B twiddles W1024^{(4c+k2)*n1} do not depend on the exchange: first batch before the barrier
     float2 tw[8];
     const float2 *twp = s.T2 + k2 * (15 * 16) + (t & 15);
@@ -351,16 +367,7 @@ __device__ __forceinline__ void subfft4096_inv3t(float2 (&x)[16], const int k2, 
                                                  const FftSmem3T &s, const int t, const uint32_t tw_taddr)
 {
     radix16_inv(x);
-    {
-        float2 *dst = s.S1 + buf * kS1Elems + t;
-        float2 tw = b;
-        dst[0] = x[r16(0)];
-#pragma unroll
-        for (int n0 = 1; n0 < 16; n0++) {
-            dst[n0 * 256] = cmul(x[r16(n0)], tw);
-            if (n0 < 15) tw = cmul(tw, b);
-        }
-    }
+    stage_a_store<256>(x, b, s.S1 + buf * kS1Elems + t);
     float2 tw[8], tw2[8];
     tmem_ld8(tw_taddr + 32 * k2, tw);        // n1 = 1..8, in flight across the barrier
     tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15 (+ one unused)
@@ -510,16 +517,7 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
                                                 const uint32_t tw_taddr, PostBarrier &&post_barrier)
 {
     radix16_inv(x);
-    {
-        float2 *dst = S1b + t;
-        float2 tw = b;
-        dst[0] = x[r16(0)];
-#pragma unroll
-        for (int n0 = 1; n0 < 16; n0++) {
-            dst[n0 * kRowElems] = cmul(x[r16(n0)], tw);
-            if (n0 < 15) tw = cmul(tw, b);
-        }
-    }
+    stage_a_store<kRowElems>(x, b, S1b + t);
     float2 tw[8], tw2[8];
     tmem_ld8(tw_taddr + 32 * k2, tw);        // n1 = 1..8, in flight across the barrier
     tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15, then the next residue's stage-A base
@@ -593,16 +591,7 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
                                                  const float2 *T2s, const uint32_t base_taddr, PostBarrier &&post_barrier)
 {
     radix16_inv(x);
-    {
-        float2 *dst = S1b + t;
-        float2 tw = b;
-        dst[0] = x[r16(0)];
-#pragma unroll
-        for (int n0 = 1; n0 < 16; n0++) {
-            dst[n0 * 256] = cmul(x[r16(n0)], tw);
-            if (n0 < 15) tw = cmul(tw, b);
-        }
-    }
+    stage_a_store<256>(x, b, S1b + t);
 #ifndef ACQ_E1B_TW15
 #define ACQ_E1B_TW15 0
 #endif
