@@ -417,6 +417,9 @@ constexpr int kEBufElems = kSub + 2;
 #ifndef ACQ_PADDED_ROWS
 #define ACQ_PADDED_ROWS 0
 #endif
+#ifndef ACQ_SWZ128
+#define ACQ_SWZ128 1   // E1B kernel (subfft4096_inv4s); the C/A kernel takes it as a template parameter
+#endif
 constexpr int kRowElems = ACQ_PADDED_ROWS ? 16 * 17 : 256;  // exchange row (padded: B->C tile at 17 n1 + c; else XOR swizzle)
 constexpr int kS1pElems = 16 * kRowElems;     // one half of the padded exchange buffer
 struct FftSmem4 {
@@ -512,7 +515,10 @@ __device__ __forceinline__ void subfft4_park_twiddles(const float2 *__restrict__
 //        next residue's base);  S1b = this sub-FFT's half of S1
 //   post_barrier(): called by every thread right after the CTA barrier (warp 0 issues the next TMA there)
 //   out: x[r16(n2)] = stage-C output for lag lag_of3(t, n2), before the W64^{k2*n2} factor
-template <class PostBarrier>
+// SWZ128: B->C tile swizzled in 16-byte chunks and read with 128-bit loads (below).  Measured (variants A/B, same
+// box): +1.2 % on the K > 1 kernel (cfg2), +0.9 % on E1B (cfg3), -0.8 % on the K = 1 kernel (cfg5) -- so the
+// instantiations choose: k_search_l1<MULTI> passes SWZ128 = MULTI, k_search_e1b uses it.
+template <bool SWZ128, class PostBarrier>
 __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
                                                 const uint32_t tw_taddr, PostBarrier &&post_barrier)
 {
@@ -550,23 +556,48 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
         for (int cc = 0; cc < 16; cc++) x[cc] = src[cc];
     }
 #else
-    {   // unpadded row: element (n1, c) at 16 n1 + (c ^ n1); on byte addresses (row is 128-byte aligned) the XOR
-        // touches bits 3..6 only: address = ((row + 8 c) ^ (8 n1)) + 128 n1
-        const uint32_t wb = smem_u32(row + c);
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wb), "f"(x[r16(0)].x), "f"(x[r16(0)].y) : "memory");
+    if constexpr (SWZ128) {
+        {   // unpadded row, swizzled in 16-byte chunks: element (n1, c) in chunk (c >> 1) ^ (n1 & 7), slot c & 1 of tile row
+            // n1, so that stage C reads two adjacent elements with one 128-bit load (half the loads and address XORs):
+            // address = ((row + 8 c) ^ (16 (n1 & 7))) + 128 n1
+            const uint32_t wb = smem_u32(row + c);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wb), "f"(x[r16(0)].x), "f"(x[r16(0)].y) : "memory");
 #pragma unroll
-        for (int i = 0; i < 15; i++) {
-            const int n1 = i + 1;
-            const float2 v = cmul(x[r16(n1)], i < 8 ? tw[i] : tw2[i - 8]);
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
+            for (int i = 0; i < 15; i++) {
+                const int n1 = i + 1;
+                const float2 v = cmul(x[r16(n1)], i < 8 ? tw[i] : tw2[i - 8]);
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (16u * (n1 & 7))) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
+            }
         }
-    }
-    __syncwarp();
-    {   // this thread is now (n0, n1 = c): element (c, cc) at 16 c + (cc ^ c) -> ((row + 136 c) ^ (8 cc))
-        const uint32_t rb = smem_u32(row + 17 * c);
+        __syncwarp();
+        {   // this thread is now (n0, n1 = c): elements (c, 2 j), (c, 2 j + 1) in chunk j ^ (c & 7) of tile row c
+            const uint32_t rb = smem_u32(row + 16 * c + 2 * (c & 7));
 #pragma unroll
-        for (int cc = 0; cc < 16; cc++)
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x[cc].x), "=f"(x[cc].y) : "r"(rb ^ (8u * cc)) : "memory");
+            for (int j = 0; j < 8; j++)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(x[2 * j].x), "=f"(x[2 * j].y), "=f"(x[2 * j + 1].x), "=f"(x[2 * j + 1].y)
+                             : "r"(rb ^ (16u * j))
+                             : "memory");
+        }
+    } else {
+        {   // unpadded row: element (n1, c) at 16 n1 + (c ^ n1); on byte addresses (row is 128-byte aligned) the XOR
+            // touches bits 3..6 only: address = ((row + 8 c) ^ (8 n1)) + 128 n1
+            const uint32_t wb = smem_u32(row + c);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wb), "f"(x[r16(0)].x), "f"(x[r16(0)].y) : "memory");
+#pragma unroll
+            for (int i = 0; i < 15; i++) {
+                const int n1 = i + 1;
+                const float2 v = cmul(x[r16(n1)], i < 8 ? tw[i] : tw2[i - 8]);
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
+            }
+        }
+        __syncwarp();
+        {   // this thread is now (n0, n1 = c): element (c, cc) at 16 c + (cc ^ c) -> ((row + 136 c) ^ (8 cc))
+            const uint32_t rb = smem_u32(row + 17 * c);
+#pragma unroll
+            for (int cc = 0; cc < 16; cc++)
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x[cc].x), "=f"(x[cc].y) : "r"(rb ^ (8u * cc)) : "memory");
+        }
     }
 #endif
     radix16_inv(x);
@@ -585,6 +616,10 @@ __device__ __forceinline__ void tmem_st1(uint32_t taddr, const float2 v)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "f"(v.x), "f"(v.y) : "memory");
 }
+
+// B->C swizzle unit of the unpadded rows: 8-byte elements XORed with n1, or 16-byte chunks XORed with n1 & 7 (ACQ_SWZ128)
+constexpr uint32_t kSwz = ACQ_SWZ128 ? 16u : 8u;
+constexpr int kSwzMask = ACQ_SWZ128 ? 7 : 15;
 
 template <class PostBarrier>
 __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
@@ -621,7 +656,7 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
         for (int i = 0; i < 8; i++) {
             const int n1 = i + 1;
             const float2 v = cmul(x[r16(n1)], tw[i]);
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (kSwz * (n1 & kSwzMask))) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
         }
 #if !ACQ_E1B_TW15
 #pragma unroll
@@ -631,16 +666,28 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
         for (int i = 0; i < 7; i++) {
             const int n1 = i + 9;
             const float2 v = cmul(x[r16(n1)], tw[ACQ_E1B_TW15 ? i + 8 : i]);
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (kSwz * (n1 & kSwzMask))) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
         }
     }
     __syncwarp();
+#if ACQ_SWZ128
+    {
+        const uint32_t rb = smem_u32(row + 16 * c + 2 * (c & 7));
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[2 * j].x), "=f"(x[2 * j].y), "=f"(x[2 * j + 1].x), "=f"(x[2 * j + 1].y)
+                         : "r"(rb ^ (16u * j))
+                         : "memory");
+    }
+#else
     {
         const uint32_t rb = smem_u32(row + 17 * c);
 #pragma unroll
         for (int cc = 0; cc < 16; cc++)
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x[cc].x), "=f"(x[cc].y) : "r"(rb ^ (8u * cc)) : "memory");
     }
+#endif
     radix16_inv(x);
 }
 
