@@ -14,7 +14,13 @@ with F.AcqEngine(table) as eng:                                   # K = 1: k_sea
     r2 = eng.search(np.concatenate([cap[:8192]] * 40), sel=sel)   # many rows: k_fwd_fft (non-cluster)
 with F.AcqEngine(table, F.default_params(k_noncoh=2, half_bin=1, dop_lo=-6, dop_hi=6)) as eng:  # MULTI kernels, E1B cluster
     r3 = eng.search(cap, sel=sel); f3 = eng.refine(r3)
-print("ok", r["snr"], r3["snr"], f["dop_hz"])
+# 2-bit sign/magnitude captures (k_front_end<MAG>) with code-Doppler copies (n_shift > 1) in the MULTI kernels and k_refine
+kw = dict(k_noncoh=8, half_bin=1, dop_lo=-80, dop_hi=80, sample_bits=2, code_doppler=1)  # 3 shifted copies
+cap2 = synth.make_capture(4243, 8, table, [(2, 4000, 38 * F.BIN_HZ, 48, 1.0), (44, 30000, -39 * F.BIN_HZ, 47, 0.4)],
+                          sample_bits=2, code_doppler=True)
+with F.AcqEngine(table, F.default_params(**kw)) as eng:
+    r4 = eng.search(cap2, sel=sel); f4 = eng.refine(r4)
+print("ok", r["snr"], r3["snr"], f["dop_hz"], r4["snr"], f4["dop_hz"])
 P
 for tool in memcheck racecheck synccheck initcheck; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > $out/$tool.log 2>&1
