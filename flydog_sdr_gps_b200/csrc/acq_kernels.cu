@@ -744,6 +744,133 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
+// k_search_l1_x3: the C/A search at THREE CTAs per SM (24 warps instead of 16).  What keeps k_search_l1 at two is its
+// register file share (126 registers: 16 points + 16 accumulators + 16 block powers per thread) and its 98.6 KiB of
+// shared memory.  Here the accumulators over k2 and the block powers live in thread-private TENSOR MEMORY (a CTA
+// allocates 128 columns: 64 per thread -- 32 accumulator, 16 block-power and 8 stage-A-base columns), which brings
+// the kernel to 80 registers; the operands come straight from L2 (no staging buffers), the stage-B twiddles from a
+// 7.5 KiB shared table, and the B->C tiles live inside the exchange rows: 71.9 KiB of shared memory per CTA.
+// Same arithmetic in the same order as k_search_l1 (bitwise-equal cells, tested).
+constexpr int kX3AccCol = 0, kX3PowCol = 32, kX3BaseCol = 48, kX3Cols = 64;
+__host__ __device__ constexpr size_t search_l1_x3_smem()
+{
+    return sizeof(float2) * (size_t)(2 * kSub + kT2Elems) + 64 * sizeof(float);
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float2 *S1 = reinterpret_cast<float2 *>(smem);                 // [2][4096]
+    float2 *T2 = S1 + 2 * kSub;                                    // [4][15][16]
+    float *red_f = reinterpret_cast<float *>(T2 + kT2Elems);       // [2 parities][16], then the TMEM slot at [48]
+    int *red_i = reinterpret_cast<int *>(red_f + 32);              // [2 parities][8]
+    const int t = threadIdx.x;
+    constexpr int L = ACQ_LAGS_L1;
+    const uint32_t tmem_base = tmem_alloc_cta<2 * kX3Cols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
+    pdl_trigger_search();
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
+        float4 *dst = reinterpret_cast<float4 *>(T2);
+        for (int i = t; i < kT2Elems / 2; i += 256) dst[i] = __ldg(src + i);
+    }
+    const uint32_t zaddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kX3Cols);
+    float2 bw = __ldg(p.tables + kT2Elems + t);  // W16384^{4t}: base of residue 0
+    tmem_st1(zaddr + kX3BaseCol, bw);
+#pragma unroll
+    for (int k2 = 1; k2 < 4; k2++) tmem_st1(zaddr + kX3BaseCol + 2 * k2, __ldg(p.tables + kT2Elems + k2 * 256 + t));
+    tmem_wait_st();
+    __syncthreads();
+    pdl_wait();
+    int it = 0;
+    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
+    auto flush = [&](int q) {
+        const Peak tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
+        acq_cell c;
+        c.peak = tot.p;
+        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
+        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
+        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
+        p.cells[((size_t)pend_cap * p.n_slots + pend_slot) * p.n_dop + pend_d] = c;
+    };
+
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileIdx ti(p, tile);
+        float pw[16];
+        for (int b = 0; b < p.K; b++) {
+            float2 x[16];
+#pragma unroll 1
+            for (int k2 = 0; k2 < 3; k2++) {
+                load_products(x, p, ti, b, k2, t);
+                subfft4096_inv4s(x, k2, bw, S1 + (it & 1) * kSub, t, T2, zaddr + kX3BaseCol, [] {});
+                it++;
+                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
+                float2 z[16];
+                if (k2 == 0) {
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) z[n2] = x[r16(n2)];
+                } else {   // acc += x * W64^{k2 n2}, two halves of eight accumulators through tensor memory
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        float2 a[8];
+                        tmem_ld8(zaddr + kX3AccCol + 16 * h, a);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; i++) z[8 * h + i] = cfma(x[r16(8 * h + i)], c_cC[k2][8 * h + i], a[i]);
+                    }
+                }
+                tmem_st16(zaddr + kX3AccCol, z);
+                tmem_wait_st();
+            }
+            // last residue: the accumulation ends in the powers
+            load_products(x, p, ti, b, 3, t);
+            subfft4096_inv4s(x, 3, bw, S1 + (it & 1) * kSub, t, T2, zaddr + kX3BaseCol, [] {});
+            it++;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                float2 a[8];
+                tmem_ld8(zaddr + kX3AccCol + 16 * h, a);
+                float2 pb[4];
+                if (MULTI && b > 0) tmem_ld4(zaddr + kX3PowCol + 8 * h, pb);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float v = cpower(cfma(x[r16(8 * h + i)], c_cC[3][8 * h + i], a[i]));
+                    if (MULTI && b > 0) pw[8 * h + i] = ((i & 1) ? pb[i >> 1].y : pb[i >> 1].x) + v;
+                    else pw[8 * h + i] = v;
+                }
+            }
+            if (MULTI && b + 1 < p.K) {
+                float2 ps[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) ps[i] = make_float2(pw[2 * i], pw[2 * i + 1]);
+                tmem_st8(zaddr + kX3PowCol, ps);
+                tmem_wait_st();
+            }
+        }
+        Peak best;
+        best.p = 0.0f;
+        best.n = 0x7fffffff;
+        best.sum = 0.0f;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) {
+            const int n = lag_of3(t, n2);
+            if (n2 < 15 || n < L) {
+                if (pw[n2] > best.p) best.p = pw[n2], best.n = n;
+                best.sum += pw[n2];
+            }
+        }
+        warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
+        pend_cap = ti.cap;
+        pend_slot = ti.slot;
+        pend_d = ti.d;
+        par ^= 1;
+    }
+    __syncthreads();
+    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
+    tmem_free_cta<2 * kX3Cols>(tmem_base, t);
+}
+
 // Tensor memory (TMEM, 256 KB per SM) as thread-private scratch.  The E1B combine needs the outputs of three
 // residues parked while the fourth is computed: 48 complex values per thread, 96 KiB per CTA.  In shared memory
 // that scratch limits the kernel to one CTA per SM and puts 96 extra loads/stores per thread and tile on the
@@ -1313,6 +1440,11 @@ static bool use_ldg_kernel()
     static const bool v = [] { const char *k = getenv("ACQ_L1_KERNEL"); return k && !strcmp(k, "ldg"); }();  // A/B runs
     return v;
 }
+static bool use_x3_kernel()
+{
+    const char *k = getenv("ACQ_L1_KERNEL");  // A/B runs and the kernel-equivalence test
+    return k && !strcmp(k, "x3");
+}
 static size_t search_e1b_ldg_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
 static size_t search_e1b_smem_bytes() { return e1b_smem_bytes(); }
 static bool use_e1b_ldg_kernel()
@@ -1329,6 +1461,9 @@ cudaError_t search_kernels_configure()
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    const int l1x = (int)search_l1_x3_smem();
+    if ((e = cudaFuncSetAttribute(k_search_l1_x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1x))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1_x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1x))) return e;
     const int l1g = (int)search_l1_ldg_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1_ldg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1g))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1_ldg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1g))) return e;
@@ -1409,6 +1544,10 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
     if (e1b) {
         if (use_e1b_ldg_kernel()) launch_k(k_search_e1b_ldg, grid, 256, search_e1b_ldg_smem_bytes(), st, pdl, a);
         else launch_k(k_search_e1b, grid, 256, search_e1b_smem_bytes(), st, pdl, a);
+    } else if (use_x3_kernel()) {
+        const long long ctas3 = (long long)sm_count * 3;
+        const int grid3 = (int)(a.n_tiles < ctas3 ? a.n_tiles : ctas3);
+        launch_k(a.K > 1 ? k_search_l1_x3<true> : k_search_l1_x3<false>, grid3, 256, search_l1_x3_smem(), st, pdl, a);
     } else if (use_ldg_kernel()) {
         launch_k(a.K > 1 ? k_search_l1_ldg<true> : k_search_l1_ldg<false>, grid, 256, search_l1_ldg_smem_bytes(), st, pdl, a);
     } else {

@@ -614,3 +614,25 @@ def test_code_doppler_compensation(gpu_required, oracle):
         rec, grid = eng.search(cape, want_grid=True)
     compare_records(rec[0], orec, ogrid, -40, 5.0, ggrid=grid[0], max_ties=1)
     assert rec[0]["dop"][1] == -39 and rec[0]["snr"][1] >= 5.0
+
+
+def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle, monkeypatch):
+    """k_search_l1_x3 (three CTAs per SM: accumulators and block powers in tensor memory, operands from L2) against
+    k_search_l1 (two CTAs per SM, TMA-staged operands): the same arithmetic in the same order, so cells are bitwise
+    equal -- K = 1 with more tiles than resident CTAs, and K = 5 half-bin sums with code-Doppler copies."""
+    table = S.navstar()
+    cases = [({}, synth.make_capture(3, 1, table, scenarios.signals("cfg1", 3)), 40),
+             (dict(dop_lo=-60, dop_hi=60, half_bin=1, k_noncoh=5, thr_l1=5.0, code_doppler=1),
+              synth.make_capture(4, 5, table, scenarios.signals("cfg2", 2), code_doppler=True), 1)]
+    for kw, cap, reps in cases:
+        out = {}
+        for kind in ("tma", "x3"):
+            monkeypatch.setenv("ACQ_L1_KERNEL", kind)
+            with F.AcqEngine(table, F.default_params(**kw)) as eng:
+                out[kind] = eng.search(np.concatenate([cap] * reps), want_grid=True)
+        monkeypatch.delenv("ACQ_L1_KERNEL")
+        (ra, ga), (rb, gb) = out["tma"], out["x3"]
+        for f in ("peak", "lag", "noise", "snr"):
+            assert np.array_equal(ga[f], gb[f]), f
+        assert ra.tobytes() == rb.tobytes()
+        assert (ga[0] == ga[-1]).all()
