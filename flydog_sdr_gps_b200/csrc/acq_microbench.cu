@@ -18,17 +18,23 @@ __global__ void __launch_bounds__(256) mb_ffma(float *out, float a, float b, lon
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) acc[i] = (float)(threadIdx.x + i);
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long c0 = clock64();
     for (int it = 0; it < kIters; it++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) acc[i] = fmaf(acc[i], a, b);
     }
     const long long c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
     float s = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) s += acc[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = c1 - c0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        cycles[0] = c1 - c0;               // SM cycles of this CTA's loop
+        cycles[1] = (long long)(g1 - g0);  // nanoseconds of the same interval
+    }
 }
 
 // 16 independent packed FFMA2 chains per thread (sm_100 fma.rn.f32x2).
@@ -166,17 +172,16 @@ extern "C" int acq_microbench(int device, double *out, int n_out)
     float *d_out = nullptr;
     long long *d_cyc = nullptr;
     cudaMalloc(&d_out, sizeof(float) * (size_t)grid * 256);
-    cudaMalloc(&d_cyc, sizeof(long long));
+    cudaMalloc(&d_cyc, 2 * sizeof(long long));
     for (int i = 0; i < n_out; i++) out[i] = 0.0;
 
     const double n_thr = (double)grid * 256;
     float ms = time_ms([&] { mb_ffma<<<grid, 256>>>(d_out, 1.0001f, 0.5f, d_cyc); }, 5);
     out[0] = n_thr * 16.0 * kIters * 2.0 / (ms * 1e-3) / 1e12;
-    long long cyc = 0;
-    cudaMemcpy(&cyc, d_cyc, sizeof cyc, cudaMemcpyDeviceToHost);
-    // block 0's loop cycles over the kernel time: only a rough clock (block 0 runs for the whole kernel
-    // when every SM holds exactly its 8 CTAs)
-    out[4] = (double)cyc / (ms * 1e-3) / 1e6;
+    long long cyc[2] = {0, 0};
+    cudaMemcpy(cyc, d_cyc, sizeof cyc, cudaMemcpyDeviceToHost);
+    // SM clock under load: clock64 cycles over globaltimer nanoseconds of the same loop in CTA 0
+    out[4] = cyc[1] > 0 ? (double)cyc[0] / (double)cyc[1] * 1e3 : 0.0;
     ms = time_ms([&] { mb_ffma2<<<grid, 256>>>(d_out, 1.0001f, 0.5f); }, 5);
     out[1] = n_thr * 16.0 * kIters * 4.0 / (ms * 1e-3) / 1e12;
     if (n_out > 5) {
