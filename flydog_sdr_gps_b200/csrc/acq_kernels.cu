@@ -50,7 +50,7 @@ struct HbAcc {
 };
 
 // K1.  Fused capture front end: unpack + fs/4 XOR mix + both half-band /2 stages, one launch.
-// A CTA produces 1024 consecutive samples of x2 for one 65536-sample block.  It needs x1[2 o0 .. 2 o0 + 2077],
+// A CTA produces kFeOut = 1024 consecutive samples of x2 for one 65536-sample block.  It needs x1[2 o0 .. 2 o0 + 2077],
 // i.e. capture bits 4 o0 .. 4 o0 + 4185 = 524 bytes starting at byte 512*chunk: the packed bytes are staged
 // into shared memory by ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier complete_tx; SASS UBLKCP),
 // x1 is formed in shared memory (never written to HBM), then x2.
@@ -58,9 +58,16 @@ struct HbAcc {
 // search.cpp:386,422-423); I = bit ^ {1,1,0,0}[i&3], Q = bit ^ {1,0,0,1}[i&3]; value = bit ? -1 : +1
 // (search.cpp:62-66,172-175).  Past the end of the block both stages see zeros (search.cpp:145).
 // Second stage as k_hb2 (optional half-bin variant, block delay for non-coherent sums).
-constexpr int kFeOut = 1024;                   // x2 samples per CTA
-constexpr int kFeX1 = 2 * kFeOut + 30;         // x1 samples needed (2078)
-constexpr int kFeBytes = 544;                  // staged capture bytes (>= 524, multiple of 16)
+// Chunk size: 1024 (16 CTAs per block).  Smaller chunks shorten the kernel itself for a single capture (10.8 -> 8.6 us
+// at 256 or 512) but the whole cold-start search got slower (76.9 -> 79.1 / 81.1 us, A/B on one box): the
+// programmatic-dependent-launch chain behind it starts later, so the product keeps 1024.
+#ifndef ACQ_FE_OUT
+#define ACQ_FE_OUT 1024
+#endif
+constexpr int kFeOut = ACQ_FE_OUT;             // x2 samples per CTA (a power of two, 256..1024)
+constexpr int kFeX1 = 2 * kFeOut + 30;         // x1 samples needed (2078 for 1024)
+constexpr int kFeChunkBytes = kFeOut / 2;      // capture bytes that belong to the chunk (4 bits per x2 sample)
+constexpr int kFeBytes = (kFeChunkBytes + 12 + 15) / 16 * 16 + 16;  // staged bytes: chunk + 88 bits of look-ahead, 16-byte units
 
 //
 // MAG (2-bit sign/magnitude capture, acq_params.sample_bits = 2 -- the MAX2769's native output, of which the
@@ -81,10 +88,10 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
     __shared__ float2 x1s[kFeX1 + 2];
     const int t = threadIdx.x;
     pdl_launch_dependents();
-    const int chunk = blockIdx.x;                      // 16 chunks per block
-    const uint8_t *pk = packed + (size_t)blockIdx.y * (MAG ? 2 : 1) * ACQ_BLOCK_BYTES + 512 * chunk;
-    const int avail = ACQ_BLOCK_BYTES - 512 * chunk;   // bytes of this block from the chunk start
-    const int nbytes = avail < kFeBytes ? avail : kFeBytes;  // 512 for the last chunk: never read past the block
+    const int chunk = blockIdx.x;                      // kN / kFeOut chunks per block
+    const uint8_t *pk = packed + (size_t)blockIdx.y * (MAG ? 2 : 1) * ACQ_BLOCK_BYTES + kFeChunkBytes * chunk;
+    const int avail = ACQ_BLOCK_BYTES - kFeChunkBytes * chunk;  // bytes of this block from the chunk start
+    const int nbytes = avail < kFeBytes ? avail : kFeBytes;     // the last chunk(s): never read past the block
     const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
     const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(sbits);
     if (t == 0) {
