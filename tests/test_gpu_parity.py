@@ -636,3 +636,35 @@ def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle, monkeypatc
             assert np.array_equal(ga[f], gb[f]), f
         assert ra.tobytes() == rb.tobytes()
         assert (ga[0] == ga[-1]).all()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_parameter_space(gpu_required, oracle, seed):
+    """Seeded sweep over the parameter space the C ABI accepts -- Doppler range (symmetric or not), half-bins,
+    K blocks, wrap mode, capture format, code-Doppler compensation, mixed-constellation selections in random order --
+    each case against the oracle on the same bytes, records and full per-Doppler tables."""
+    rng = np.random.default_rng(9000 + seed)
+    table = S.reference_table()
+    half = int(rng.integers(0, 2))
+    K = int(rng.choice([1, 1, 2, 3, 5]))
+    span = int(rng.integers(2, 30)) * (2 if half else 1)
+    lo = -int(rng.integers(0, span + 1))
+    hi = lo + span
+    bits = int(rng.choice([1, 2]))
+    kw = dict(dop_lo=lo, dop_hi=hi, half_bin=half, k_noncoh=K, wrap_mode=int(rng.integers(0, 2)), sample_bits=bits,
+              code_doppler=int(rng.integers(0, 2)), thr_l1=16.0 if K == 1 else 6.0, thr_e1b=16.0 if K == 1 else 6.0)
+    sel = rng.choice(len(table), size=int(rng.integers(1, 7)), replace=False).astype(np.int32)
+    step = F.BIN_HZ / (2 if half else 1)
+    sig = []
+    for s in sel[:3]:   # up to three of the searched satellites are present, inside the searched span
+        period = 65472 if table[s][3] == S.E1B else 16368
+        sig.append((int(s), int(rng.integers(0, period)), float(rng.uniform(lo, hi)) * step,
+                    float(rng.uniform(44, 50)), float(rng.uniform(0, 6.28))))
+    cap = synth.make_capture(500 + seed, K, table, sig, sample_bits=bits, code_doppler=bool(kw["code_doppler"]))
+    with F.AcqEngine(table, F.default_params(**kw)) as eng:
+        rec, grid = eng.search(cap, sel=sel, want_grid=True)
+    orec, ogrid = oracle.search(cap, table, sel=sel, params=oracle.default_params(**kw), want_grid=True)
+    thr = np.array([kw["thr_e1b"] if table[s][3] == S.E1B else kw["thr_l1"] for s in sel])
+    for i in range(len(sel)):   # per-constellation thresholds: compare record by record
+        compare_records(rec[0][i:i + 1], orec[i:i + 1], ogrid[i:i + 1], lo, float(thr[i]), ggrid=grid[0][i:i + 1], max_ties=1)
+    assert np.array_equal(rec[0]["sat"], sel)
