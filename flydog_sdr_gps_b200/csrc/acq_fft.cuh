@@ -524,9 +524,26 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
 {
     radix16_inv(x);
     stage_a_store<kRowElems>(x, b, S1b + t);
+#ifndef ACQ_TW_LD4
+#define ACQ_TW_LD4 0
+#endif
+#if ACQ_TW_LD4 == 2
+    float2 tw1[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(tw1[j].x), "=f"(tw1[j].y) : "r"(tw_taddr + 32 * k2 + 2 * j) : "memory");
+#define TW_AT(i) tw1[(i)]
+#elif ACQ_TW_LD4
+    float2 twq[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) tmem_ld4(tw_taddr + 32 * k2 + 8 * j, twq[j]);
+#define TW_AT(i) twq[(i) >> 2][(i) & 3]
+#else
     float2 tw[8], tw2[8];
     tmem_ld8(tw_taddr + 32 * k2, tw);        // n1 = 1..8, in flight across the barrier
     tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15, then the next residue's stage-A base
+#define TW_AT(i) ((i) < 8 ? tw[(i)] : tw2[(i) - 8])
+#endif
     __syncthreads();
     post_barrier();
     float2 *row = S1b + (t >> 4) * kRowElems;  // row n0 = t >> 4
@@ -538,16 +555,16 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
     }
     radix16_inv(x);
     tmem_wait_ld();
-    b = tw2[7];
+    b = TW_AT(15);
     __syncwarp();  // the half-warp has consumed its row: reuse it as the B->C tile, element (n1, c) at 17 n1 + c
 #if ACQ_PADDED_ROWS
     {
         float2 *dst = row + c;
         dst[0] = x[r16(0)];
 #pragma unroll
-        for (int i = 0; i < 8; i++) dst[(i + 1) * 17] = cmul(x[r16(i + 1)], tw[i]);
+        for (int i = 0; i < 8; i++) dst[(i + 1) * 17] = cmul(x[r16(i + 1)], TW_AT(i));
 #pragma unroll
-        for (int i = 0; i < 7; i++) dst[(i + 9) * 17] = cmul(x[r16(i + 9)], tw2[i]);
+        for (int i = 0; i < 7; i++) dst[(i + 9) * 17] = cmul(x[r16(i + 9)], TW_AT(i + 8));
     }
     __syncwarp();
     {
@@ -565,7 +582,7 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
 #pragma unroll
             for (int i = 0; i < 15; i++) {
                 const int n1 = i + 1;
-                const float2 v = cmul(x[r16(n1)], i < 8 ? tw[i] : tw2[i - 8]);
+                const float2 v = cmul(x[r16(n1)], TW_AT(i));
                 asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (16u * (n1 & 7))) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
             }
         }
@@ -587,7 +604,7 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
 #pragma unroll
             for (int i = 0; i < 15; i++) {
                 const int n1 = i + 1;
-                const float2 v = cmul(x[r16(n1)], i < 8 ? tw[i] : tw2[i - 8]);
+                const float2 v = cmul(x[r16(n1)], TW_AT(i));
                 asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (8u * n1)) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
             }
         }
@@ -602,6 +619,7 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
 #endif
     radix16_inv(x);
 }
+#undef TW_AT
 
 // Form of subfft4096_inv4 for kernels whose tensor memory is taken by parked data (k_search_e1b: 96 of a thread's
 // 128 columns hold three residues): the stage-B twiddles W1024^{(4c+k2)*n1} come from a 7.5 KiB shared-memory

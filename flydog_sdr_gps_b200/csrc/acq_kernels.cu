@@ -631,6 +631,13 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
 // 32 KiB buffer; the B->C tiles live inside the exchange rows.  The L2 round trip (the LDG of the _ldg form sits
 // at the head of every warp's dependent chain) is off the critical path; 98.6 KiB of shared memory per CTA.
 constexpr int kIssueLanes = ACQ_PADDED_ROWS ? 16 : 1;  // threads of warp 0 that issue the operand copies
+// Unroll factor of the loop over the four residues of a transform.  Rolled, the compiler moves the 16 accumulators
+// between two register sets once per sub-FFT (about 40 MOVs per warp and sub-FFT in the ncu source view); unrolled
+// by two it renames instead.  Measured: K = 1 kernel +1.3 % (cfg5) and -1.2 us per cold-start search (cfg1); K > 1
+// kernel unchanged (27.79 M tiles/s either way), so it stays rolled; by four the kernels spill.
+#ifndef ACQ_K2_UNROLL
+#define ACQ_K2_UNROLL 2
+#endif
 
 template <bool MULTI>
 __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
@@ -693,7 +700,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         float2 acc[16];
         for (int b = 0; b < p.K; b++) {
             float2 x[16];
-#pragma unroll 1
+            constexpr int kK2Unroll = MULTI ? 1 : ACQ_K2_UNROLL;
+#pragma unroll kK2Unroll
             for (int k2 = 0; k2 < 4; k2++) {
                 float2 *S1b = s.S1 + (it & 1) * kS1pElems;
                 {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471), operands from smem
@@ -964,6 +972,12 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_ldg(const SearchArgs p)
 #define ACQ_E1B_BEST4 1
 #endif
 constexpr int kE1bBaseCol = 96;  // TMEM columns [96, 104): W16384^{4t+k2}, k2 = 0..3
+// Unroll factor of the residue loop (see ACQ_K2_UNROLL): measured on cfg3 19.6 M tiles/s rolled, 19.9 M by two,
+// 20.4 M fully unrolled (the park/no-park branch and the residue-dependent constants fold away; 24 bytes of spill).
+#ifndef ACQ_E1B_K2_UNROLL
+#define ACQ_E1B_K2_UNROLL 4
+#endif
+constexpr int kE1bK2Unroll = ACQ_E1B_K2_UNROLL;
 struct E1bSmem {
     float2 *S1;  // [2][4096]
     float2 *E;   // [4098]
@@ -1040,7 +1054,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileIdx ti(p, tile);
         float2 x[16];
-#pragma unroll 1
+#pragma unroll kE1bK2Unroll
         for (int k2 = 0; k2 < 4; k2++) {
             float2 *S1b = s.S1 + (it & 1) * kSub;
             {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471), operands from smem
