@@ -121,3 +121,19 @@ def test_capture_sources(tmp_path):
         assert np.array_equal(f.next(3), caps.reshape(-1))
     with pytest.raises(OSError):
         capture.CaptureFile(tmp_path / "missing.dat")
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference runs on the host cores alone (no GPU) and prints the one-line JSON contract."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "cells/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("acquisition cells/sec") and line["config"]["workload"] == "cfg2"
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
