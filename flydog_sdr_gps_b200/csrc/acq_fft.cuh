@@ -524,26 +524,10 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
 {
     radix16_inv(x);
     stage_a_store<kRowElems>(x, b, S1b + t);
-#ifndef ACQ_TW_LD4
-#define ACQ_TW_LD4 0
-#endif
-#if ACQ_TW_LD4 == 2
-    float2 tw1[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(tw1[j].x), "=f"(tw1[j].y) : "r"(tw_taddr + 32 * k2 + 2 * j) : "memory");
-#define TW_AT(i) tw1[(i)]
-#elif ACQ_TW_LD4
-    float2 twq[4][4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) tmem_ld4(tw_taddr + 32 * k2 + 8 * j, twq[j]);
-#define TW_AT(i) twq[(i) >> 2][(i) & 3]
-#else
     float2 tw[8], tw2[8];
     tmem_ld8(tw_taddr + 32 * k2, tw);        // n1 = 1..8, in flight across the barrier
     tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15, then the next residue's stage-A base
 #define TW_AT(i) ((i) < 8 ? tw[(i)] : tw2[(i) - 8])
-#endif
     __syncthreads();
     post_barrier();
     float2 *row = S1b + (t >> 4) * kRowElems;  // row n0 = t >> 4
