@@ -44,22 +44,39 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+    nvidia-smi needs a few hundred ms to deliver its first sample, longer than a short timed region: it is started
+    before the warm-up, samples carry timestamps, and only those between mark_start() and mark_end() are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         if not self.proc:
@@ -71,22 +88,27 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                row = (float(f[1]), float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+            rs = {name for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9])
+                  if v.lower().startswith("active")}
+            rows.append((self._epoch(f[9]) if len(f) > 9 else None, row, rs))
+        if not rows:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None
+                  and self.t0 <= r[0] <= self.t1]
+        use = inside or rows  # a region shorter than the sampling period: fall back to every sample of the run
+        reasons = set().union(*[r[2] for r in use])
+        return {"sm_mhz": statistics.median([r[1][0] for r in use]), "sm_max_mhz": max(r[1][1] for r in use),
+                "reasons": sorted(reasons), "samples": len(use), "samples_in_timed_region": len(inside),
+                "samples_total": len(rows), "period_ms": 20}
 
 
 # ------------------------------------------------------------------------------------------ workload
@@ -285,6 +307,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -292,9 +317,7 @@ def main():
     # ---- device-resident timing: K steps of the product path, L2 flushed between steps (flush outside the
     # event pairs).  No events between the kernels here: the four launches of a step are chained by
     # programmatic dependent launch, which an event record in between would switch off.
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_start()
     launches0 = eng.launch_count
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -322,6 +345,7 @@ def main():
     barrier()
     eng.set_profiling(False)
     prof_ms = sum(a.elapsed_time(b) for a, b in evs_p) / args.steps
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
