@@ -516,8 +516,9 @@ __device__ __forceinline__ void subfft4_park_twiddles(const float2 *__restrict__
 //   post_barrier(): called by every thread right after the CTA barrier (warp 0 issues the next TMA there)
 //   out: x[r16(n2)] = stage-C output for lag lag_of3(t, n2), before the W64^{k2*n2} factor
 // SWZ128: B->C tile swizzled in 16-byte chunks and read with 128-bit loads (below).  Measured (variants A/B, same
-// box): +1.2 % on the K > 1 kernel (cfg2), +0.9 % on E1B (cfg3), -0.8 % on the K = 1 kernel (cfg5) -- so the
-// instantiations choose: k_search_l1<MULTI> passes SWZ128 = MULTI, k_search_e1b uses it.
+// box): +1.2 % on the K > 1 kernel (cfg2), +0.9 % on E1B (cfg3); on the K = 1 kernel -0.8 % with the rolled residue
+// loop, +1.5 % (cfg5) once that loop is unrolled by two -- every product kernel uses it now, the 8-byte swizzle
+// stays as the template's other branch.
 template <bool SWZ128, class PostBarrier>
 __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
                                                 const uint32_t tw_taddr, PostBarrier &&post_barrier)

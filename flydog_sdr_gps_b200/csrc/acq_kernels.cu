@@ -713,7 +713,10 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 #pragma unroll
                     for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
                 }
-                subfft4096_inv4<MULTI>(x, k2, bw, S1b, t, tw_taddr, [&]() {
+#ifndef ACQ_SWZ128_K1
+#define ACQ_SWZ128_K1 1  // K = 1 kernel: 128-bit stage-C loads pay once the residue loop is unrolled (cfg5 26.15 -> 26.55 M tiles/s)
+#endif
+                subfft4096_inv4<MULTI || ACQ_SWZ128_K1>(x, k2, bw, S1b, t, tw_taddr, [&]() {
                     if (t < kIssueLanes) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
                         if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
                         else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
