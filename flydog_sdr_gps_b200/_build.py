@@ -51,5 +51,33 @@ def build(force=False, verbose=False, defines=(), out=None):
     return lib
 
 
+# Experiment variants (A/B forms of the kernels and launch policy).  They are separate libraries: the product
+# library contains none of this code and reads no environment variable.
+VARIANTS = {
+    "l1_ldg": ["ACQ_VARIANT_L1_LDG"],        # C/A search, operands straight from L2
+    "l1_x3": ["ACQ_VARIANT_L1_X3"],          # C/A search at three CTAs per SM (accumulators in tensor memory)
+    "e1b_ldg": ["ACQ_VARIANT_E1B_LDG", "ACQ_FORCE_E1B_KERNEL=1"],  # one-CTA E1B search, operands straight from L2
+    "e1b_cta": ["ACQ_FORCE_E1B_KERNEL=1"],   # always the one-CTA E1B form
+    "e1b_cluster": ["ACQ_FORCE_E1B_KERNEL=2"],  # always the cluster/DSMEM E1B form
+    "pdl0": ["ACQ_FORCE_PDL=0"],
+    "pdl1": ["ACQ_FORCE_PDL=1"],
+    "devrec": ["ACQ_HOST_RECORDS=0"],        # records through device memory + copy, stream wait (no mapped memory, no polling)
+}
+
+
+def variant_path(name):
+    return os.path.join(CSRC, "variants", "libacq_b200_%s.so" % name)
+
+
+def build_variant(name, force=False):
+    path = variant_path(name)
+    deps = [os.path.join(CSRC, f) for f in CU_SOURCES + CPP_SOURCES + HEADERS + ["acq_variants.cuh"]]
+    fresh = os.path.exists(path) and all(os.path.getmtime(d) <= os.path.getmtime(path) for d in deps if os.path.exists(d))
+    if fresh and not force:
+        return path
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    return build(defines=VARIANTS[name], out=path)
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

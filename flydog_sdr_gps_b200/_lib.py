@@ -13,9 +13,10 @@ class AcqSat(C.Structure):
 
 
 class AcqParams(C.Structure):
-    _fields_ = [("dop_lo", C.c_int32), ("dop_hi", C.c_int32), ("half_bin", C.c_int32), ("k_noncoh", C.c_int32),
+    _fields_ = [("struct_size", C.c_uint32),
+                ("dop_lo", C.c_int32), ("dop_hi", C.c_int32), ("half_bin", C.c_int32), ("k_noncoh", C.c_int32),
                 ("thr_l1", C.c_float), ("thr_e1b", C.c_float), ("wrap_mode", C.c_int32), ("sample_bits", C.c_int32),
-                ("code_doppler", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("code_doppler", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 # every symbol include/acq_b200.h declares: (name, restype, argtypes)
@@ -54,6 +55,17 @@ def lib_path():
     return _build.LIB
 
 
+def _bind(path):
+    if not os.path.exists(path):
+        raise RuntimeError("%s is missing and could not be built; the engine has no CPU fallback" % os.path.basename(path))
+    L = C.CDLL(path)
+    for name, res, args in _SIGNATURES:
+        fn = getattr(L, name)  # AttributeError if the library does not export the header's symbol
+        fn.restype = res
+        fn.argtypes = args
+    return L
+
+
 def load():
     """Load libacq_b200.so (building it first if sources are newer).  Raises if that is impossible."""
     global _lib
@@ -61,12 +73,16 @@ def load():
         path = os.environ.get("ACQ_B200_LIB")  # experiment variant of the same CUDA library (A/B runs)
         if not path:
             path = _build.build() if _build.needs_build() else _build.LIB
-        if not os.path.exists(path):
-            raise RuntimeError("libacq_b200.so is missing and could not be built; the engine has no CPU fallback")
-        L = C.CDLL(path)
-        for name, res, args in _SIGNATURES:
-            fn = getattr(L, name)  # AttributeError if the library does not export the header's symbol
-            fn.restype = res
-            fn.argtypes = args
-        _lib = L
+        _lib = _bind(path)
     return _lib
+
+
+_variants = {}
+
+
+def load_variant(name):
+    """An experiment variant of the library (tools/build_variants.py; A/B forms of the kernels live only there),
+    loaded NEXT TO the product library -- used by the tests that assert bitwise equality between kernel forms."""
+    if name not in _variants:
+        _variants[name] = _bind(_build.build_variant(name))
+    return _variants[name]

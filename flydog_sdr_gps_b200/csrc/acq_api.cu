@@ -96,27 +96,45 @@ struct acq_engine {
     size_t block_bytes = ACQ_BLOCK_BYTES;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    bool pending = false;
+    bool pending = false;       // acq_submit outstanding
+    int pending_rows = 0;       // ... whose records still sit in h_records (copied to pending_out by acq_poll/acq_wait)
+    acq_record *pending_out = nullptr;
+    // device-path ordering: an event behind the last acq_search_device; whatever touches the shared scratch next waits for it
+    cudaEvent_t dev_done = nullptr;
+    bool dev_pending = false;
     int64_t launches = 0;
     bool profiling = false, prof_valid = false;
-    cudaEvent_t prof[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t prof[4] = {nullptr, nullptr, nullptr, nullptr};
 
-    int pdl = -1;        // programmatic dependent launch between the kernels of a search: -1 = by size, ACQ_PDL=0|1 forces
-    int e1b_kernel = 0;  // 0 = by tile count, 1 = one CTA per tile, 2 = cluster of four CTAs per tile (ACQ_E1B_KERNEL)
     // persistent device data
     float2 *d_tables = nullptr, *d_rot = nullptr, *d_C = nullptr, *d_Ep = nullptr;
     // per-call scratch (grown on demand)
-    size_t cap_blocks = 0, cap_cells = 0, cap_rows = 0, cap_packed = 0;
+    size_t cap_blocks = 0, cap_cells = 0, cap_rows = 0, cap_packed = 0, cap_row_count = 0;
     uint8_t *d_packed = nullptr;
     float2 *d_x2 = nullptr, *d_Dp = nullptr;
     acq_cell *d_cells = nullptr;
     acq_record *d_records = nullptr;
-    // selection cache
+    unsigned *d_row_count = nullptr;   // [rows] finished cells per (capture, sat) row; zero between searches
+    unsigned *d_rows_done = nullptr;   // finished rows of a host-polled search; zero between searches
+    float2 *d_partial = nullptr;       // [2 * sm_count][16][256]: hand-over of split tiles (balanced K = 1 launch)
+    unsigned *d_flags = nullptr;       // [2 * sm_count]
+    unsigned epoch = 0;                // search counter: value of the hand-over flags and of the completion word
+    // host path: pinned staging of small captures; records and the completion word in mapped pinned memory,
+    // written by the search kernels themselves
+    uint8_t *h_packed = nullptr;
+    size_t cap_h_packed = 0;
+    acq_record *h_records = nullptr, *dh_records = nullptr;  // host / device address of the same mapped buffer
+    size_t cap_h_records = 0;
+    unsigned *h_flag = nullptr, *dh_flag = nullptr;
+    // selection: work list [n_slots] (C/A entries first, then E1B) and slot -> table index
     std::vector<int32_t> sel_cache;
-    bool sel_valid = false;
+    int sel_kind = -1;  // -1 none, 0 whole table, 1 one satellite, 2 uploaded list
     int n_l1 = 0, n_e1b = 0, n_slots = 0;
-    int2 *d_work = nullptr;   // [n_slots]: L1 entries first, then E1B
-    int *d_slot_sat = nullptr;
+    const int2 *cur_work = nullptr;
+    const int *cur_slot_sat = nullptr;
+    int2 *d_work_full = nullptr, *d_work_single = nullptr, *d_work = nullptr;   // whole table / (s, 0) per s / uploaded
+    int *d_sat_full = nullptr, *d_slot_sat = nullptr;                            // identity / uploaded
+    int full_n_l1 = 0;
     size_t cap_slots = 0;
     // refinement (acq_refine): satellite types on the device, record/output scratch, shape of the last host-path search
     int *d_sat_type = nullptr;
@@ -130,11 +148,32 @@ namespace {
 
 using namespace acq;
 
+// Build-time switches of the experiment variants (tools/build_variants.py); the product library defines none of
+// them and reads no environment variable.
+//   ACQ_FORCE_PDL=0|1        programmatic dependent launch off / always (default: by search size)
+//   ACQ_FORCE_E1B_KERNEL=1|2 one-CTA / cluster form of the E1B search regardless of the tile count
+//   ACQ_HOST_RECORDS=0       records through device memory + copy even for small searches
+#ifndef ACQ_FORCE_PDL
+#define ACQ_FORCE_PDL -1
+#endif
+#ifndef ACQ_FORCE_E1B_KERNEL
+#define ACQ_FORCE_E1B_KERNEL 0
+#endif
+#ifndef ACQ_HOST_RECORDS
+#define ACQ_HOST_RECORDS 1
+#endif
+// Host path, small searches: the capture goes through an engine-owned pinned staging buffer (a pageable source would
+// make cudaMemcpyAsync synchronous), the kernels write the records straight into mapped pinned memory, and the host
+// polls a completion word there instead of waiting for the stream.  Above these sizes: plain copies and a stream wait.
+constexpr size_t kStagePackedMax = 256u << 10;  // bytes
+constexpr int kHostRecordRowsMax = 2048;         // records (24 B each: single PCIe writes from the SMs)
+
 int free_engine(acq_engine *e)
 {
     if (!e) return ACQ_OK;
     DeviceGuard g(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->dev_pending && e->dev_done) cudaEventSynchronize(e->dev_done);
     cudaFree(e->d_tables);
     cudaFree(e->d_rot);
     cudaFree(e->d_C);
@@ -144,12 +183,23 @@ int free_engine(acq_engine *e)
     cudaFree(e->d_Dp);
     cudaFree(e->d_cells);
     cudaFree(e->d_records);
+    cudaFree(e->d_row_count);
+    cudaFree(e->d_rows_done);
+    cudaFree(e->d_partial);
+    cudaFree(e->d_flags);
+    cudaFree(e->d_work_full);
+    cudaFree(e->d_work_single);
     cudaFree(e->d_work);
+    cudaFree(e->d_sat_full);
     cudaFree(e->d_slot_sat);
     cudaFree(e->d_sat_type);
     cudaFree(e->d_ref_rec);
     cudaFree(e->d_fine);
+    if (e->h_packed) cudaFreeHost(e->h_packed);
+    if (e->h_records) cudaFreeHost(e->h_records);
+    if (e->h_flag) cudaFreeHost(e->h_flag);
     if (e->done) cudaEventDestroy(e->done);
+    if (e->dev_done) cudaEventDestroy(e->dev_done);
     for (cudaEvent_t ev : e->prof)
         if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -157,24 +207,39 @@ int free_engine(acq_engine *e)
     return ACQ_OK;
 }
 
+// Everything that is about to touch the shared scratch from the host (reallocation, synchronous copies) first
+// drains the engine stream and the last device-path search.
+int drain(acq_engine *e)
+{
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->dev_pending) {
+        CU(cudaEventSynchronize(e->dev_done));
+        e->dev_pending = false;
+    }
+    return ACQ_OK;
+}
+
 template <typename T>
-int grow(T *&ptr, size_t &cap, size_t need_elems)
+int grow(acq_engine *e, T *&ptr, size_t &cap, size_t need_elems, bool zero = false)
 {
     if (need_elems <= cap && ptr) return ACQ_OK;
+    int rc = drain(e);
+    if (rc) return rc;
     if (ptr) CU(cudaFree(ptr));
     ptr = nullptr;
     cap = 0;
     CU(cudaMalloc(&ptr, need_elems * sizeof(T)));
+    if (zero) CU(cudaMemset(ptr, 0, need_elems * sizeof(T)));
     cap = need_elems;
     return ACQ_OK;
 }
 
-int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool own_packed)
+int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool host_path)
 {
     const size_t blocks = (size_t)n_captures * e->prm.k_noncoh;
     if (blocks > e->cap_blocks || !e->d_x2) {
-        // changing scratch under an in-flight stream is not allowed: drain first
-        CU(cudaStreamSynchronize(e->stream));
+        int rc = drain(e);  // changing scratch under an in-flight search is not allowed
+        if (rc) return rc;
         if (e->d_x2) CU(cudaFree(e->d_x2));
         if (e->d_Dp) CU(cudaFree(e->d_Dp));
         e->d_x2 = e->d_Dp = nullptr;
@@ -183,77 +248,127 @@ int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool own_packed)
         CU(cudaMalloc(&e->d_Dp, blocks * e->nvar * e->n_shift * kN * sizeof(float2)));
         e->cap_blocks = blocks;
     }
-    if (own_packed) {
-        int rc = grow(e->d_packed, e->cap_packed, blocks * e->block_bytes);
-        if (rc) return rc;
-    }
     const size_t rows = (size_t)n_captures * n_slots;
-    int rc = grow(e->d_cells, e->cap_cells, rows * e->n_dop);
-    if (rc) return rc;
-    return grow(e->d_records, e->cap_rows, rows);
+    int rc;
+    if ((rc = grow(e, e->d_cells, e->cap_cells, rows * e->n_dop))) return rc;
+    if ((rc = grow(e, e->d_row_count, e->cap_row_count, rows, true))) return rc;
+    if (!host_path) return ACQ_OK;
+    const size_t bytes = blocks * e->block_bytes;
+    if ((rc = grow(e, e->d_packed, e->cap_packed, bytes))) return rc;
+    if (bytes <= kStagePackedMax && bytes > e->cap_h_packed) {
+        if ((rc = drain(e))) return rc;
+        if (e->h_packed) CU(cudaFreeHost(e->h_packed));
+        e->h_packed = nullptr;
+        e->cap_h_packed = 0;
+        CU(cudaHostAlloc(&e->h_packed, bytes, cudaHostAllocDefault));
+        e->cap_h_packed = bytes;
+    }
+    if (ACQ_HOST_RECORDS && rows <= (size_t)kHostRecordRowsMax) {
+        if (rows > e->cap_h_records) {
+            if ((rc = drain(e))) return rc;
+            if (e->h_records) CU(cudaFreeHost(e->h_records));
+            e->h_records = e->dh_records = nullptr;
+            e->cap_h_records = 0;
+            CU(cudaHostAlloc(&e->h_records, rows * sizeof(acq_record), cudaHostAllocMapped));
+            CU(cudaHostGetDevicePointer(&e->dh_records, e->h_records, 0));
+            e->cap_h_records = rows;
+        }
+        return ACQ_OK;
+    }
+    return grow(e, e->d_records, e->cap_rows, rows);
 }
 
-// Split the selection into the 1 ms-window (Navstar/QZSS/SBAS) and E1B work lists.
+// Split the selection into the 1 ms-window (Navstar/QZSS/SBAS) and E1B work lists.  The whole table and single
+// satellites (what the literal SearchTask loop asks for, one satellite per capture) use lists built at acq_create;
+// any other list is uploaded, which drains the engine first.
 int set_selection(acq_engine *e, const int32_t *sel, int n_sel)
 {
-    std::vector<int32_t> s;
+    const int n_sats = (int)e->sats.size();
     if (!sel) {
-        s.resize(e->sats.size());
-        for (size_t i = 0; i < s.size(); i++) s[i] = (int32_t)i;
-    } else {
-        if (n_sel <= 0) return fail(ACQ_ERR_ARG, "n_sel must be > 0 when sel is given");
-        s.assign(sel, sel + n_sel);
+        if (e->sel_kind != 0) {
+            e->sel_cache.resize(n_sats);
+            for (int i = 0; i < n_sats; i++) e->sel_cache[i] = i;
+            e->sel_kind = 0;
+        }
+        e->cur_work = e->d_work_full;
+        e->cur_slot_sat = e->d_sat_full;
+        e->n_l1 = e->full_n_l1;
+        e->n_e1b = n_sats - e->full_n_l1;
+        e->n_slots = n_sats;
+        return ACQ_OK;
     }
-    for (int32_t v : s)
-        if (v < 0 || v >= (int32_t)e->sats.size())
-            return fail(ACQ_ERR_ARG, "satellite index %d outside the table (0..%zu)", v, e->sats.size() - 1);
-    if (e->sel_valid && s == e->sel_cache) return ACQ_OK;
+    if (n_sel <= 0) return fail(ACQ_ERR_ARG, "n_sel must be > 0 when sel is given");
+    for (int i = 0; i < n_sel; i++)
+        if (sel[i] < 0 || sel[i] >= n_sats)
+            return fail(ACQ_ERR_ARG, "satellite index %d outside the table (0..%d)", sel[i], n_sats - 1);
+    if (n_sel == 1) {
+        const int sat = sel[0];
+        e->sel_cache.assign(1, sat);
+        e->sel_kind = 1;
+        e->cur_work = e->d_work_single + sat;
+        e->cur_slot_sat = e->d_sat_full + sat;
+        e->n_e1b = (e->sats[sat].type == ACQ_E1B) ? 1 : 0;
+        e->n_l1 = 1 - e->n_e1b;
+        e->n_slots = 1;
+        return ACQ_OK;
+    }
+    if (e->sel_kind == 2 && (int)e->sel_cache.size() == n_sel && std::equal(sel, sel + n_sel, e->sel_cache.begin())) {
+        e->cur_work = e->d_work;
+        e->cur_slot_sat = e->d_slot_sat;
+        return ACQ_OK;
+    }
     std::vector<int2> work;
-    std::vector<int> slot_sat(s.size());
+    work.reserve(n_sel);
     int n_l1 = 0;
     for (int pass = 0; pass < 2; pass++)
-        for (size_t i = 0; i < s.size(); i++) {
-            const bool e1b = (e->sats[s[i]].type == ACQ_E1B);
+        for (int i = 0; i < n_sel; i++) {
+            const bool e1b = (e->sats[sel[i]].type == ACQ_E1B);
             if ((pass == 1) != e1b) continue;
-            work.push_back(make_int2(s[i], (int)i));
+            work.push_back(make_int2(sel[i], i));
             if (!e1b) n_l1++;
         }
-    for (size_t i = 0; i < s.size(); i++) slot_sat[i] = s[i];
-    if (s.size() > e->cap_slots) {
-        CU(cudaStreamSynchronize(e->stream));
+    int rc = drain(e);  // the lists may still be read by a search in flight; the copies below are synchronous
+    if (rc) return rc;
+    e->sel_kind = -1;
+    if ((size_t)n_sel > e->cap_slots) {
         if (e->d_work) CU(cudaFree(e->d_work));
         if (e->d_slot_sat) CU(cudaFree(e->d_slot_sat));
         e->d_work = nullptr;
         e->d_slot_sat = nullptr;
         e->cap_slots = 0;
-        CU(cudaMalloc(&e->d_work, s.size() * sizeof(int2)));
-        CU(cudaMalloc(&e->d_slot_sat, s.size() * sizeof(int)));
-        e->cap_slots = s.size();
+        CU(cudaMalloc(&e->d_work, (size_t)n_sel * sizeof(int2)));
+        CU(cudaMalloc(&e->d_slot_sat, (size_t)n_sel * sizeof(int)));
+        e->cap_slots = (size_t)n_sel;
     }
-    // synchronous copies (pageable source): the vectors die at return
-    CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemcpy(e->d_work, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(e->d_slot_sat, slot_sat.data(), slot_sat.size() * sizeof(int), cudaMemcpyHostToDevice));
-    e->sel_cache = s;
-    e->sel_valid = true;
+    CU(cudaMemcpy(e->d_slot_sat, sel, (size_t)n_sel * sizeof(int), cudaMemcpyHostToDevice));
+    e->sel_cache.assign(sel, sel + n_sel);
+    e->sel_kind = 2;
+    e->cur_work = e->d_work;
+    e->cur_slot_sat = e->d_slot_sat;
     e->n_l1 = n_l1;
-    e->n_e1b = (int)s.size() - n_l1;
-    e->n_slots = (int)s.size();
+    e->n_e1b = n_sel - n_l1;
+    e->n_slots = n_sel;
     return ACQ_OK;
 }
 
-// Enqueue front end + search + best-Doppler on `st` for captures already on the device.
-int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq_record *out_dev, cudaStream_t st)
+// Enqueue front end + forward FFT + search (which ends in the best-Doppler pick) on `st` for captures already on the
+// device.  records_dev: where the kernels write the records (device memory, or the device alias of mapped host memory);
+// flag_dev: mapped completion word, or NULL.
+int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq_record *records_dev, unsigned *flag_dev,
+                   cudaStream_t st)
 {
     const int K = e->prm.k_noncoh;
     const int blocks = n_captures * K;
     const bool prof = e->profiling;
+    if (e->dev_pending) CU(cudaStreamWaitEvent(st, e->dev_done, 0));  // a no-op on the stream that recorded it
     // Programmatic dependent launch between the kernels of a search: a gain where the search is a few waves of tiles
     // (single captures: 85 -> 77 us for the reference's 32-PRN cold start), a measured 3 % loss on long searches
     // (the search CTAs are placed while the forward FFT still holds SMs), so by default only up to 64 tiles per SM.
     // Event records between the kernels (profiling) would serialise them anyway.
     const long long tiles_total = (long long)n_captures * e->n_slots * e->n_dop * K;
-    const bool pdl = !prof && (e->pdl == 1 || (e->pdl < 0 && tiles_total <= 64LL * e->sm_count));
+    const bool pdl = !prof && (ACQ_FORCE_PDL == 1 || (ACQ_FORCE_PDL < 0 && tiles_total <= 64LL * e->sm_count));
+    if (++e->epoch == 0) e->epoch = 1;
     if (prof) CU(cudaEventRecord(e->prof[0], st));
     e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
@@ -275,29 +390,41 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     a.n_shift = e->n_shift;
     a.smax = e->smax;
     a.cd_div = e->cd_div;
+    a.slot_sat = e->cur_slot_sat;
+    a.records = records_dev;
+    a.row_count = e->d_row_count;
+    a.rows_done = e->d_rows_done;
+    a.host_flag = flag_dev;
+    a.n_rows_total = (unsigned)(n_captures * e->n_slots);
+    a.epoch = e->epoch;
+    a.partial = e->d_partial;
+    a.flags = e->d_flags;
+    a.wait_prior = 1;
     if (e->n_l1 > 0) {
-        a.work = e->d_work;
+        a.work = e->cur_work;
         a.n_work = e->n_l1;
         a.n_tiles = (long long)n_captures * e->n_l1 * e->n_dop;
         e->launches += launch_search(a, false, e->sm_count, st, pdl);
+        // The C/A kernel raises its launch-dependents trigger only after its own wait for the forward FFT, so an E1B
+        // launch chained to it by programmatic dependent launch starts with the capture spectra complete: it does
+        // not wait again, and its CTAs move in as the C/A kernel's last CTAs retire (the two write disjoint rows).
+        if (pdl) a.wait_prior = 0;
     }
     if (e->n_e1b > 0) {
-        a.work = e->d_work + e->n_l1;
+        a.work = e->cur_work + e->n_l1;
         a.n_work = e->n_e1b;
         a.n_tiles = (long long)n_captures * e->n_e1b * e->n_dop;
         // Cluster/DSMEM form when every tile can have a cluster of its own (one wave: 9 us per tile against
-        // 12.5 us for the one-CTA form, measured), when forced (A/B runs), and always for non-coherent sums
+        // 12.5 us for the one-CTA form, measured), when forced (variant builds), and always for non-coherent sums
         // (its threads keep the block powers of their 16 lags in registers).  With more tiles than that the
         // one-CTA-per-tile form has 2.9x the throughput (profiles/r1_e1b_cluster_ab.json).
-        const bool use_cluster = K > 1 || e->e1b_kernel == 2 || (e->e1b_kernel == 0 && a.n_tiles <= e->sm_count / 4);
+        const bool use_cluster =
+            K > 1 || ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && a.n_tiles <= e->sm_count / 4);
         if (use_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st, pdl);
         else e->launches += launch_search(a, true, e->sm_count, st, pdl);
     }
-    if (prof) CU(cudaEventRecord(e->prof[3], st));
-    e->launches += launch_best_dop(e->d_cells, e->d_slot_sat, out_dev, n_captures, e->n_slots, e->n_dop,
-                                   e->prm.dop_lo, st, pdl);
     if (prof) {
-        CU(cudaEventRecord(e->prof[4], st));
+        CU(cudaEventRecord(e->prof[3], st));
         e->prof_valid = true;
     }
     CU(cudaGetLastError());
@@ -314,12 +441,27 @@ int check_search_args(acq_engine *e, const void *packed, int n_captures, const v
     return ACQ_OK;
 }
 
-// after set_selection: a search kernel launch indexes its tiles with 32 bits
+// after set_selection: a search kernel launch indexes its tiles with 32 bits (and four units per tile with 64)
 int check_tile_count(acq_engine *e, int n_captures)
 {
     if ((double)n_captures * (double)e->n_slots * (double)e->n_dop > (double)acq::kMaxTilesPerLaunch)
         return fail(ACQ_ERR_UNSUPPORTED, "search too large for one call (more than 2^31 - 1 tiles): split the captures");
     return ACQ_OK;
+}
+
+// Wait for a host-polled search: the kernels store `epoch` to the mapped completion word once the last record is
+// in host memory.  The stream is queried now and then so that a failed launch cannot hang the caller.
+int poll_flag(acq_engine *e)
+{
+    volatile unsigned *flag = e->h_flag;
+    for (unsigned spins = 1;; spins++) {
+        if (*flag == e->epoch) return ACQ_OK;
+        if ((spins & 0x3ff) == 0) {
+            const cudaError_t q = cudaStreamQuery(e->stream);
+            if (q == cudaSuccess) return (*flag == e->epoch) ? ACQ_OK : fail(ACQ_ERR_CUDA, "search finished without its completion signal");
+            if (q != cudaErrorNotReady) return fail(ACQ_ERR_CUDA, "search failed: %s", cudaGetErrorString(q));
+        }
+    }
 }
 
 int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel, acq_record *out,
@@ -328,25 +470,53 @@ int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int3
     int rc = check_search_args(e, packed, n_captures, out);
     if (rc) return rc;
     DeviceGuard g(e->device);
+    e->last_captures = 0;  // until this search is enqueued, there are no spectra acq_refine could use
     if ((rc = set_selection(e, sel, n_sel))) return rc;
     if ((rc = check_tile_count(e, n_captures))) return rc;
     if ((rc = ensure_scratch(e, n_captures, e->n_slots, true))) return rc;
     const size_t bytes = (size_t)n_captures * e->prm.k_noncoh * e->block_bytes;
-    CU(cudaMemcpyAsync(e->d_packed, packed, bytes, cudaMemcpyHostToDevice, e->stream));
-    e->last_captures = 0;
-    if ((rc = enqueue_search(e, e->d_packed, n_captures, e->d_records, e->stream))) return rc;
-    e->last_captures = n_captures;
     const size_t rows = (size_t)n_captures * e->n_slots;
-    CU(cudaMemcpyAsync(out, e->d_records, rows * sizeof(acq_record), cudaMemcpyDeviceToHost, e->stream));
+    const bool host_records = ACQ_HOST_RECORDS && rows <= (size_t)kHostRecordRowsMax;
+    const long long tiles_total = (long long)rows * e->n_dop * e->prm.k_noncoh;
+    const bool poll = host_records && sync && !grid && !e->profiling && tiles_total <= 64LL * e->sm_count;
+    const uint8_t *src = packed;
+    if (bytes <= kStagePackedMax) {
+        memcpy(e->h_packed, packed, bytes);
+        src = e->h_packed;
+    }
+    CU(cudaMemcpyAsync(e->d_packed, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = enqueue_search(e, e->d_packed, n_captures, host_records ? e->dh_records : e->d_records,
+                             poll ? e->dh_flag : nullptr, e->stream)))
+        return rc;
+    e->last_captures = n_captures;
+    if (!host_records) CU(cudaMemcpyAsync(out, e->d_records, rows * sizeof(acq_record), cudaMemcpyDeviceToHost, e->stream));
     if (grid)
         CU(cudaMemcpyAsync(grid, e->d_cells, rows * e->n_dop * sizeof(acq_cell), cudaMemcpyDeviceToHost, e->stream));
-    if (sync) {
-        CU(cudaStreamSynchronize(e->stream));
-    } else {
+    if (!sync) {
         CU(cudaEventRecord(e->done, e->stream));
         e->pending = true;
+        e->pending_rows = host_records ? (int)rows : 0;
+        e->pending_out = out;
+        return ACQ_OK;
     }
+    if (poll) {
+        if ((rc = poll_flag(e))) return rc;
+    } else {
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    e->dev_pending = false;  // this search was ordered behind the last device-path search, so that one is complete too
+    if (host_records) memcpy(out, e->h_records, rows * sizeof(acq_record));
     return ACQ_OK;
+}
+
+// completion of an acq_submit: records that the kernels left in the mapped buffer go to the caller's array
+void finish_pending(acq_engine *e)
+{
+    if (e->pending_rows > 0 && e->pending_out)
+        memcpy(e->pending_out, e->h_records, (size_t)e->pending_rows * sizeof(acq_record));
+    e->pending = false;
+    e->pending_rows = 0;
+    e->pending_out = nullptr;
 }
 
 }  // namespace
@@ -359,6 +529,8 @@ int acq_abi_version(void) { return ACQ_ABI_VERSION; }
 int acq_params_default(acq_params *p)
 {
     if (!p) return fail(ACQ_ERR_ARG, "params is NULL");
+    memset(p, 0, sizeof *p);
+    p->struct_size = (uint32_t)sizeof(acq_params);
     p->dop_lo = -20;  // int(-5000/BIN_SIZE), gps/search.cpp:465
     p->dop_hi = 20;
     p->half_bin = 0;
@@ -368,7 +540,6 @@ int acq_params_default(acq_params *p)
     p->wrap_mode = ACQ_WRAP_REFERENCE;
     p->sample_bits = 1;  // the sampler's I_sign stream, gps/search.cpp:408-411
     p->code_doppler = 0;
-    p->reserved[0] = p->reserved[1] = p->reserved[2] = 0;
     return ACQ_OK;
 }
 
@@ -378,8 +549,17 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     *out = nullptr;
     if (!sats || n_sats <= 0 || n_sats > 4096) return fail(ACQ_ERR_ARG, "bad satellite table (n_sats=%d)", n_sats);
     acq_params prm;
-    if (params) prm = *params;
-    else acq_params_default(&prm);
+    if (params) {
+        // the first member is the size of the caller's structure: anything but this library's layout is refused
+        // before a byte beyond it is read
+        if (params->struct_size != (uint32_t)sizeof(acq_params))
+            return fail(ACQ_ERR_ARG, "acq_params.struct_size is %u, this library (ABI version %d) expects %zu: fill the "
+                        "structure with acq_params_default() from the matching acq_b200.h", params->struct_size,
+                        ACQ_ABI_VERSION, sizeof(acq_params));
+        prm = *params;
+    } else {
+        acq_params_default(&prm);
+    }
     if (prm.dop_hi < prm.dop_lo) return fail(ACQ_ERR_ARG, "dop_hi < dop_lo");
     if (prm.k_noncoh < 1 || prm.k_noncoh > 255) return fail(ACQ_ERR_ARG, "k_noncoh must be in 1..255");
     if (prm.half_bin != 0 && prm.half_bin != 1) return fail(ACQ_ERR_ARG, "half_bin must be 0 or 1");
@@ -388,7 +568,8 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     if (prm.sample_bits < 0 || prm.sample_bits > 2) return fail(ACQ_ERR_ARG, "sample_bits must be 1 or 2 (0 = 1)");
     if (prm.sample_bits == 0) prm.sample_bits = 1;  // the member used to be "reserved, must be 0"
     if (prm.code_doppler != 0 && prm.code_doppler != 1) return fail(ACQ_ERR_ARG, "code_doppler must be 0 or 1");
-    if (prm.reserved[0] || prm.reserved[1] || prm.reserved[2]) return fail(ACQ_ERR_ARG, "reserved members must be 0");
+    for (int32_t r : prm.reserved)
+        if (r) return fail(ACQ_ERR_ARG, "reserved members must be 0");
     // code-Doppler compensation: largest lag shift over the Doppler range, reached in the last block
     const int cd_div = 385 * (prm.half_bin ? 2 : 1);  // FS/DECIM/f_L1 = 4.092e6/1575.42e6 = 1/385 exactly
     int smax = 0;
@@ -453,11 +634,40 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
         }                                                                                           \
     } while (0)
 
-    if (const char *kv = getenv("ACQ_PDL")) e->pdl = strcmp(kv, "0") != 0 ? 1 : 0;
-    if (const char *kv = getenv("ACQ_E1B_KERNEL")) e->e1b_kernel = !strcmp(kv, "cta") ? 1 : !strcmp(kv, "cluster") ? 2 : 0;
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUE(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
+    CUE(cudaEventCreateWithFlags(&e->dev_done, cudaEventDisableTiming));
     CUE(search_kernels_configure());
+    // hand-over buffers of the balanced K = 1 launch, completion counters, mapped completion word
+    CUE(cudaMalloc(&e->d_partial, (size_t)2 * e->sm_count * 16 * 256 * sizeof(float2)));
+    CUE(cudaMalloc(&e->d_flags, (size_t)2 * e->sm_count * sizeof(unsigned)));
+    CUE(cudaMemset(e->d_flags, 0, (size_t)2 * e->sm_count * sizeof(unsigned)));
+    CUE(cudaMalloc(&e->d_rows_done, sizeof(unsigned)));
+    CUE(cudaMemset(e->d_rows_done, 0, sizeof(unsigned)));
+    CUE(cudaHostAlloc(&e->h_flag, sizeof(unsigned), cudaHostAllocMapped));
+    *e->h_flag = 0;
+    CUE(cudaHostGetDevicePointer(&e->dh_flag, e->h_flag, 0));
+    {   // work lists that need no upload: the whole table (C/A rows first, then E1B) and every single satellite
+        std::vector<int2> full, single(n_sats);
+        std::vector<int> ident(n_sats);
+        for (int pass = 0; pass < 2; pass++)
+            for (int i = 0; i < n_sats; i++) {
+                const bool e1b = (sats[i].type == ACQ_E1B);
+                if ((pass == 1) != e1b) continue;
+                full.push_back(make_int2(i, i));
+                if (!e1b) e->full_n_l1++;
+            }
+        for (int i = 0; i < n_sats; i++) {
+            single[i] = make_int2(i, 0);
+            ident[i] = i;
+        }
+        CUE(cudaMalloc(&e->d_work_full, n_sats * sizeof(int2)));
+        CUE(cudaMalloc(&e->d_work_single, n_sats * sizeof(int2)));
+        CUE(cudaMalloc(&e->d_sat_full, n_sats * sizeof(int)));
+        CUE(cudaMemcpy(e->d_work_full, full.data(), n_sats * sizeof(int2), cudaMemcpyHostToDevice));
+        CUE(cudaMemcpy(e->d_work_single, single.data(), n_sats * sizeof(int2), cudaMemcpyHostToDevice));
+        CUE(cudaMemcpy(e->d_sat_full, ident.data(), n_sats * sizeof(int), cudaMemcpyHostToDevice));
+    }
 
     // ---- twiddle tables, constants (double precision on the host, rounded once)
     const double two_pi = 6.283185307179586476925286766559;
@@ -487,8 +697,7 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     float hb[17];
     for (int i = 0; i < 16; i++) hb[i] = (float)taps_even[i];
     hb[16] = (float)0.500009;
-    launch_tables_init(cC, hb);
-    CUE(cudaGetLastError());
+    CUE(launch_tables_init(cC, hb));
     CUE(cudaMalloc(&e->d_tables, tables.size() * sizeof(float2)));
     CUE(cudaMemcpy(e->d_tables, tables.data(), tables.size() * sizeof(float2), cudaMemcpyHostToDevice));
     {
@@ -518,7 +727,9 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
             codelen_boc[2 * i + 1] = 1;
         } else {
             ca_code_bits(sats[i].t1, sats[i].t2, &chips[(size_t)i * 128]);
-            codelen_boc[2 * i] = 1023;
+            // SearchInit builds replicas for Navstar and QZSS rows only (gps/search.cpp:244): an SBAS row of the
+            // table keeps the all-zero spectrum of the reference's static code[] array (codelen 0 = no replica)
+            codelen_boc[2 * i] = (sats[i].type == ACQ_SBAS) ? 0 : 1023;
             codelen_boc[2 * i + 1] = 0;
         }
     }
@@ -575,12 +786,17 @@ int acq_search_device(acq_engine *e, const uint8_t *packed_dev, int n_captures, 
     if (((uintptr_t)packed_dev & 15) != 0)
         return fail(ACQ_ERR_ARG, "packed_dev must be 16-byte aligned (the front end stages it with bulk async copies)");
     DeviceGuard g(e->device);
+    e->last_captures = 0;  // spectra now belong to a search on the caller's stream: acq_refine does not apply
     if ((rc = set_selection(e, sel, n_sel))) return rc;
     if ((rc = check_tile_count(e, n_captures))) return rc;
     if ((rc = ensure_scratch(e, n_captures, e->n_slots, false))) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    e->last_captures = 0;  // spectra now belong to a search on the caller's stream: acq_refine does not apply
-    return enqueue_search(e, packed_dev, n_captures, out_dev, st);
+    if ((rc = enqueue_search(e, packed_dev, n_captures, out_dev, nullptr, st))) return rc;
+    if (st != e->stream) {  // whatever uses the engine's scratch next (any stream, or the host) waits for this search
+        CU(cudaEventRecord(e->dev_done, st));
+        e->dev_pending = true;
+    }
+    return ACQ_OK;
 }
 
 int acq_submit(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel, acq_record *out)
@@ -595,7 +811,7 @@ int acq_poll(acq_engine *e)
     DeviceGuard g(e->device);
     cudaError_t q = cudaEventQuery(e->done);
     if (q == cudaSuccess) {
-        e->pending = false;
+        finish_pending(e);
         return 1;
     }
     if (q == cudaErrorNotReady) return 0;
@@ -608,8 +824,12 @@ int acq_wait(acq_engine *e)
     if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");
     if (!e->pending) return ACQ_OK;
     DeviceGuard g(e->device);
-    e->pending = false;
-    CU(cudaEventSynchronize(e->done));
+    const cudaError_t w = cudaEventSynchronize(e->done);
+    if (w != cudaSuccess) {
+        e->pending = false;
+        return fail(ACQ_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(w));
+    }
+    finish_pending(e);
     return ACQ_OK;
 }
 
@@ -633,9 +853,9 @@ int acq_refine(acq_engine *e, const acq_record *rec, int n_records, acq_fine *ou
             return fail(ACQ_ERR_ARG, "record %d: Doppler index %d outside %d..%d", i, r.dop, e->prm.dop_lo, e->prm.dop_hi);
     }
     DeviceGuard g(e->device);
-    int rc = grow(e->d_ref_rec, e->cap_ref_rec, (size_t)n_records);
+    int rc = grow(e, e->d_ref_rec, e->cap_ref_rec, (size_t)n_records);
     if (rc) return rc;
-    if ((rc = grow(e->d_fine, e->cap_fine, (size_t)n_records))) return rc;
+    if ((rc = grow(e, e->d_fine, e->cap_fine, (size_t)n_records))) return rc;
     CU(cudaMemcpyAsync(e->d_ref_rec, rec, (size_t)n_records * sizeof(acq_record), cudaMemcpyHostToDevice, e->stream));
     e->launches += launch_refine(e->d_Dp, e->d_Ep, e->d_ref_rec, e->d_sat_type, e->d_fine, n_records, e->n_slots,
                                  e->prm.k_noncoh, e->nvar, e->prm.half_bin, e->ext_len, e->Q, e->n_shift, e->smax,
@@ -733,8 +953,9 @@ int acq_get_kernel_ms(acq_engine *e, float *out, int n_out)
     if (!e || !out || n_out < 4) return fail(ACQ_ERR_ARG, "bad argument");
     if (!e->prof_valid) return fail(ACQ_ERR_ARG, "no profiled search yet (call acq_set_profiling first)");
     DeviceGuard g(e->device);
-    CU(cudaEventSynchronize(e->prof[4]));
-    for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&out[i], e->prof[i], e->prof[i + 1]));
+    CU(cudaEventSynchronize(e->prof[3]));
+    for (int i = 0; i < 3; i++) CU(cudaEventElapsedTime(&out[i], e->prof[i], e->prof[i + 1]));
+    out[3] = 0.0f;  // the best-Doppler pick is part of the search kernels
     return ACQ_OK;
 }
 

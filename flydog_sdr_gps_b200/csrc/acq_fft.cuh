@@ -406,24 +406,21 @@ __device__ __forceinline__ void subfft4096_inv3t(float2 (&x)[16], const int k2, 
 //     column t and writes its output n0 to row n0, column t: the same 16 slots, so the reuse is
 //     thread-private), and the code-spectrum run E (32 KiB + 16 B: the Doppler offset is only 8-byte aligned)
 //     lands in a buffer of its own.  The L2 round trip leaves the dependent chain of every warp.
-//   * Exchange rows are padded to 272 elements (16 x 17): the B->C tile of a half-warp lives in the row that
-//     half-warp has just consumed (row n0, read by nobody else), element (n1, c) at 17 n1 + c -- conflict-free
-//     column writes and row reads with compile-time offsets, and no separate tile buffer.
+//   * The B->C tile of a half-warp lives in the exchange row that half-warp has just consumed (row n0, read by
+//     nobody else), XOR-swizzled in 16-byte chunks -- conflict-free column writes and 128-bit row reads, no padding
+//     (so a capture residue can still land in the buffer by one 32 KiB bulk copy) and no separate tile buffer.
 //   * TMEM column 30/31 of residue k2 (the unused sixteenth twiddle slot) carries the stage-A base
 //     W16384^{4t + (k2+1 mod 4)} of the NEXT sub-FFT, so it arrives with the stage-B twiddles.
 // Shared memory per CTA: 2 x 34 KiB (S1) + 32 KiB + 16 B (E) + one mbarrier.
 // ---------------------------------------------------------------------------------------------
 constexpr int kEBufElems = kSub + 2;
-#ifndef ACQ_PADDED_ROWS
-#define ACQ_PADDED_ROWS 0
-#endif
 #ifndef ACQ_SWZ128
 #define ACQ_SWZ128 1   // E1B kernel (subfft4096_inv4s); the C/A kernel takes it as a template parameter
 #endif
-constexpr int kRowElems = ACQ_PADDED_ROWS ? 16 * 17 : 256;  // exchange row (padded: B->C tile at 17 n1 + c; else XOR swizzle)
-constexpr int kS1pElems = 16 * kRowElems;     // one half of the padded exchange buffer
+constexpr int kRowElems = 256;                // exchange row; the B->C tile of a half-warp lives in it, XOR-swizzled
+constexpr int kS1pElems = 16 * kRowElems;     // one half of the exchange buffer
 struct FftSmem4 {
-    float2 *S1;  // [2][16][272]
+    float2 *S1;  // [2][16][256]
     float2 *E;   // [4098]
     unsigned long long *bar;
 };
@@ -542,22 +539,6 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
     tmem_wait_ld();
     b = TW_AT(15);
     __syncwarp();  // the half-warp has consumed its row: reuse it as the B->C tile, element (n1, c) at 17 n1 + c
-#if ACQ_PADDED_ROWS
-    {
-        float2 *dst = row + c;
-        dst[0] = x[r16(0)];
-#pragma unroll
-        for (int i = 0; i < 8; i++) dst[(i + 1) * 17] = cmul(x[r16(i + 1)], TW_AT(i));
-#pragma unroll
-        for (int i = 0; i < 7; i++) dst[(i + 9) * 17] = cmul(x[r16(i + 9)], TW_AT(i + 8));
-    }
-    __syncwarp();
-    {
-        const float2 *src = row + 17 * c;  // this thread is now (n0, n1 = c)
-#pragma unroll
-        for (int cc = 0; cc < 16; cc++) x[cc] = src[cc];
-    }
-#else
     if constexpr (SWZ128) {
         {   // unpadded row, swizzled in 16-byte chunks: element (n1, c) in chunk (c >> 1) ^ (n1 & 7), slot c & 1 of tile row
             // n1, so that stage C reads two adjacent elements with one 128-bit load (half the loads and address XORs):
@@ -601,7 +582,6 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
                 asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x[cc].x), "=f"(x[cc].y) : "r"(rb ^ (8u * cc)) : "memory");
         }
     }
-#endif
     radix16_inv(x);
 }
 #undef TW_AT

@@ -8,13 +8,11 @@
 //   K6b k_build_ext  : polyphase, margin-extended code-spectrum rows                 (search.cpp:283-284,471)
 //   K3-5 k_search_l1 / k_search_e1b : conj(D).C product, 16384-point inverse FFT, |.|^2, non-coherent
 //                      sum, max / first-argmax / mean per (capture, sat, Doppler)    (search.cpp:465-494)
-//   K5b k_best_dop   : best-snr Doppler per (capture, sat), lowest index on ties    (search.cpp:495)
+//   K5b finish_tile  : best-snr Doppler per (capture, sat), lowest index on ties    (search.cpp:495), folded into K3-5
 //
 // The half-band stages use explicit round-to-nearest mul/add in the reference's summation order
 // (no FMA contraction), so the FFT inputs are bit-identical to the reference's x86 build.
 #include <cooperative_groups.h>
-#include <stdlib.h>
-#include <string.h>
 
 #include "acq_fft.cuh"
 #include "acq_kernels.cuh"
@@ -25,11 +23,11 @@ namespace acq {
 //   [0] = COEF[0], [1..15] = COEF[2], COEF[4] .. COEF[30], [16] = COEF[15]
 __constant__ float c_hb[17];
 
-int launch_tables_init(const float2 *h_cC, const float *h_hb)
+cudaError_t launch_tables_init(const float2 *h_cC, const float *h_hb)
 {
-    cudaMemcpyToSymbol(c_cC, h_cC, sizeof(float2) * 64);
-    cudaMemcpyToSymbol(c_hb, h_hb, sizeof(float) * 17);
-    return 0;
+    cudaError_t e = cudaMemcpyToSymbol(c_cC, h_cC, sizeof(float2) * 64);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_hb, h_hb, sizeof(float) * 17);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,7 +199,7 @@ __global__ void __launch_bounds__(256) k_hb1_code(const uint32_t *__restrict__ c
     const int i0 = 2 * o;
     auto sample = [&](int j) -> float {
         const int i = i0 + j;
-        if (i >= ACQ_NSAMPLES) return 0.0f;
+        if (i >= ACQ_NSAMPLES || codelen == 0) return 0.0f;  // codelen 0: a row the reference builds no replica for (SBAS)
         const int ci = (i >> 4) % codelen;
         unsigned c = (cw[ci >> 5] >> (ci & 31)) & 1u;
         if (boc) c ^= ((i & 15) >= 8) ? 1u : 0u;
@@ -271,7 +269,7 @@ template <bool POLY>
 __global__ void __launch_bounds__(256, 1) k_fwd_fft(const float2 *__restrict__ x2, float2 *__restrict__ out,
                                                     const float2 *__restrict__ tables, int n_rows)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const FftSmem3 s = fft_smem3_carve(smem);
     float2 *Z = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());
     const int t = threadIdx.x;
@@ -331,7 +329,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const FftSmem3 s = fft_smem3_carve(smem);
     float2 *Y = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());  // [2][16][256]
     const int t = threadIdx.x;
@@ -456,7 +454,7 @@ __device__ __forceinline__ Peak block_reduce_peak(Peak v, float *red_f, int *red
 }
 
 struct TileIdx {
-    int sat, slot, cap, d, dop, v;
+    int sat, slot, cap, d, dop, v, wi;
     // The host keeps a launch below 2^31 tiles (launch_search), so the decomposition runs on 32-bit unsigned
     // divisions: every warp pays it once per tile, and a K = 1 tile is only four sub-FFTs long.
     __device__ __forceinline__ TileIdx(const SearchArgs &p, long long tile)
@@ -465,13 +463,32 @@ struct TileIdx {
         const unsigned cw = tl / nd;
         d = (int)(tl - cw * nd);
         cap = (int)(cw / nw);
-        const int wi = (int)(cw - (unsigned)cap * nw);
+        wi = (int)(cw - (unsigned)cap * nw);
         const int2 wk = p.work[wi];
         sat = wk.x;
         slot = wk.y;
+        set_dop(p);
+    }
+    __device__ __forceinline__ void set_dop(const SearchArgs &p)
+    {
         const int h = p.dop_lo + d;
         v = p.half_bin ? (h & 1) : 0;
         dop = p.half_bin ? ((h - v) >> 1) : h;
+    }
+    // the next tile in launch order, without divisions
+    __device__ __forceinline__ void advance(const SearchArgs &p)
+    {
+        if (++d == p.n_dop) {
+            d = 0;
+            if (++wi == p.n_work) {
+                wi = 0;
+                cap++;
+            }
+            const int2 wk = p.work[wi];
+            sat = wk.x;
+            slot = wk.y;
+        }
+        set_dop(p);
     }
 };
 
@@ -484,14 +501,82 @@ __device__ __forceinline__ size_t d_row(const SearchArgs &p, const TileIdx &ti, 
     return bv * p.n_shift + (size_t)(p.smax + code_shift(b, p.dop_lo + ti.d, p.cd_div));
 }
 
-__device__ __forceinline__ void store_cell(const SearchArgs &p, const TileIdx &ti, const Peak &tot, int L)
+// End of a tile, executed by ONE WHOLE WARP of the CTA (all 32 lanes; `tot` is valid in lane 0):
+//   (1) the tile's cell: ave_pwr = tot_pwr / L, snr = max_pwr / ave_pwr with IEEE division (search.cpp:493-494);
+//   (2) the best-over-Doppler pick of Correlate() (max_snr = 0; for dop ascending: if (snr > max_snr) take it --
+//       search.cpp:455,495), folded into the search kernels: every finished cell bumps the row's counter, and the
+//       warp that brings it to n_dop owns the row -- all other cells were stored and fenced before their writers'
+//       atomicAdd -- scans it (lanes stride over the Doppler cells, then a shuffle reduction that prefers the larger
+//       snr and on equal snr the lower Doppler index: what the sequential scan keeps) and writes the record.  A row
+//       whose snr never exceeds 0 (or is NaN) keeps {lag 0, dop 0, zeros}.  The counter is left at zero for the next
+//       search.  No separate kernel, no launch gap: what remains after the last tile is one 41-cell scan;
+//   (3) optionally the completion signal of the whole search for a host that polls mapped memory.
+// (2) and (3) of finish_tile, out of line (it runs once per row, not once per tile) and on scalar arguments so that
+// the search kernels do not keep their parameter block in registers for it.
+__device__ __noinline__ void pick_best_doppler(const acq_cell *rc, int n_dop, int dop_lo, int sat, acq_record *rec,
+                                               unsigned *row_count, unsigned *rows_done, unsigned *host_flag,
+                                               unsigned n_rows_total, unsigned epoch, int lane)
 {
-    acq_cell c;
-    c.peak = tot.p;
-    c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
-    c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
-    c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
-    p.cells[((size_t)ti.cap * p.n_slots + ti.slot) * p.n_dop + ti.d] = c;
+    __threadfence();
+    float best = 0.0f;
+    int best_d = 0x7fffffff;
+    for (int dd = lane; dd < n_dop; dd += 32) {
+        const float snr = __ldcg(&rc[dd].snr);
+        if (snr > best) best = snr, best_d = dd;  // ascending d within a lane: first maximum kept
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, best, off);
+        const int d2 = __shfl_xor_sync(0xffffffffu, best_d, off);
+        if (s2 > best || (s2 == best && d2 < best_d)) best = s2, best_d = d2;
+    }
+    if (lane != 0) return;
+    *row_count = 0;
+    acq_record r;
+    r.sat = sat;
+    r.lag = 0;
+    r.dop = 0;
+    r.peak = 0.0f;
+    r.noise = 0.0f;
+    r.snr = 0.0f;
+    if (best > 0.0f) {
+        const float4 cc = __ldcg(reinterpret_cast<const float4 *>(rc + best_d));  // {peak, noise, snr, lag}
+        r.lag = __float_as_int(cc.w);
+        r.dop = dop_lo + best_d;
+        r.peak = cc.x;
+        r.noise = cc.y;
+        r.snr = cc.z;
+    }
+    *rec = r;
+    if (host_flag) {
+        __threadfence_system();
+        if (atomicAdd(rows_done, 1u) + 1u == n_rows_total) {
+            *rows_done = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned *>(host_flag) = epoch;
+        }
+    }
+}
+
+__device__ __forceinline__ void finish_tile(const SearchArgs &p, int cap, int slot, int d, const Peak &tot, int L, int lane)
+{
+    const size_t row = (size_t)cap * p.n_slots + slot;
+    acq_cell *rc = p.cells + row * p.n_dop;
+    unsigned prev = 0;
+    if (lane == 0) {
+        acq_cell c;
+        c.peak = tot.p;
+        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
+        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
+        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
+        rc[d] = c;
+        __threadfence();
+        prev = atomicAdd(p.row_count + row, 1u);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev + 1u == (unsigned)p.n_dop)
+        pick_best_doppler(rc, p.n_dop, p.dop_lo, p.slot_sat[slot], p.records + row, p.row_count + row, p.rows_done,
+                          p.host_flag, p.n_rows_total, p.epoch, lane);
 }
 
 // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471, support/simd.cpp:12-40).
@@ -543,49 +628,204 @@ __device__ __forceinline__ Peak merge_warp_peaks(const float *slot_f, const int 
     return v;
 }
 
-template <bool MULTI>
-__global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
+// The C/A search kernels.  Both operands of a sub-FFT are staged in shared memory by TMA bulk copies issued one
+// sub-FFT ahead (see subfft4096_inv4): D into the idle half of the exchange buffer, E into its own 32 KiB buffer; the
+// B->C tiles live inside the exchange rows.  The L2 round trip is off every warp's dependent chain (the load-from-L2
+// A/B form, acq_variants.cuh, is 7 % slower); 98.6 KiB of shared memory per CTA, two CTAs per SM.
+//
+// Unroll factor of the loop over the four residues of a transform.  Rolled, the compiler moves the 16 accumulators
+// between two register sets once per sub-FFT (about 40 MOVs per warp and sub-FFT in the ncu source view); unrolled
+// by two it renames instead.  Measured: K = 1 kernel +1.3 % (cfg5) and -1.2 us per cold-start search (cfg1); K > 1
+// kernel unchanged (27.79 M tiles/s either way), so it stays rolled; by four the kernels spill.
+#ifndef ACQ_K2_UNROLL
+#define ACQ_K2_UNROLL 2
+#endif
+constexpr int kK2Unroll = ACQ_K2_UNROLL;
+
+// Shared prologue/epilogue state of the two C/A kernels.
+struct L1Smem {
+    FftSmem4 s;
+    float *red_f;  // [2 parities][16], then the TMEM slot at [48]
+    int *red_i;    // [2 parities][8]
+};
+__device__ __forceinline__ L1Smem l1_smem_carve(unsigned char *smem)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const FftSmem3T s = fft_smem3t_carve(smem);
-    float *red_f = reinterpret_cast<float *>(smem + fft_smem3t_bytes());  // [2 parities][16]
-    int *red_i = reinterpret_cast<int *>(red_f + 32);                      // [2 parities][8]
+    L1Smem m;
+    m.s = fft_smem4_carve(smem);
+    m.red_f = reinterpret_cast<float *>(smem + fft_smem4_bytes());
+    m.red_i = reinterpret_cast<int *>(m.red_f + 32);
+    return m;
+}
+
+// max / first argmax / sum of this thread's 16 lags n = lag_of3(t, n2) < 4092 (search.cpp:486-490); n grows with n2
+__device__ __forceinline__ Peak thread_peak_l1(const float (&pw)[16], int t)
+{
+    Peak best;
+    best.p = 0.0f;
+    best.n = 0x7fffffff;
+    best.sum = 0.0f;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; n2++) {
+        const int n = lag_of3(t, n2);
+        if (n2 < 15 || n < ACQ_LAGS_L1) {
+            if (pw[n2] > best.p) best.p = pw[n2], best.n = n;
+            best.sum += pw[n2];
+        }
+    }
+    return best;
+}
+
+// k_search_l1 -- K = 1 (the reference's search): BALANCED over the resident CTAs.  A tile is four sub-FFT units
+// (one per input residue k2) whose outputs are accumulated in a fixed chain acc = ((x0 + x1 c1) + x2 c2) + x3 c3.
+// The launch's 4 n_tiles units are cut into gridDim.x equal contiguous ranges, so that e.g. the 1312 tiles of a
+// 32-PRN cold-start search keep all 296 CTAs busy for 17.7 units each instead of five rounds of whole tiles
+// (4.43 waves run as 5).  A tile cut by a range boundary is shared by two CTAs: CTA g runs its HEAD residues
+// 0..j-1 FIRST, stores the partial chain value (16 complex per thread) to `partial[g]` and raises flags[g]; CTA g+1
+// runs the TAIL residues j..3 LAST -- its sub-FFT does not depend on the partial -- then picks the partial up and
+// continues the very same chain, so every cell is bitwise what the unsplit tile computes (the records do not
+// depend on how a search is cut).  Head first / tail last means a waiter's flag was raised a whole range ago; all
+// CTAs of the launch are resident (grid <= 2 per SM) and a CTA only ever waits for its lower neighbour.
+__global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const L1Smem m = l1_smem_carve(smem);
+    const FftSmem4 &s = m.s;
+    float *red_f = m.red_f;
+    int *red_i = m.red_i;
     const int t = threadIdx.x;
     constexpr int L = ACQ_LAGS_L1;
-    // stage-B twiddles live in tensor memory: 128 columns per thread, warps w and w+4 share lanes
     const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
     const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
-    pdl_trigger_search();
-    subfft3_park_twiddles(p.tables, tw_taddr, t);
-    const float2 *base = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
-    int buf = 0;
-    pdl_wait();
-    // The cross-warp merge of a tile's peak is deferred to the next tile: the warp partials are left in a
-    // parity slot and thread 0 merges them after the next tile's first sub-FFT barrier, so the reduction
-    // costs no CTA barrier of its own (it matters at K = 1, where a tile is only four sub-FFTs).
-    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&](int q) {
-        const Peak tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
-        acq_cell c;
-        c.peak = tot.p;
-        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
-        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
-        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
-        p.cells[((size_t)pend_cap * p.n_slots + pend_slot) * p.n_dop + pend_d] = c;
+    subfft4_park_twiddles(p.tables, tw_taddr, t);
+    const float2 *bases = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
+    const uint32_t bar = smem_u32(s.bar);
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (p.wait_prior) pdl_wait();
+    pdl_trigger_search();  // after the wait: a search launch that follows this one need not wait for the front end itself
+
+    // this CTA's range of units [u0, u1): tail residues of tile tA-1 (nA of them), full tiles [tA, tB), head
+    // residues of tile tB (nB of them).  Ranges are at least four units long (grid <= n_tiles).
+    int tA, tB, nA, nB;
+    {
+        const unsigned long long U = 4ull * (unsigned long long)p.n_tiles;
+        const unsigned long long u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1ull) / gridDim.x;
+        tA = (int)((u0 + 3) >> 2);
+        tB = (int)(u1 >> 2);
+        nA = (int)(4ull * tA - u0);
+        nB = (int)(u1 - 4ull * tB);
+    }
+    // thread 0: stage the operands of unit (tn, k2n) -- D into S1 half `half`, E into the E buffer
+    auto issue = [&](const TileIdx &tn, int k2n, int half) {
+        const int r = (k2n - tn.dop) & 3;
+        const int q = (k2n - tn.dop - r) >> 2;
+        const float2 *Dk = p.Dp + d_row(p, tn, 0) * kN + k2n * kSub;
+        const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
+        fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
+        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
+        tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+        tma_load_1d(smem_u32(s.S1 + half * kS1pElems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+    };
+    // the unit after the last full tile (or after the head piece when there is no full tile): the tail piece
+    auto issue_tail = [&](int half) {
+        if (nA > 0) issue(TileIdx(p, tA - 1), 4 - nA, half);
+    };
+    int it = 0;  // units done: S1 half and mbarrier phase parity = it & 1
+    float2 bw;   // stage-A base of the next unit; subfft4096_inv4 leaves the base of residue k2+1 behind
+    {
+        const int k2_first = (nB > 0 || tA < tB) ? 0 : 4 - nA;
+        bw = __ldg(bases + k2_first * 256);
+        if (t == 0) issue(TileIdx(p, nB > 0 ? tB : (tA < tB ? tA : tA - 1)), k2_first, 0);
+    }
+    // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2 (search.cpp:471), operands from shared memory; then
+    // the sub-FFT.  `next` runs in thread 0 right after the CTA barrier: every warp is past its operand reads of this
+    // unit and past stage C of the previous one, so the next unit's operands may land.
+    auto unit = [&](const TileIdx &ti, const int k2, float2 (&x)[16], auto &&next) {
+        float2 *S1b = s.S1 + (it & 1) * kS1pElems;
+        const int r = (k2 - ti.dop) & 3;
+        const int q = (k2 - ti.dop - r) >> 2;
+        const float2 *Dk = S1b + t;
+        const float2 *Ek = s.E + ((p.Q + q) & 1) + t;
+        mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+        for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
+        subfft4096_inv4<true>(x, k2, bw, S1b, t, tw_taddr, [&]() {
+            if (t == 0) next((it + 1) & 1);
+        });
+        it++;
+    };
+    // The cross-warp merge of a tile's peak is deferred to the next unit: the warp partials are left in a parity slot
+    // and warp 0 merges them after that unit's CTA barrier, so the reduction costs no barrier of its own (it matters
+    // at K = 1, where a tile is only four units).
+    int par = 0, pend_cap = 0, pend_slot = 0, pend_d = 0;
+    bool pend = false;
+    auto flush = [&]() {   // warp 0
+        Peak tot;
+        tot.p = tot.sum = 0.0f;
+        tot.n = 0;
+        if (t == 0) tot = merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1));
+        finish_tile(p, pend_cap, pend_slot, pend_d, tot, L, t);
+    };
+    auto tile_done = [&](const TileIdx &ti, const float2 (&acc)[16]) {
+        float pw[16];
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) pw[n2] = cpower(acc[n2]);
+        // parity slot `par` was last read (flush) during the previous tile, before >= 3 CTA barriers
+        warp_reduce_peak(thread_peak_l1(pw, t), red_f + 16 * par, red_i + 8 * par, t);
+        pend = true;
+        pend_cap = ti.cap;
+        pend_slot = ti.slot;
+        pend_d = ti.d;
+        par ^= 1;
     };
 
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const TileIdx ti(p, tile);
-        float P[MULTI ? 16 : 1];
-        float2 acc[16];
-        for (int b = 0; b < p.K; b++) {
-            float2 x[16];
+    float2 acc[16];
+    // ---- head residues of tile tB (continued by CTA blockIdx.x + 1)
+    if (nB > 0) {
+        const TileIdx ti(p, tB);
 #pragma unroll 1
+        for (int k2 = 0; k2 < nB; k2++) {
+            float2 x[16];
+            unit(ti, k2, x, [&](int half) {
+                if (k2 + 1 < nB) issue(ti, k2 + 1, half);
+                else if (tA < tB) issue(TileIdx(p, tA), 0, half);
+                else issue_tail(half);
+            });
+            if (k2 == 0) {
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
+            } else {
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
+            }
+        }
+        float2 *dst = p.partial + (size_t)blockIdx.x * (16 * 256) + t;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) __stcg(dst + 256 * n2, acc[n2]);
+        __threadfence();
+        __syncthreads();
+        if (t == 0) *reinterpret_cast<volatile unsigned *>(p.flags + blockIdx.x) = p.epoch;
+        bw = __ldg(bases + ((tA < tB) ? 0 : (4 - nA)) * 256);
+    }
+    // ---- full tiles
+    if (tA < tB) {
+        TileIdx ti(p, tA);
+        for (int tile = tA; tile < tB; tile++) {
+            float2 x[16];
+#pragma unroll kK2Unroll
             for (int k2 = 0; k2 < 4; k2++) {
-                load_products(x, p, ti, b, k2, t);
-                subfft4096_inv3t(x, k2, __ldg(base + k2 * 256), buf, s, t, tw_taddr);
-                buf ^= 1;
-                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
+                unit(ti, k2, x, [&](int half) {
+                    if (k2 < 3) issue(ti, k2 + 1, half);
+                    else if (tile + 1 < tB) {
+                        TileIdx tn = ti;
+                        tn.advance(p);
+                        issue(tn, 0, half);
+                    } else issue_tail(half);
+                });
+                if (k2 == 0 && pend) {   // previous tile's peak
+                    if (t < 32) flush();
+                    pend = false;
+                }
                 if (k2 == 0) {
 #pragma unroll
                     for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
@@ -594,71 +834,66 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
                     for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
                 }
             }
-            if (MULTI) {
-                // block b was delayed by 16*b samples in the front end (k_front_end), so lag n lines up across blocks
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
-            }
+            tile_done(ti, acc);
+            ti.advance(p);
         }
-        // power, max, first argmax, sum over lags n < 4092   (search.cpp:486-490); a thread's n grows with n2
-        Peak best;
-        best.p = 0.0f;
-        best.n = 0x7fffffff;
-        best.sum = 0.0f;
-#pragma unroll
-        for (int n2 = 0; n2 < 16; n2++) {
-            const int n = lag_of3(t, n2);
-            const float pw = MULTI ? P[n2] : cpower(acc[n2]);
-            if (n2 < 15 || n < L) {
-                if (pw > best.p) best.p = pw, best.n = n;
-                best.sum += pw;
+    }
+    // ---- tail residues of tile tA - 1 (begun by CTA blockIdx.x - 1)
+    if (nA > 0) {
+        const TileIdx ti(p, tA - 1);
+        const int k0 = 4 - nA;
+        if (tA < tB) bw = __ldg(bases + k0 * 256);
+#pragma unroll 1
+        for (int k2 = k0; k2 < 4; k2++) {
+            float2 x[16];
+            unit(ti, k2, x, [&](int half) {
+                if (k2 < 3) issue(ti, k2 + 1, half);
+            });
+            if (pend) {
+                if (t < 32) flush();
+                pend = false;
             }
+            if (k2 == k0) {   // pick up the chain where CTA blockIdx.x - 1 left it (its flag went up a whole range ago)
+                const volatile unsigned *flag = p.flags + (blockIdx.x - 1);
+                while (*flag != p.epoch) {
+                }
+                __threadfence();
+                const float2 *src = p.partial + (size_t)(blockIdx.x - 1) * (16 * 256) + t;
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) acc[n2] = __ldcg(src + 256 * n2);
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
         }
-        // parity slot `par` was last read (flush) during the previous tile, before >= 3 CTA barriers
-        warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
-        pend_cap = ti.cap;
-        pend_slot = ti.slot;
-        pend_d = ti.d;
-        par ^= 1;
+        tile_done(ti, acc);
     }
     __syncthreads();
-    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
+    if (pend && t < 32) flush();
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
-// k_search_l1: as k_search_l1_ldg, but both operands of a sub-FFT are staged in shared memory by TMA bulk copies
-// issued one sub-FFT ahead (see subfft4096_inv4): D into the idle half of the exchange buffer, E into its own
-// 32 KiB buffer; the B->C tiles live inside the exchange rows.  The L2 round trip (the LDG of the _ldg form sits
-// at the head of every warp's dependent chain) is off the critical path; 98.6 KiB of shared memory per CTA.
-constexpr int kIssueLanes = ACQ_PADDED_ROWS ? 16 : 1;  // threads of warp 0 that issue the operand copies
-// Unroll factor of the loop over the four residues of a transform.  Rolled, the compiler moves the 16 accumulators
-// between two register sets once per sub-FFT (about 40 MOVs per warp and sub-FFT in the ncu source view); unrolled
-// by two it renames instead.  Measured: K = 1 kernel +1.3 % (cfg5) and -1.2 us per cold-start search (cfg1); K > 1
-// kernel unchanged (27.79 M tiles/s either way), so it stays rolled; by four the kernels spill.
-#ifndef ACQ_K2_UNROLL
-#define ACQ_K2_UNROLL 2
-#endif
-
-template <bool MULTI>
-__global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
+// k_search_l1_multi -- k_noncoh > 1: a tile runs K inverse FFTs whose powers are summed in registers,
+// P[n] += |r_b[(n + 16 b) mod N]|^2; the 16-lag-per-block code advance is removed in the front end by delaying block
+// b (see k_hb2).  Persistent CTAs stride over the tiles (a tile is 4 K units long: no balancing needed).
+__global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const FftSmem4 s = fft_smem4_carve(smem);
-    float *red_f = reinterpret_cast<float *>(smem + fft_smem4_bytes());  // [2 parities][16]
-    int *red_i = reinterpret_cast<int *>(red_f + 32);                     // [2 parities][8]
+    const L1Smem m = l1_smem_carve(smem);
+    const FftSmem4 &s = m.s;
+    float *red_f = m.red_f;
+    int *red_i = m.red_i;
     const int t = threadIdx.x;
     constexpr int L = ACQ_LAGS_L1;
     const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
     const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
-    pdl_trigger_search();
     subfft4_park_twiddles(p.tables, tw_taddr, t);
     float2 bw = __ldg(p.tables + kT2Elems + t);  // W16384^{4t}: base of residue 0; later bases come from TMEM
     const uint32_t bar = smem_u32(s.bar);
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
-    pdl_wait();
-    // lanes 0..15 of warp 0: stage the operands of sub-FFT (tn, bn, k2n) -- D row by row into S1 half `half`,
-    // E into the E buffer (lane 0)
+    if (p.wait_prior) pdl_wait();
+    pdl_trigger_search();
+    // thread 0: stage the operands of sub-FFT (tn, bn, k2n) -- D into S1 half `half`, E into the E buffer
     auto issue = [&](const TileIdx &tn, int bn, int k2n, int half) {
         const int r = (k2n - tn.dop) & 3;
         const int q = (k2n - tn.dop - r) >> 2;
@@ -670,38 +905,28 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
 #endif
         fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
-        if (t == 0) {
-            mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
-            tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
-        }
-#if ACQ_PADDED_ROWS
-        __syncwarp(0xffffu);
-        tma_load_1d(smem_u32(s.S1 + half * kS1pElems + t * kRowElems), Dk + 256 * t, (uint32_t)(sizeof(float2) * 256), bar);
-#else
-        if (t == 0) tma_load_1d(smem_u32(s.S1 + half * kS1pElems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
-#endif
+        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
+        tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+        tma_load_1d(smem_u32(s.S1 + half * kS1pElems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
     };
-    if (t < kIssueLanes && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&](int q) {
-        const Peak tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
-        acq_cell c;
-        c.peak = tot.p;
-        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
-        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
-        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
-        p.cells[((size_t)pend_cap * p.n_slots + pend_slot) * p.n_dop + pend_d] = c;
+    auto flush = [&]() {   // warp 0: the previous tile's peak (deferred cross-warp merge, see k_search_l1)
+        Peak tot;
+        tot.p = tot.sum = 0.0f;
+        tot.n = 0;
+        if (t == 0) tot = merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1));
+        finish_tile(p, pend_cap, pend_slot, pend_d, tot, L, t);
     };
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileIdx ti(p, tile);
-        float P[MULTI ? 16 : 1];
+        float P[16];
         float2 acc[16];
         for (int b = 0; b < p.K; b++) {
             float2 x[16];
-            constexpr int kK2Unroll = MULTI ? 1 : ACQ_K2_UNROLL;
-#pragma unroll kK2Unroll
+#pragma unroll 1
             for (int k2 = 0; k2 < 4; k2++) {
                 float2 *S1b = s.S1 + (it & 1) * kS1pElems;
                 {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471), operands from smem
@@ -713,18 +938,15 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 #pragma unroll
                     for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
                 }
-#ifndef ACQ_SWZ128_K1
-#define ACQ_SWZ128_K1 1  // K = 1 kernel: 128-bit stage-C loads pay once the residue loop is unrolled (cfg5 26.15 -> 26.55 M tiles/s)
-#endif
-                subfft4096_inv4<MULTI || ACQ_SWZ128_K1>(x, k2, bw, S1b, t, tw_taddr, [&]() {
-                    if (t < kIssueLanes) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                subfft4096_inv4<true>(x, k2, bw, S1b, t, tw_taddr, [&]() {
+                    if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
                         if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
                         else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
                         else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
                     }
                 });
                 it++;
-                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
+                if (t < 32 && b == 0 && k2 == 0 && pend_cap >= 0) flush();
                 if (k2 == 0) {
 #pragma unroll
                     for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
@@ -733,160 +955,19 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                     for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
                 }
             }
-            if (MULTI) {
+            // block b was delayed by 16*b samples in the front end (k_front_end), so lag n lines up across blocks
 #pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
-            }
+            for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
         }
-        Peak best;
-        best.p = 0.0f;
-        best.n = 0x7fffffff;
-        best.sum = 0.0f;
-#pragma unroll
-        for (int n2 = 0; n2 < 16; n2++) {
-            const int n = lag_of3(t, n2);
-            const float pw = MULTI ? P[n2] : cpower(acc[n2]);
-            if (n2 < 15 || n < L) {
-                if (pw > best.p) best.p = pw, best.n = n;
-                best.sum += pw;
-            }
-        }
-        warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
+        warp_reduce_peak(thread_peak_l1(P, t), red_f + 16 * par, red_i + 8 * par, t);
         pend_cap = ti.cap;
         pend_slot = ti.slot;
         pend_d = ti.d;
         par ^= 1;
     }
     __syncthreads();
-    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
+    if (t < 32 && pend_cap >= 0) flush();
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
-}
-
-// k_search_l1_x3: the C/A search at THREE CTAs per SM (24 warps instead of 16).  What keeps k_search_l1 at two is its
-// register file share (126 registers: 16 points + 16 accumulators + 16 block powers per thread) and its 98.6 KiB of
-// shared memory.  Here the accumulators over k2 and the block powers live in thread-private TENSOR MEMORY (a CTA
-// allocates 128 columns: 64 per thread -- 32 accumulator, 16 block-power and 8 stage-A-base columns), which brings
-// the kernel to 80 registers; the operands come straight from L2 (no staging buffers), the stage-B twiddles from a
-// 7.5 KiB shared table, and the B->C tiles live inside the exchange rows: 71.9 KiB of shared memory per CTA.
-// Same arithmetic in the same order as k_search_l1 (bitwise-equal cells, tested).
-constexpr int kX3AccCol = 0, kX3PowCol = 32, kX3BaseCol = 48, kX3Cols = 64;
-__host__ __device__ constexpr size_t search_l1_x3_smem()
-{
-    return sizeof(float2) * (size_t)(2 * kSub + kT2Elems) + 64 * sizeof(float);
-}
-
-template <bool MULTI>
-__global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
-{
-    extern __shared__ __align__(1024) unsigned char smem[];
-    float2 *S1 = reinterpret_cast<float2 *>(smem);                 // [2][4096]
-    float2 *T2 = S1 + 2 * kSub;                                    // [4][15][16]
-    float *red_f = reinterpret_cast<float *>(T2 + kT2Elems);       // [2 parities][16], then the TMEM slot at [48]
-    int *red_i = reinterpret_cast<int *>(red_f + 32);              // [2 parities][8]
-    const int t = threadIdx.x;
-    constexpr int L = ACQ_LAGS_L1;
-    const uint32_t tmem_base = tmem_alloc_cta<2 * kX3Cols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
-    pdl_trigger_search();
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
-        float4 *dst = reinterpret_cast<float4 *>(T2);
-        for (int i = t; i < kT2Elems / 2; i += 256) dst[i] = __ldg(src + i);
-    }
-    const uint32_t zaddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kX3Cols);
-    float2 bw = __ldg(p.tables + kT2Elems + t);  // W16384^{4t}: base of residue 0
-    tmem_st1(zaddr + kX3BaseCol, bw);
-#pragma unroll
-    for (int k2 = 1; k2 < 4; k2++) tmem_st1(zaddr + kX3BaseCol + 2 * k2, __ldg(p.tables + kT2Elems + k2 * 256 + t));
-    tmem_wait_st();
-    __syncthreads();
-    pdl_wait();
-    int it = 0;
-    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&](int q) {
-        const Peak tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
-        acq_cell c;
-        c.peak = tot.p;
-        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
-        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
-        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
-        p.cells[((size_t)pend_cap * p.n_slots + pend_slot) * p.n_dop + pend_d] = c;
-    };
-
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const TileIdx ti(p, tile);
-        float pw[16];
-        for (int b = 0; b < p.K; b++) {
-            float2 x[16];
-#pragma unroll 1
-            for (int k2 = 0; k2 < 3; k2++) {
-                load_products(x, p, ti, b, k2, t);
-                subfft4096_inv4s(x, k2, bw, S1 + (it & 1) * kSub, t, T2, zaddr + kX3BaseCol, [] {});
-                it++;
-                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
-                float2 z[16];
-                if (k2 == 0) {
-#pragma unroll
-                    for (int n2 = 0; n2 < 16; n2++) z[n2] = x[r16(n2)];
-                } else {   // acc += x * W64^{k2 n2}, two halves of eight accumulators through tensor memory
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        float2 a[8];
-                        tmem_ld8(zaddr + kX3AccCol + 16 * h, a);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 8; i++) z[8 * h + i] = cfma(x[r16(8 * h + i)], c_cC[k2][8 * h + i], a[i]);
-                    }
-                }
-                tmem_st16(zaddr + kX3AccCol, z);
-                tmem_wait_st();
-            }
-            // last residue: the accumulation ends in the powers
-            load_products(x, p, ti, b, 3, t);
-            subfft4096_inv4s(x, 3, bw, S1 + (it & 1) * kSub, t, T2, zaddr + kX3BaseCol, [] {});
-            it++;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                float2 a[8];
-                tmem_ld8(zaddr + kX3AccCol + 16 * h, a);
-                float2 pb[4];
-                if (MULTI && b > 0) tmem_ld4(zaddr + kX3PowCol + 8 * h, pb);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float v = cpower(cfma(x[r16(8 * h + i)], c_cC[3][8 * h + i], a[i]));
-                    if (MULTI && b > 0) pw[8 * h + i] = ((i & 1) ? pb[i >> 1].y : pb[i >> 1].x) + v;
-                    else pw[8 * h + i] = v;
-                }
-            }
-            if (MULTI && b + 1 < p.K) {
-                float2 ps[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) ps[i] = make_float2(pw[2 * i], pw[2 * i + 1]);
-                tmem_st8(zaddr + kX3PowCol, ps);
-                tmem_wait_st();
-            }
-        }
-        Peak best;
-        best.p = 0.0f;
-        best.n = 0x7fffffff;
-        best.sum = 0.0f;
-#pragma unroll
-        for (int n2 = 0; n2 < 16; n2++) {
-            const int n = lag_of3(t, n2);
-            if (n2 < 15 || n < L) {
-                if (pw[n2] > best.p) best.p = pw[n2], best.n = n;
-                best.sum += pw[n2];
-            }
-        }
-        warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
-        pend_cap = ti.cap;
-        pend_slot = ti.slot;
-        pend_d = ti.d;
-        par ^= 1;
-    }
-    __syncthreads();
-    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
-    tmem_free_cta<2 * kX3Cols>(tmem_base, t);
 }
 
 // Tensor memory (TMEM, 256 KB per SM) as thread-private scratch.  The E1B combine needs the outputs of three
@@ -897,73 +978,6 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
 // registers) move the parked values over the tensor-memory datapath instead.  Warps w and w+4 share lanes and
 // use disjoint column ranges; a CTA allocates 256 columns, so two CTAs fill the SM's 512.
 constexpr int kE1bTmemCols = 256;  // 2 warp sets x 96 columns, rounded up to a power of two
-
-__global__ void __launch_bounds__(256, 2) k_search_e1b_ldg(const SearchArgs p)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    const FftSmem3 s = fft_smem3_carve(smem);
-    float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes());
-    int *red_i = reinterpret_cast<int *>(red_f + 16);
-    const int t = threadIdx.x;
-    constexpr int L = ACQ_LAGS_E1B;
-    const uint32_t tmem_base = tmem_alloc_cta<kE1bTmemCols>(reinterpret_cast<uint32_t *>(red_f + 32), t);
-    pdl_trigger_search();
-    load_t2(s, p.tables, t);
-    // this thread's scratch: lane 32*(warp%4) + (t%32), columns [96*(warp/4), +96): [k2][n2] complex
-    const uint32_t zaddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * 96);
-    const float2 *base = p.tables + kT2Elems + t;
-    int buf = 0;
-    pdl_wait();
-
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const TileIdx ti(p, tile);
-        float2 x[16];
-#pragma unroll 1
-        for (int k2 = 0; k2 < 4; k2++) {
-            load_products(x, p, ti, 0, k2, t);
-            subfft4096_inv3(x, k2, __ldg(base + k2 * 256), buf, s, t);
-            buf ^= 1;
-            if (k2 < 3) {
-                float2 z[16];
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) z[n2] = (k2 == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[k2][n2]);
-                tmem_st16(zaddr + 32 * k2, z);
-                tmem_wait_st();
-            }
-        }
-        // radix-4 combine over k2, lags n = lag_of3(t, n2) + 4096 m < 16368.  Lags are not visited in
-        // increasing order here, so ties compare the index explicitly (first index wins, search.cpp:488).
-        Peak best;
-        best.p = 0.0f;
-        best.n = 0x7fffffff;
-        best.sum = 0.0f;
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-            float2 za[4], zb[4], zc[4];
-            tmem_ld4(zaddr + 0 * 32 + 8 * c4, za);
-            tmem_ld4(zaddr + 1 * 32 + 8 * c4, zb);
-            tmem_ld4(zaddr + 2 * 32 + 8 * c4, zc);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int n2 = 4 * c4 + i;
-                float2 z0 = za[i], z1 = zb[i], z2 = zc[i];
-                float2 z3 = cmul(x[r16(n2)], c_cC[3][n2]);
-                radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
-                const float2 zz[4] = {z0, z1, z2, z3};
-#pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    const int n = lag_of3(t, n2) + 4096 * m;
-                    const float pw = cpower(zz[m]);
-                    if (n < L) peak_merge(best, pw, n, pw);
-                }
-            }
-        }
-        const Peak tot = block_reduce_peak(best, red_f, red_i, t);
-        if (t == 0) store_cell(p, ti, tot, L);
-    }
-    tmem_free_cta<kE1bTmemCols>(tmem_base, t);
-}
 
 // k_search_e1b: as k_search_e1b_ldg, with the operand staging of k_search_l1 -- both operands of a sub-FFT land in
 // shared memory by TMA bulk copies issued one sub-FFT ahead (D into the idle half of the exchange buffer, E into
@@ -1014,7 +1028,6 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     const int t = threadIdx.x;
     constexpr int L = ACQ_LAGS_E1B;
     const uint32_t tmem_base = tmem_alloc_cta<kE1bTmemCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
-    pdl_trigger_search();
     {   // stage-B twiddle table into shared memory
         const float4 *src = reinterpret_cast<const float4 *>(p.tables);
         float4 *dst = reinterpret_cast<float4 *>(s.T2);
@@ -1030,7 +1043,8 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     const uint32_t bar = smem_u32(s.bar);
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
-    pdl_wait();
+    if (p.wait_prior) pdl_wait();
+    pdl_trigger_search();
     auto issue = [&](const TileIdx &tn, int k2n, int half) {  // thread 0: stage the operands of sub-FFT (tn, k2n)
         const int r = (k2n - tn.dop) & 3;
         const int q = (k2n - tn.dop - r) >> 2;
@@ -1044,14 +1058,12 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0);
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&](int q) {
-        const Peak tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
-        acq_cell c;
-        c.peak = tot.p;
-        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
-        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
-        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
-        p.cells[((size_t)pend_cap * p.n_slots + pend_slot) * p.n_dop + pend_d] = c;
+    auto flush = [&]() {   // warp 0: the previous tile's peak (deferred cross-warp merge, see k_search_l1)
+        Peak tot;
+        tot.p = tot.sum = 0.0f;
+        tot.n = 0;
+        if (t == 0) tot = merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1));
+        finish_tile(p, pend_cap, pend_slot, pend_d, tot, L, t);
     };
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -1076,7 +1088,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
                 }
             });
             it++;
-            if (t == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
+            if (t < 32 && k2 == 0 && pend_cap >= 0) flush();  // previous tile's peak
             if (k2 < 3) {
                 float2 z[16];
 #pragma unroll
@@ -1162,7 +1174,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
         par ^= 1;
     }
     __syncthreads();
-    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
+    if (t < 32 && pend_cap >= 0) flush();
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);
 }
 
@@ -1186,7 +1198,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const FftSmem3 s = fft_smem3_carve(smem);
     float2 *Y = reinterpret_cast<float2 *>(smem + fft_smem3_bytes());            // [2][16][256] own residue
     float *red_f = reinterpret_cast<float *>(smem + fft_smem3_bytes() + 2 * sizeof(float2) * kSub);
@@ -1196,7 +1208,6 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b
     const int t = threadIdx.x;
     const int rank = (int)cluster.block_rank();  // = k2 in the sub-FFT phase, = n2 slice in the combine phase
     constexpr int L = ACQ_LAGS_E1B;
-    pdl_trigger_search();
     load_t2(s, p.tables, t);
     const float2 bw = __ldg(p.tables + kT2Elems + rank * 256 + t);
     const float2 *Yr[4];
@@ -1206,7 +1217,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b
     int *peaks_i0 = cluster.map_shared_rank(peaks_i, 0);
     const int n_clusters = gridDim.x >> 2;
     int buf = 0, yb = 0;
-    pdl_wait();
+    if (p.wait_prior) pdl_wait();
+    pdl_trigger_search();
 
     for (long long tile = blockIdx.x >> 2; tile < p.n_tiles; tile += n_clusters) {
         const TileIdx ti(p, tile);
@@ -1254,64 +1266,23 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b
             peaks_i0[rank] = tot.n;
         }
         cluster.sync();  // peaks have landed in rank 0
-        if (rank == 0 && t == 0) {
+        if (rank == 0 && t < 32) {
             Peak all;
             all.p = peaks_f[0];
             all.sum = peaks_f[1];
             all.n = peaks_i[0];
 #pragma unroll
             for (int k = 1; k < 4; k++) peak_merge(all, peaks_f[2 * k], peaks_i[k], peaks_f[2 * k + 1]);
-            store_cell(p, ti, all, L);
+            finish_tile(p, ti.cap, ti.slot, ti.d, all, L, t);
         }
         // the peak slots are rewritten only after the next tile's first cluster barrier, which rank 0's
         // thread 0 reaches after the merge above
     }
 }
 
-// K5b.  max_snr = 0; for dop ascending: if (snr > max_snr) take it   (search.cpp:455,495).
-// One warp per (capture, sat) row: lanes stride over the Doppler cells, then a shuffle reduction that
-// prefers the larger snr and, on equal snr, the lower Doppler index (what the sequential scan keeps).
-// A row whose snr never exceeds 0 (or is NaN) keeps {lag 0, dop 0, zeros}.
-__global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ cells, const int *__restrict__ slot_sat,
-                                                  acq_record *__restrict__ out, int n_rows, int n_slots, int n_dop,
-                                                  int dop_lo)
-{
-    pdl_wait();  // before the early exit: completion of this grid must imply completion of its predecessors
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n_rows) return;
-    const acq_cell *c = cells + (size_t)row * n_dop;
-    float best = 0.0f;
-    int best_d = 0x7fffffff;
-    for (int d = lane; d < n_dop; d += 32) {
-        const float snr = c[d].snr;
-        if (snr > best) best = snr, best_d = d;  // ascending d within a lane: first maximum kept
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const float s2 = __shfl_xor_sync(0xffffffffu, best, off);
-        const int d2 = __shfl_xor_sync(0xffffffffu, best_d, off);
-        if (s2 > best || (s2 == best && d2 < best_d)) best = s2, best_d = d2;
-    }
-    if (lane == 0) {
-        acq_record r;
-        r.sat = slot_sat[row % n_slots];
-        r.lag = 0;
-        r.dop = 0;
-        r.peak = 0.0f;
-        r.noise = 0.0f;
-        r.snr = 0.0f;
-        if (best > 0.0f) {
-            const acq_cell cc = c[best_d];
-            r.lag = cc.lag;
-            r.dop = dop_lo + best_d;
-            r.peak = cc.peak;
-            r.noise = cc.noise;
-            r.snr = cc.snr;
-        }
-        out[row] = r;
-    }
-}
+#if defined(ACQ_VARIANT_L1_LDG) || defined(ACQ_VARIANT_L1_X3) || defined(ACQ_VARIANT_E1B_LDG)
+#include "acq_variants.cuh"  // A/B forms: experiment builds only (tools/build_variants.py)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K6.  Acquisition refinement for the hand-off to tracking.  The search reports the code phase
@@ -1457,25 +1428,8 @@ static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);  // errors surface through cudaGetLastError() in the caller
 }
 
-static size_t search_l1_ldg_smem_bytes() { return fft_smem3t_bytes() + 64 * sizeof(float); }
 static size_t search_l1_smem_bytes() { return fft_smem4_bytes() + 64 * sizeof(float); }
-static bool use_ldg_kernel()
-{
-    static const bool v = [] { const char *k = getenv("ACQ_L1_KERNEL"); return k && !strcmp(k, "ldg"); }();  // A/B runs
-    return v;
-}
-static bool use_x3_kernel()
-{
-    const char *k = getenv("ACQ_L1_KERNEL");  // A/B runs and the kernel-equivalence test
-    return k && !strcmp(k, "x3");
-}
-static size_t search_e1b_ldg_smem_bytes() { return fft_smem3_bytes() + 64 * sizeof(float); }
 static size_t search_e1b_smem_bytes() { return e1b_smem_bytes(); }
-static bool use_e1b_ldg_kernel()
-{
-    const char *k = getenv("ACQ_E1B_CTA_KERNEL");  // A/B runs and the kernel-equivalence test
-    return k && !strcmp(k, "ldg");
-}
 static size_t search_e1b_cluster_smem_bytes() { return fft_smem3_bytes() + 2 * sizeof(float2) * kSub + 64 * sizeof(float); }
 static size_t fwd_smem_bytes() { return fft_smem3_bytes() + kZBytes; }
 
@@ -1483,17 +1437,23 @@ cudaError_t search_kernels_configure()
 {
     cudaError_t e;
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
-    if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
-    if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
+#ifdef ACQ_VARIANT_L1_X3
     const int l1x = (int)search_l1_x3_smem();
     if ((e = cudaFuncSetAttribute(k_search_l1_x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1x))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1_x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1x))) return e;
-    const int l1g = (int)search_l1_ldg_smem_bytes();
+#endif
+#ifdef ACQ_VARIANT_L1_LDG
+    const int l1g = (int)(fft_smem3t_bytes() + 64 * sizeof(float));
     if ((e = cudaFuncSetAttribute(k_search_l1_ldg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1g))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1_ldg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1g))) return e;
-    if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
-    const int e1g = (int)search_e1b_ldg_smem_bytes();
+#endif
+#ifdef ACQ_VARIANT_E1B_LDG
+    const int e1g = (int)(fft_smem3_bytes() + 64 * sizeof(float));
     if ((e = cudaFuncSetAttribute(k_search_e1b_ldg, cudaFuncAttributeMaxDynamicSharedMemorySize, e1g))) return e;
+#endif
     const int ec = (int)search_e1b_cluster_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ec))) return e;
@@ -1566,17 +1526,23 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
     const long long max_ctas = (long long)sm_count * 2;
     const int grid = (int)(a.n_tiles < max_ctas ? a.n_tiles : max_ctas);
     if (e1b) {
-        if (use_e1b_ldg_kernel()) launch_k(k_search_e1b_ldg, grid, 256, search_e1b_ldg_smem_bytes(), st, pdl, a);
-        else launch_k(k_search_e1b, grid, 256, search_e1b_smem_bytes(), st, pdl, a);
-    } else if (use_x3_kernel()) {
-        const long long ctas3 = (long long)sm_count * 3;
-        const int grid3 = (int)(a.n_tiles < ctas3 ? a.n_tiles : ctas3);
-        launch_k(a.K > 1 ? k_search_l1_x3<true> : k_search_l1_x3<false>, grid3, 256, search_l1_x3_smem(), st, pdl, a);
-    } else if (use_ldg_kernel()) {
-        launch_k(a.K > 1 ? k_search_l1_ldg<true> : k_search_l1_ldg<false>, grid, 256, search_l1_ldg_smem_bytes(), st, pdl, a);
-    } else {
-        launch_k(a.K > 1 ? k_search_l1<true> : k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
+#ifdef ACQ_VARIANT_E1B_LDG
+        launch_k(k_search_e1b_ldg, grid, 256, fft_smem3_bytes() + 64 * sizeof(float), st, pdl, a);
+#else
+        launch_k(k_search_e1b, grid, 256, search_e1b_smem_bytes(), st, pdl, a);
+#endif
+        return 1;
     }
+#if defined(ACQ_VARIANT_L1_X3)
+    const long long ctas3 = (long long)sm_count * 3;
+    const int grid3 = (int)(a.n_tiles < ctas3 ? a.n_tiles : ctas3);
+    launch_k(a.K > 1 ? k_search_l1_x3<true> : k_search_l1_x3<false>, grid3, 256, search_l1_x3_smem(), st, pdl, a);
+#elif defined(ACQ_VARIANT_L1_LDG)
+    launch_k(a.K > 1 ? k_search_l1_ldg<true> : k_search_l1_ldg<false>, grid, 256, fft_smem3t_bytes() + 64 * sizeof(float), st,
+             pdl, a);
+#else
+    launch_k(a.K > 1 ? k_search_l1_multi : k_search_l1, grid, 256, search_l1_smem_bytes(), st, pdl, a);
+#endif
     return 1;
 }
 
@@ -1597,14 +1563,6 @@ int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, con
     if (n_rows <= 0) return 0;
     RefineArgs a{Dp, Ep, rec, sat_type, out, n_slots, K, nvar, half_bin, ext_len, Q, n_shift, smax, cd_div};
     k_refine<<<n_rows, 256, 0, st>>>(a);
-    return 1;
-}
-
-int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
-                    int dop_lo, cudaStream_t st, bool pdl)
-{
-    const int n_rows = n_cap * n_slots;
-    launch_k(k_best_dop, (n_rows + 3) / 4, 128, 0, st, pdl, cells, slot_sat, out, n_rows, n_slots, n_dop, dop_lo);
     return 1;
 }
 

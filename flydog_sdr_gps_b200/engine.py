@@ -29,9 +29,9 @@ class AcqError(RuntimeError):
         self.code = code
 
 
-def _check(rc):
+def _check(rc, lib=None):
     if rc != 0:
-        raise AcqError(rc, _lib.load().acq_last_error().decode())
+        raise AcqError(rc, (lib or _lib.load()).acq_last_error().decode())
 
 
 def default_params(**kw):
@@ -55,15 +55,16 @@ def microbench(device=0):
 class AcqEngine:
     """One engine per GPU.  `sats` is the receiver's satellite table [(prn, t1, t2, type), ...]."""
 
-    def __init__(self, sats, params=None, device=0):
-        self._L = _lib.load()
+    def __init__(self, sats, params=None, device=0, variant=None):
+        """variant: name of an experiment build of the library (flydog_sdr_gps_b200/_build.py VARIANTS; tests only)."""
+        self._L = _lib.load_variant(variant) if variant else _lib.load()
         self.sats = [tuple(int(v) for v in s) for s in sats]
         self.params = params if params is not None else default_params()
         arr = (_lib.AcqSat * len(self.sats))()
         for i, s in enumerate(self.sats):
             arr[i].prn, arr[i].t1, arr[i].t2, arr[i].type = s
         h = C.c_void_p()
-        _check(self._L.acq_create(C.byref(h), C.byref(self.params), arr, len(self.sats), device))
+        _check(self._L.acq_create(C.byref(h), C.byref(self.params), arr, len(self.sats), device), self._L)
         self._h = h
         self.device = device
 
@@ -104,17 +105,18 @@ class AcqEngine:
         return int(self._L.acq_launch_count(self._h))
 
     def set_profiling(self, on=True):
-        _check(self._L.acq_set_profiling(self._h, 1 if on else 0))
+        _check(self._L.acq_set_profiling(self._h, 1 if on else 0), self._L)
 
     def kernel_ms(self):
-        """Device time of each kernel of the most recent search (needs set_profiling(True))."""
+        """Device time of each kernel of the most recent search (needs set_profiling(True)).  The best-Doppler pick
+        is part of the search kernels."""
         out = (C.c_float * 4)()
-        _check(self._L.acq_get_kernel_ms(self._h, out, 4))
-        return dict(zip(["front_end", "fwd_fft", "search", "best_dop"], [float(v) for v in out]))
+        _check(self._L.acq_get_kernel_ms(self._h, out, 4), self._L)
+        return dict(zip(["front_end", "fwd_fft", "search"], [float(v) for v in out[:3]]))
 
     def device_info(self):
         d, s, c = C.c_int(), C.c_int(), C.c_int()
-        _check(self._L.acq_device_info(self._h, C.byref(d), C.byref(s), C.byref(c)))
+        _check(self._L.acq_device_info(self._h, C.byref(d), C.byref(s), C.byref(c)), self._L)
         return {"device": d.value, "sm_count": s.value, "sm_clock_khz": c.value}
 
     def cells_per_search(self, sel=None):
@@ -148,44 +150,44 @@ class AcqEngine:
         if want_grid:
             grid = np.zeros((n_cap, n_sel, self.n_dop), CELL_DTYPE)
             _check(self._L.acq_search_grid(self._h, a.ctypes.data, n_cap, sp, n_sel, out.ctypes.data,
-                                           grid.ctypes.data))
+                                           grid.ctypes.data), self._L)
             return out, grid
-        _check(self._L.acq_search(self._h, a.ctypes.data, n_cap, sp, n_sel, out.ctypes.data))
+        _check(self._L.acq_search(self._h, a.ctypes.data, n_cap, sp, n_sel, out.ctypes.data), self._L)
         return out
 
     def search_ptr(self, packed_ptr, n_cap, out_ptr, sel=None):
         """acq_search on raw host pointers (e.g. pinned torch tensors): no allocation on the way."""
         sp, n_sel, keep = self._sel(sel)
-        _check(self._L.acq_search(self._h, packed_ptr, n_cap, sp, n_sel, out_ptr))
+        _check(self._L.acq_search(self._h, packed_ptr, n_cap, sp, n_sel, out_ptr), self._L)
 
     def submit(self, packed, out, sel=None):
         a, n_cap = self._packed(packed)
         sp, n_sel, keep = self._sel(sel)
         assert out.dtype == RECORD_DTYPE and out.size == n_cap * n_sel
         self._keep = (a, keep, out)
-        _check(self._L.acq_submit(self._h, a.ctypes.data, n_cap, sp, n_sel, out.ctypes.data))
+        _check(self._L.acq_submit(self._h, a.ctypes.data, n_cap, sp, n_sel, out.ctypes.data), self._L)
 
     def poll(self):
         rc = self._L.acq_poll(self._h)
         if rc < 0:
-            _check(rc)
+            _check(rc, self._L)
         return bool(rc)
 
     def wait(self):
-        _check(self._L.acq_wait(self._h))
+        _check(self._L.acq_wait(self._h), self._L)
 
     # ---- device-resident search (torch tensors on this engine's GPU)
     def search_device(self, packed_dev, out_dev, n_cap, sel=None, stream_ptr=None):
         """packed_dev / out_dev: device pointers (ints).  Enqueues on stream_ptr (None = engine stream)."""
         sp, n_sel, keep = self._sel(sel)
-        _check(self._L.acq_search_device(self._h, packed_dev, n_cap, sp, n_sel, out_dev, stream_ptr))
+        _check(self._L.acq_search_device(self._h, packed_dev, n_cap, sp, n_sel, out_dev, stream_ptr), self._L)
 
     def refine(self, records):
         """acq_refine: hand-off refinement of the records of the most recent search()/wait() -- FINE_DTYPE array of
         the same shape (Doppler in Hz from a three-bin interpolation, code phase in FS samples from early/late)."""
         r = np.ascontiguousarray(records, RECORD_DTYPE)
         out = np.zeros(r.shape, FINE_DTYPE)
-        _check(self._L.acq_refine(self._h, r.ctypes.data, r.size, out.ctypes.data))
+        _check(self._L.acq_refine(self._h, r.ctypes.data, r.size, out.ctypes.data), self._L)
         return out
 
     def detected(self, records):
@@ -198,7 +200,7 @@ class AcqEngine:
     # ---- introspection
     def code_spectrum(self, sat):
         out = np.zeros(2 * N, np.float32)
-        _check(self._L.acq_get_code_spectrum(self._h, sat, out.ctypes.data))
+        _check(self._L.acq_get_code_spectrum(self._h, sat, out.ctypes.data), self._L)
         return out.view(np.complex64)
 
     def capture_spectrum(self, packed_block, half_rot=0):
@@ -206,5 +208,5 @@ class AcqEngine:
         assert a.size == self.block_bytes
         x2 = np.zeros(2 * N, np.float32)
         D = np.zeros(2 * N, np.float32)
-        _check(self._L.acq_get_capture_spectrum(self._h, a.ctypes.data, half_rot, x2.ctypes.data, D.ctypes.data))
+        _check(self._L.acq_get_capture_spectrum(self._h, a.ctypes.data, half_rot, x2.ctypes.data, D.ctypes.data), self._L)
         return x2.view(np.complex64), D.view(np.complex64)

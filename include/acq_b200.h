@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ACQ_ABI_VERSION 2   /* 2: acq_params grew from 32 to 48 bytes (code_doppler) */
+#define ACQ_ABI_VERSION 3   /* 3: acq_params carries its own size (struct_size first, 64 bytes); 2: code_doppler */
 
 /* Fixed geometry of the reference search (gps/gps.h:60-82, kiwi.config:259). */
 #define ACQ_FFT_LEN 16384      /* FFT_LEN */
@@ -72,6 +72,9 @@ enum { ACQ_WRAP_REFERENCE = 0, ACQ_WRAP_CIRCULAR = 1 };
 
 /* Search parameters.  acq_params_default() fills the values the reference compiles in. */
 typedef struct acq_params {
+    uint32_t struct_size; /* sizeof(acq_params) of the caller's header, filled by acq_params_default.  acq_create refuses
+                             a structure whose size differs from the library's (a caller built against another ABI
+                             version would otherwise be read past its end) */
     int32_t dop_lo;     /* first Doppler index, inclusive.  default -20 (gps/search.cpp:465) */
     int32_t dop_hi;     /* last Doppler index, inclusive.   default +20 */
     int32_t half_bin;   /* 0: index = bins of ACQ_BIN_HZ (reference).  1: index = half-bins (extension) */
@@ -89,7 +92,7 @@ typedef struct acq_params {
                              correlation loss of long sums at high Doppler (0.52 chip over 80 ms at 10 kHz); costs
                              (2 max|s| + 1) shifted copies of every capture spectrum (at most ACQ_MAX_CODE_SHIFTS),
                              nothing in the search kernels.  No effect when k_noncoh = 1. */
-    int32_t reserved[3];  /* must be 0 */
+    int32_t reserved[6];  /* must be 0 */
 } acq_params;
 
 #define ACQ_MAX_CODE_SHIFTS 33 /* acq_create fails with ACQ_ERR_UNSUPPORTED when code_doppler needs more shifted copies */
@@ -158,7 +161,9 @@ int acq_destroy(acq_engine *e);
  *   packed : HOST memory, n_captures * k_noncoh * ACQ_CAPTURE_BLOCK_BYTES(sample_bits) bytes (ACQ_BLOCK_BYTES per
  *            block in the reference's 1-bit format); capture c occupies k_noncoh consecutive blocks.
  *            (Pinned memory avoids a staging copy.)
- *   sel    : n_sel table indices to search, or NULL for the whole table (then n_sel is ignored).
+ *   sel    : n_sel table indices to search, or NULL for the whole table (then n_sel is ignored).  Rows of type
+ *            ACQ_SBAS carry an all-zero code spectrum, as in the reference (SearchInit builds replicas for Navstar,
+ *            QZSS and E1B rows only, gps/search.cpp:244,306): their records are {lag 0, dop 0, snr 0}.
  *   out    : HOST memory, n_captures * n_sel records, record [c*n_sel + s].
  * Synchronous: returns when `out` is filled. */
 int acq_search(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel,
@@ -172,7 +177,12 @@ int acq_search_grid(acq_engine *e, const uint8_t *packed, int n_captures, const 
 /* Device-resident variant: packed and out are DEVICE pointers on the engine's GPU, work is
  * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the engine's own stream) and the
  * call returns without synchronising.  sel is a HOST array, consumed before returning.
- * packed_dev must be 16-byte aligned (the front end stages the capture with bulk asynchronous copies). */
+ * packed_dev must be 16-byte aligned (the front end stages the capture with bulk asynchronous copies).
+ * Ordering: the engine's scratch (capture spectra, per-Doppler cells, work lists) is shared by all calls.  The engine
+ * records an event behind every device-path search and makes whatever touches that scratch next -- a search on
+ * another stream, a host-path call, a change of selection or a scratch reallocation -- wait for it, so calls issued
+ * from the one driving host thread never overwrite data a running search still reads.  The caller remains
+ * responsible for packed_dev / out_dev staying valid until its stream has passed the search. */
 int acq_search_device(acq_engine *e, const uint8_t *packed_dev, int n_captures, const int32_t *sel, int n_sel,
                       acq_record *out_dev, void *stream);
 

@@ -158,6 +158,13 @@ void orc_code_baseband(const orc_sat *sat, float *out)
     uint8_t chips[4092];
     int codelen;
     const int e1b = (sat->type == ORC_E1B);
+    if (sat->type == ORC_SBAS) {
+        /* search.cpp:244 `if (sp->type != Navstar && sp->type != QZSS) continue;` -- and the E1B loop (:306) takes
+         * E1B rows only: an SBAS row of Sats[] gets no replica, code[sat] stays all zero (file-static storage). */
+        memset(out, 0, sizeof(float) * 2 * N);
+        free(buf);
+        return;
+    }
     if (e1b) {
         orc_e1b_chips(sat->prn, chips);
         codelen = 4092;

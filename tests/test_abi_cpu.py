@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
     assert engine.CELL_DTYPE.itemsize == 16    # acq_cell
     assert engine.FINE_DTYPE.itemsize == 16    # acq_fine
     assert C.sizeof(_lib.AcqSat) == 16
-    assert C.sizeof(_lib.AcqParams) == 48  # ABI version 2: + code_doppler, reserved[3]
+    assert C.sizeof(_lib.AcqParams) == 64  # ABI version 3: struct_size first, reserved[6]
 
 
 def test_defaults_are_the_reference_constants():
@@ -52,8 +52,8 @@ def test_defaults_are_the_reference_constants():
     assert p.thr_l1 == 16.0 and p.thr_e1b == 16.0                            # gps/gps.h:60, search.cpp:549
     assert p.wrap_mode == engine.WRAP_REFERENCE
     assert p.sample_bits == 1                                                # I_sign only, search.cpp:408-411
-    assert p.code_doppler == 0 and list(p.reserved) == [0, 0, 0]
-    assert _lib.load().acq_abi_version() == 2
+    assert p.code_doppler == 0 and list(p.reserved) == [0] * 6 and p.struct_size == 64
+    assert _lib.load().acq_abi_version() == 3
 
 
 def test_no_cpu_fallback():
@@ -87,6 +87,40 @@ def test_argument_errors_without_gpu():
     big = engine.default_params(code_doppler=1, k_noncoh=255, dop_lo=-2048, dop_hi=2048)
     assert L.acq_create(C.byref(h), C.byref(big), C.byref(sat), 1, 0) == -4  # ACQ_ERR_UNSUPPORTED
     assert b"shifted copies" in L.acq_last_error()
+
+
+def test_params_struct_size_guard():
+    """A caller built against another ABI version (different sizeof(acq_params)) is refused before the library reads
+    past the end of its structure (v1 callers passed 32 bytes, v2 48)."""
+    L = _lib.load()
+    h = C.c_void_p()
+    sat = _lib.AcqSat(1, 2, 6, 0)
+    for bad in (0, 32, 48, 128):
+        p = engine.default_params()
+        p.struct_size = bad
+        assert L.acq_create(C.byref(h), C.byref(p), C.byref(sat), 1, 0) == -1
+        assert b"struct_size" in L.acq_last_error()
+    p = engine.default_params()
+    p.reserved[5] = 1
+    assert L.acq_create(C.byref(h), C.byref(p), C.byref(sat), 1, 0) == -1
+    assert b"reserved" in L.acq_last_error()
+
+
+def test_product_library_reads_no_environment_and_holds_no_experiment_kernels():
+    """The drop-in library's behaviour must not depend on the host process's environment: A/B kernel
+    forms and launch-policy switches exist only in the variant libraries tools/build_variants.py builds."""
+    import subprocess
+    csrc = os.path.join(ROOT, "flydog_sdr_gps_b200", "csrc")
+    for f in ("acq_api.cu", "acq_kernels.cu", "acq_fft.cuh", "search_dropin.cpp", "acq_microbench.cu"):
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+    syms = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
+    # (the statically linked CUDA runtime imports getenv for its own CUDA_* variables: only the sources can be checked)
+    for k in ("k_search_l1_ldg", "k_search_l1_x3", "k_search_e1b_ldg"):
+        assert k not in syms, k
+    sass = subprocess.run(["cuobjdump", "-elf", _lib.lib_path()], capture_output=True, text=True).stdout
+    for k in ("k_search_l1_ldg", "k_search_l1_x3", "k_search_e1b_ldg"):
+        assert k not in sass, k
+    assert "k_search_l1_multi" in sass and "k_search_e1b" in sass
 
 
 def test_product_never_imports_the_oracle():

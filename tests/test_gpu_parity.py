@@ -348,7 +348,7 @@ def test_dropin_batch_mode_and_gsig(gpu_required, golden_search):
     d2.close()
 
 
-def test_e1b_cluster_kernel_equals_single_cta_kernel(gpu_required, oracle, monkeypatch):
+def test_e1b_cluster_kernel_equals_single_cta_kernel(gpu_required, oracle):
     """The cluster/DSMEM form of the E1B search (four CTAs per tile) against the one-CTA-per-tile form on the same
     capture: same sub-FFTs and combine, so peaks and lags are bitwise equal; only the order of the noise sum
     differs.  Both against the oracle."""
@@ -357,9 +357,8 @@ def test_e1b_cluster_kernel_equals_single_cta_kernel(gpu_required, oracle, monke
     cap = synth.make_capture(33, 1, table, [(1, 30000, -6 * F.BIN_HZ, 47, 0.4), (7, 1000, 31 * F.BIN_HZ, 46, 1.4),
                                             (11, 65000, 0.0, 45, 2.4)])
     out = {}
-    for kind in ("cta", "cluster"):
-        monkeypatch.setenv("ACQ_E1B_KERNEL", kind)
-        with F.AcqEngine(table, F.default_params(**kw)) as eng:
+    for kind in ("cta", "cluster"):   # variant libraries that force one form (the product picks by tile count)
+        with F.AcqEngine(table, F.default_params(**kw), variant="e1b_" + kind) as eng:
             out[kind] = eng.search(cap, want_grid=True)
     (ra, ga), (rb, gb) = out["cta"], out["cluster"]
     assert np.array_equal(ga["peak"], gb["peak"]) and np.array_equal(ga["lag"], gb["lag"])
@@ -370,7 +369,7 @@ def test_e1b_cluster_kernel_equals_single_cta_kernel(gpu_required, oracle, monke
     assert {int(r["sat"]) for r in rb[0] if r["snr"] >= 16} >= {1, 7, 11}
 
 
-def test_e1b_tma_staged_kernel_equals_ldg_kernel(gpu_required, oracle, monkeypatch):
+def test_e1b_tma_staged_kernel_equals_ldg_kernel(gpu_required, oracle):
     """The operand-staging E1B kernel (TMA bulk copies one sub-FFT ahead, deferred peak merge) against the earlier
     load-from-L2 form: the arithmetic is the same instruction for instruction, so the whole grid is bitwise equal.
     More tiles than resident CTAs, so the deferred merge and the cross-tile prefetch are exercised."""
@@ -378,10 +377,8 @@ def test_e1b_tma_staged_kernel_equals_ldg_kernel(gpu_required, oracle, monkeypat
     kw = scenarios.params_kw("cfg3")
     cap = synth.make_capture(37, 1, table, [(0, 12345, 17 * F.BIN_HZ, 47, 0.4), (8, 64000, -39 * F.BIN_HZ, 46, 1.4)])
     out = {}
-    for kind in ("tma", "ldg"):
-        monkeypatch.setenv("ACQ_E1B_KERNEL", "cta")
-        monkeypatch.setenv("ACQ_E1B_CTA_KERNEL", kind)
-        with F.AcqEngine(table, F.default_params(**kw)) as eng:
+    for kind, variant in (("tma", "e1b_cta"), ("ldg", "e1b_ldg")):
+        with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
             out[kind] = eng.search(cap, want_grid=True)
     (ra, ga), (rb, gb) = out["tma"], out["ldg"]
     for f in ("peak", "lag", "noise", "snr"):
@@ -616,7 +613,7 @@ def test_code_doppler_compensation(gpu_required, oracle):
     assert rec[0]["dop"][1] == -39 and rec[0]["snr"][1] >= 5.0
 
 
-def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle, monkeypatch):
+def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle):
     """k_search_l1_x3 (three CTAs per SM: accumulators and block powers in tensor memory, operands from L2) against
     k_search_l1 (two CTAs per SM, TMA-staged operands): the same arithmetic in the same order, so cells are bitwise
     equal -- K = 1 with more tiles than resident CTAs, and K = 5 half-bin sums with code-Doppler copies."""
@@ -626,11 +623,9 @@ def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle, monkeypatc
               synth.make_capture(4, 5, table, scenarios.signals("cfg2", 2), code_doppler=True), 1)]
     for kw, cap, reps in cases:
         out = {}
-        for kind in ("tma", "x3"):
-            monkeypatch.setenv("ACQ_L1_KERNEL", kind)
-            with F.AcqEngine(table, F.default_params(**kw)) as eng:
+        for kind, variant in (("tma", None), ("x3", "l1_x3")):   # the product kernels against the variant library
+            with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
                 out[kind] = eng.search(np.concatenate([cap] * reps), want_grid=True)
-        monkeypatch.delenv("ACQ_L1_KERNEL")
         (ra, ga), (rb, gb) = out["tma"], out["x3"]
         for f in ("peak", "lag", "noise", "snr"):
             assert np.array_equal(ga[f], gb[f]), f
