@@ -109,13 +109,12 @@ struct acq_engine {
     // persistent device data
     float2 *d_tables = nullptr, *d_rot = nullptr, *d_C = nullptr, *d_Ep = nullptr;
     // per-call scratch (grown on demand)
-    size_t cap_blocks = 0, cap_cells = 0, cap_rows = 0, cap_packed = 0, cap_row_count = 0;
+    size_t cap_blocks = 0, cap_cells = 0, cap_rows = 0, cap_packed = 0;
     uint8_t *d_packed = nullptr;
     float2 *d_x2 = nullptr, *d_Dp = nullptr;
     acq_cell *d_cells = nullptr;
     acq_record *d_records = nullptr;
-    unsigned *d_row_count = nullptr;   // [rows] finished cells per (capture, sat) row; zero between searches
-    unsigned *d_rows_done = nullptr;   // finished rows of a host-polled search; zero between searches
+    unsigned *d_ctas_done = nullptr;   // finished search CTAs of a small search (folded best-Doppler pick); zero between searches
     float2 *d_partial = nullptr;       // [2 * sm_count][16][256]: hand-over of split tiles (balanced K = 1 launch)
     unsigned *d_flags = nullptr;       // [2 * sm_count]
     unsigned epoch = 0;                // search counter: value of the hand-over flags and of the completion word
@@ -166,7 +165,11 @@ using namespace acq;
 // make cudaMemcpyAsync synchronous), the kernels write the records straight into mapped pinned memory, and the host
 // polls a completion word there instead of waiting for the stream.  Above these sizes: plain copies and a stream wait.
 constexpr size_t kStagePackedMax = 256u << 10;  // bytes
-constexpr int kHostRecordRowsMax = 2048;         // records (24 B each: single PCIe writes from the SMs)
+constexpr int kHostRecordRowsMax = 256;          // records (24 B each: single PCIe writes from the SMs)
+// Up to this many (capture, sat) rows the best-Doppler pick rides on the search launches (their last CTA picks all
+// rows: a few microseconds at most); above, a kernel of its own follows (nothing against a long search).
+constexpr int kFoldPickRowsMax = 256;
+static_assert(kHostRecordRowsMax <= kFoldPickRowsMax, "the completion word is raised by the folded pick");
 
 int free_engine(acq_engine *e)
 {
@@ -183,8 +186,7 @@ int free_engine(acq_engine *e)
     cudaFree(e->d_Dp);
     cudaFree(e->d_cells);
     cudaFree(e->d_records);
-    cudaFree(e->d_row_count);
-    cudaFree(e->d_rows_done);
+    cudaFree(e->d_ctas_done);
     cudaFree(e->d_partial);
     cudaFree(e->d_flags);
     cudaFree(e->d_work_full);
@@ -251,7 +253,6 @@ int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool host_path)
     const size_t rows = (size_t)n_captures * n_slots;
     int rc;
     if ((rc = grow(e, e->d_cells, e->cap_cells, rows * e->n_dop))) return rc;
-    if ((rc = grow(e, e->d_row_count, e->cap_row_count, rows, true))) return rc;
     if (!host_path) return ACQ_OK;
     const size_t bytes = blocks * e->block_bytes;
     if ((rc = grow(e, e->d_packed, e->cap_packed, bytes))) return rc;
@@ -390,12 +391,23 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     a.n_shift = e->n_shift;
     a.smax = e->smax;
     a.cd_div = e->cd_div;
+    const int n_rows = n_captures * e->n_slots;
+    const bool fold = n_rows <= kFoldPickRowsMax;
+    const long long tiles_l1 = (long long)n_captures * e->n_l1 * e->n_dop, tiles_e1b = (long long)n_captures * e->n_e1b * e->n_dop;
+    // Cluster/DSMEM form of the E1B search when every tile can have a cluster of its own (one wave: 9 us per tile
+    // against 12.5 us for the one-CTA form, measured), when forced (variant builds), and always for non-coherent sums
+    // (its threads keep the block powers of their 16 lags in registers).  With more tiles than that the
+    // one-CTA-per-tile form has 2.9x the throughput (profiles/r1_e1b_cluster_ab.json).
+    const bool e1b_cluster =
+        K > 1 || ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && tiles_e1b <= e->sm_count / 4);
     a.slot_sat = e->cur_slot_sat;
     a.records = records_dev;
-    a.row_count = e->d_row_count;
-    a.rows_done = e->d_rows_done;
-    a.host_flag = flag_dev;
-    a.n_rows_total = (unsigned)(n_captures * e->n_slots);
+    a.ctas_done = e->d_ctas_done;
+    a.host_flag = fold ? flag_dev : nullptr;
+    a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, false, e->sm_count) +
+                                     search_grid_ctas(tiles_e1b, e1b_cluster, e->sm_count))
+                        : 0u;
+    a.n_rows = n_rows;
     a.epoch = e->epoch;
     a.partial = e->d_partial;
     a.flags = e->d_flags;
@@ -403,26 +415,24 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     if (e->n_l1 > 0) {
         a.work = e->cur_work;
         a.n_work = e->n_l1;
-        a.n_tiles = (long long)n_captures * e->n_l1 * e->n_dop;
+        a.n_tiles = tiles_l1;
         e->launches += launch_search(a, false, e->sm_count, st, pdl);
         // The C/A kernel raises its launch-dependents trigger only after its own wait for the forward FFT, so an E1B
         // launch chained to it by programmatic dependent launch starts with the capture spectra complete: it does
-        // not wait again, and its CTAs move in as the C/A kernel's last CTAs retire (the two write disjoint rows).
-        if (pdl) a.wait_prior = 0;
+        // not wait again, and its CTAs move in as the C/A kernel's last CTAs retire (the two write disjoint rows;
+        // with the pick folded in, nothing downstream needs the launches to finish in order).
+        if (pdl && fold) a.wait_prior = 0;
     }
     if (e->n_e1b > 0) {
         a.work = e->cur_work + e->n_l1;
         a.n_work = e->n_e1b;
-        a.n_tiles = (long long)n_captures * e->n_e1b * e->n_dop;
-        // Cluster/DSMEM form when every tile can have a cluster of its own (one wave: 9 us per tile against
-        // 12.5 us for the one-CTA form, measured), when forced (variant builds), and always for non-coherent sums
-        // (its threads keep the block powers of their 16 lags in registers).  With more tiles than that the
-        // one-CTA-per-tile form has 2.9x the throughput (profiles/r1_e1b_cluster_ab.json).
-        const bool use_cluster =
-            K > 1 || ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && a.n_tiles <= e->sm_count / 4);
-        if (use_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st, pdl);
+        a.n_tiles = tiles_e1b;
+        if (e1b_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st, pdl);
         else e->launches += launch_search(a, true, e->sm_count, st, pdl);
     }
+    if (!fold)
+        e->launches += launch_best_dop(e->d_cells, e->cur_slot_sat, records_dev, n_captures, e->n_slots, e->n_dop,
+                                       e->prm.dop_lo, st, pdl);
     if (prof) {
         CU(cudaEventRecord(e->prof[3], st));
         e->prof_valid = true;
@@ -642,8 +652,8 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     CUE(cudaMalloc(&e->d_partial, (size_t)2 * e->sm_count * 16 * 256 * sizeof(float2)));
     CUE(cudaMalloc(&e->d_flags, (size_t)2 * e->sm_count * sizeof(unsigned)));
     CUE(cudaMemset(e->d_flags, 0, (size_t)2 * e->sm_count * sizeof(unsigned)));
-    CUE(cudaMalloc(&e->d_rows_done, sizeof(unsigned)));
-    CUE(cudaMemset(e->d_rows_done, 0, sizeof(unsigned)));
+    CUE(cudaMalloc(&e->d_ctas_done, sizeof(unsigned)));
+    CUE(cudaMemset(e->d_ctas_done, 0, sizeof(unsigned)));
     CUE(cudaHostAlloc(&e->h_flag, sizeof(unsigned), cudaHostAllocMapped));
     *e->h_flag = 0;
     CUE(cudaHostGetDevicePointer(&e->dh_flag, e->h_flag, 0));

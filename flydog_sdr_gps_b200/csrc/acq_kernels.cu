@@ -8,7 +8,7 @@
 //   K6b k_build_ext  : polyphase, margin-extended code-spectrum rows                 (search.cpp:283-284,471)
 //   K3-5 k_search_l1 / k_search_e1b : conj(D).C product, 16384-point inverse FFT, |.|^2, non-coherent
 //                      sum, max / first-argmax / mean per (capture, sat, Doppler)    (search.cpp:465-494)
-//   K5b finish_tile  : best-snr Doppler per (capture, sat), lowest index on ties    (search.cpp:495), folded into K3-5
+//   K5b k_best_dop / search_cta_done : best-snr Doppler per (capture, sat), lowest index on ties (search.cpp:495)
 //
 // The half-band stages use explicit round-to-nearest mul/add in the reference's summation order
 // (no FMA contraction), so the FFT inputs are bit-identical to the reference's x86 build.
@@ -501,82 +501,104 @@ __device__ __forceinline__ size_t d_row(const SearchArgs &p, const TileIdx &ti, 
     return bv * p.n_shift + (size_t)(p.smax + code_shift(b, p.dop_lo + ti.d, p.cd_div));
 }
 
-// End of a tile, executed by ONE WHOLE WARP of the CTA (all 32 lanes; `tot` is valid in lane 0):
-//   (1) the tile's cell: ave_pwr = tot_pwr / L, snr = max_pwr / ave_pwr with IEEE division (search.cpp:493-494);
-//   (2) the best-over-Doppler pick of Correlate() (max_snr = 0; for dop ascending: if (snr > max_snr) take it --
-//       search.cpp:455,495), folded into the search kernels: every finished cell bumps the row's counter, and the
-//       warp that brings it to n_dop owns the row -- all other cells were stored and fenced before their writers'
-//       atomicAdd -- scans it (lanes stride over the Doppler cells, then a shuffle reduction that prefers the larger
-//       snr and on equal snr the lower Doppler index: what the sequential scan keeps) and writes the record.  A row
-//       whose snr never exceeds 0 (or is NaN) keeps {lag 0, dop 0, zeros}.  The counter is left at zero for the next
-//       search.  No separate kernel, no launch gap: what remains after the last tile is one 41-cell scan;
-//   (3) optionally the completion signal of the whole search for a host that polls mapped memory.
-// (2) and (3) of finish_tile, out of line (it runs once per row, not once per tile) and on scalar arguments so that
-// the search kernels do not keep their parameter block in registers for it.
-__device__ __noinline__ void pick_best_doppler(const acq_cell *rc, int n_dop, int dop_lo, int sat, acq_record *rec,
-                                               unsigned *row_count, unsigned *rows_done, unsigned *host_flag,
-                                               unsigned n_rows_total, unsigned epoch, int lane)
+// The cell of a finished tile (one thread): ave_pwr = tot_pwr / L, snr = max_pwr / ave_pwr with IEEE division
+// (search.cpp:493-494).
+__device__ __forceinline__ void store_cell(const SearchArgs &p, int cap, int slot, int d, const Peak &tot, int L)
 {
-    __threadfence();
-    float best = 0.0f;
-    int best_d = 0x7fffffff;
-    for (int dd = lane; dd < n_dop; dd += 32) {
-        const float snr = __ldcg(&rc[dd].snr);
-        if (snr > best) best = snr, best_d = dd;  // ascending d within a lane: first maximum kept
-    }
+    acq_cell c;
+    c.peak = tot.p;
+    c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
+    c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
+    c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
+    p.cells[((size_t)cap * p.n_slots + slot) * p.n_dop + d] = c;
+}
+
+// Best-over-Doppler pick of Correlate(): max_snr = 0; for dop ascending: if (snr > max_snr) take it (search.cpp:455,495).
+// One warp per (capture, sat) row: lanes stride over the Doppler cells, then a shuffle reduction that prefers the larger
+// snr and, on equal snr, the lower Doppler index (what the sequential scan keeps).  A row whose snr never exceeds 0 (or
+// is NaN) keeps {lag 0, dop 0, zeros}.  ROWS rows are in flight per warp (independent loads).
+template <int ROWS>
+__device__ __forceinline__ void pick_rows(const acq_cell *cells, const int *__restrict__ slot_sat, acq_record *out, int row0,
+                                          int row_step, int n_rows, int n_slots, int n_dop, int dop_lo, int lane)
+{
+    for (int rb = row0; rb < n_rows; rb += ROWS * row_step) {
+        float best[ROWS];
+        int best_d[ROWS];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const float s2 = __shfl_xor_sync(0xffffffffu, best, off);
-        const int d2 = __shfl_xor_sync(0xffffffffu, best_d, off);
-        if (s2 > best || (s2 == best && d2 < best_d)) best = s2, best_d = d2;
-    }
-    if (lane != 0) return;
-    *row_count = 0;
-    acq_record r;
-    r.sat = sat;
-    r.lag = 0;
-    r.dop = 0;
-    r.peak = 0.0f;
-    r.noise = 0.0f;
-    r.snr = 0.0f;
-    if (best > 0.0f) {
-        const float4 cc = __ldcg(reinterpret_cast<const float4 *>(rc + best_d));  // {peak, noise, snr, lag}
-        r.lag = __float_as_int(cc.w);
-        r.dop = dop_lo + best_d;
-        r.peak = cc.x;
-        r.noise = cc.y;
-        r.snr = cc.z;
-    }
-    *rec = r;
-    if (host_flag) {
-        __threadfence_system();
-        if (atomicAdd(rows_done, 1u) + 1u == n_rows_total) {
-            *rows_done = 0;
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned *>(host_flag) = epoch;
+        for (int i = 0; i < ROWS; i++) {
+            best[i] = 0.0f;
+            best_d[i] = 0x7fffffff;
+            const int row = rb + i * row_step;
+            if (row < n_rows) {
+                const acq_cell *c = cells + (size_t)row * n_dop;
+                for (int d = lane; d < n_dop; d += 32) {
+                    const float snr = __ldcg(&c[d].snr);
+                    if (snr > best[i]) best[i] = snr, best_d[i] = d;  // ascending d within a lane: first maximum kept
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float s2 = __shfl_xor_sync(0xffffffffu, best[i], off);
+                const int d2 = __shfl_xor_sync(0xffffffffu, best_d[i], off);
+                if (s2 > best[i] || (s2 == best[i] && d2 < best_d[i])) best[i] = s2, best_d[i] = d2;
+            }
+            const int row = rb + i * row_step;
+            if (lane == 0 && row < n_rows) {
+                acq_record r;
+                r.sat = slot_sat[row % n_slots];
+                r.lag = 0;
+                r.dop = 0;
+                r.peak = 0.0f;
+                r.noise = 0.0f;
+                r.snr = 0.0f;
+                if (best[i] > 0.0f) {
+                    const float4 cc = __ldcg(reinterpret_cast<const float4 *>(cells + (size_t)row * n_dop + best_d[i]));
+                    r.lag = __float_as_int(cc.w);  // acq_cell {peak, noise, snr, lag}
+                    r.dop = dop_lo + best_d[i];
+                    r.peak = cc.x;
+                    r.noise = cc.y;
+                    r.snr = cc.z;
+                }
+                out[row] = r;
+            }
         }
     }
 }
 
-__device__ __forceinline__ void finish_tile(const SearchArgs &p, int cap, int slot, int d, const Peak &tot, int L, int lane)
+// End of a search kernel's CTA.  Small searches (SearchArgs::ctas_total > 0) fold the best-Doppler pick into the
+// search launches: every CTA that stored cells bumps a counter once, after a fence; the CTA that brings it to
+// ctas_total -- the last one of the whole search, C/A and E1B launches together -- picks all rows (every cell was
+// stored and fenced before its writer's atomicAdd), zeroes the counter for the next search and, for a host that polls
+// mapped memory, raises the completion word behind the records.  No separate kernel, no launch gap, nothing per tile.
+// Call with all threads of the CTA, after the CTA's last cell store; `s_last` is a shared-memory word.
+__device__ __noinline__ void search_cta_done(const acq_cell *cells, const int *slot_sat, acq_record *records, unsigned *ctas_done,
+                                             unsigned ctas_total, unsigned *host_flag, unsigned epoch, int n_rows, int n_slots,
+                                             int n_dop, int dop_lo, unsigned *s_last, int t)
 {
-    const size_t row = (size_t)cap * p.n_slots + slot;
-    acq_cell *rc = p.cells + row * p.n_dop;
-    unsigned prev = 0;
-    if (lane == 0) {
-        acq_cell c;
-        c.peak = tot.p;
-        c.noise = __fdiv_rn(tot.sum, (float)L);   // ave_pwr = tot_pwr / i   (search.cpp:493)
-        c.snr = __fdiv_rn(tot.p, c.noise);        // snr = max_pwr / ave_pwr (search.cpp:494)
-        c.lag = (tot.n == 0x7fffffff) ? 0 : tot.n;
-        rc[d] = c;
-        __threadfence();
-        prev = atomicAdd(p.row_count + row, 1u);
+    if (t == 0) {
+        __threadfence();  // this CTA's cells (all stored by this thread) before the count
+        *s_last = (atomicAdd(ctas_done, 1u) + 1u == ctas_total) ? 1u : 0u;
     }
-    prev = __shfl_sync(0xffffffffu, prev, 0);
-    if (prev + 1u == (unsigned)p.n_dop)
-        pick_best_doppler(rc, p.n_dop, p.dop_lo, p.slot_sat[slot], p.records + row, p.row_count + row, p.rows_done,
-                          p.host_flag, p.n_rows_total, p.epoch, lane);
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    pick_rows<4>(cells, slot_sat, records, t >> 5, 8, n_rows, n_slots, n_dop, dop_lo, t & 31);
+    if (host_flag) __threadfence_system();  // the records are in host memory before the word that announces them
+    __syncthreads();
+    if (t == 0) {
+        *ctas_done = 0;
+        if (host_flag) *reinterpret_cast<volatile unsigned *>(host_flag) = epoch;
+    }
+}
+
+__device__ __forceinline__ void search_cta_epilogue(const SearchArgs &p, unsigned *s_last, int t)
+{
+    if (p.ctas_total)
+        search_cta_done(p.cells, p.slot_sat, p.records, p.ctas_done, p.ctas_total, p.host_flag, p.epoch, p.n_rows, p.n_slots,
+                        p.n_dop, p.dop_lo, s_last, t);
 }
 
 // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471, support/simd.cpp:12-40).
@@ -759,12 +781,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     // at K = 1, where a tile is only four units).
     int par = 0, pend_cap = 0, pend_slot = 0, pend_d = 0;
     bool pend = false;
-    auto flush = [&]() {   // warp 0
-        Peak tot;
-        tot.p = tot.sum = 0.0f;
-        tot.n = 0;
-        if (t == 0) tot = merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1));
-        finish_tile(p, pend_cap, pend_slot, pend_d, tot, L, t);
+    auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge)
+        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
     };
     auto tile_done = [&](const TileIdx &ti, const float2 (&acc)[16]) {
         float pw[16];
@@ -823,7 +841,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                     } else issue_tail(half);
                 });
                 if (k2 == 0 && pend) {   // previous tile's peak
-                    if (t < 32) flush();
+                    if (t == 0) flush();
                     pend = false;
                 }
                 if (k2 == 0) {
@@ -850,7 +868,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                 if (k2 < 3) issue(ti, k2 + 1, half);
             });
             if (pend) {
-                if (t < 32) flush();
+                if (t == 0) flush();
                 pend = false;
             }
             if (k2 == k0) {   // pick up the chain where CTA blockIdx.x - 1 left it (its flag went up a whole range ago)
@@ -868,13 +886,16 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         tile_done(ti, acc);
     }
     __syncthreads();
-    if (pend && t < 32) flush();
+    if (pend && t == 0) flush();
+    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
-// k_search_l1_multi -- k_noncoh > 1: a tile runs K inverse FFTs whose powers are summed in registers,
+// k_search_l1_multi<true> -- k_noncoh > 1: a tile runs K inverse FFTs whose powers are summed in registers,
 // P[n] += |r_b[(n + 16 b) mod N]|^2; the 16-lag-per-block code advance is removed in the front end by delaying block
 // b (see k_hb2).  Persistent CTAs stride over the tiles (a tile is 4 K units long: no balancing needed).
+// <false> is the same loop for K = 1 (whole tiles per CTA): the A/B form of k_search_l1, variant builds only.
+template <bool MULTI>
 __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -912,12 +933,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
     if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&]() {   // warp 0: the previous tile's peak (deferred cross-warp merge, see k_search_l1)
-        Peak tot;
-        tot.p = tot.sum = 0.0f;
-        tot.n = 0;
-        if (t == 0) tot = merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1));
-        finish_tile(p, pend_cap, pend_slot, pend_d, tot, L, t);
+    auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge)
+        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
     };
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -926,7 +943,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
         float2 acc[16];
         for (int b = 0; b < p.K; b++) {
             float2 x[16];
-#pragma unroll 1
+            constexpr int kUnroll = MULTI ? 1 : kK2Unroll;
+#pragma unroll kUnroll
             for (int k2 = 0; k2 < 4; k2++) {
                 float2 *S1b = s.S1 + (it & 1) * kS1pElems;
                 {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471), operands from smem
@@ -946,7 +964,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
                     }
                 });
                 it++;
-                if (t < 32 && b == 0 && k2 == 0 && pend_cap >= 0) flush();
+                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush();
                 if (k2 == 0) {
 #pragma unroll
                     for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
@@ -957,7 +975,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
             }
             // block b was delayed by 16*b samples in the front end (k_front_end), so lag n lines up across blocks
 #pragma unroll
-            for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
+            for (int n2 = 0; n2 < 16; n2++) P[n2] = (!MULTI || b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
         }
         warp_reduce_peak(thread_peak_l1(P, t), red_f + 16 * par, red_i + 8 * par, t);
         pend_cap = ti.cap;
@@ -966,7 +984,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
         par ^= 1;
     }
     __syncthreads();
-    if (t < 32 && pend_cap >= 0) flush();
+    if (t == 0 && pend_cap >= 0) flush();
+    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
@@ -1058,12 +1077,8 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0);
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&]() {   // warp 0: the previous tile's peak (deferred cross-warp merge, see k_search_l1)
-        Peak tot;
-        tot.p = tot.sum = 0.0f;
-        tot.n = 0;
-        if (t == 0) tot = merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1));
-        finish_tile(p, pend_cap, pend_slot, pend_d, tot, L, t);
+    auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge)
+        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
     };
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -1088,7 +1103,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
                 }
             });
             it++;
-            if (t < 32 && k2 == 0 && pend_cap >= 0) flush();  // previous tile's peak
+            if (t == 0 && k2 == 0 && pend_cap >= 0) flush();  // previous tile's peak
             if (k2 < 3) {
                 float2 z[16];
 #pragma unroll
@@ -1174,7 +1189,8 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
         par ^= 1;
     }
     __syncthreads();
-    if (t < 32 && pend_cap >= 0) flush();
+    if (t == 0 && pend_cap >= 0) flush();
+    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);
 }
 
@@ -1266,18 +1282,30 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b
             peaks_i0[rank] = tot.n;
         }
         cluster.sync();  // peaks have landed in rank 0
-        if (rank == 0 && t < 32) {
+        if (rank == 0 && t == 0) {
             Peak all;
             all.p = peaks_f[0];
             all.sum = peaks_f[1];
             all.n = peaks_i[0];
 #pragma unroll
             for (int k = 1; k < 4; k++) peak_merge(all, peaks_f[2 * k], peaks_i[k], peaks_f[2 * k + 1]);
-            finish_tile(p, ti.cap, ti.slot, ti.d, all, L, t);
+            store_cell(p, ti.cap, ti.slot, ti.d, all, L);
         }
         // the peak slots are rewritten only after the next tile's first cluster barrier, which rank 0's
         // thread 0 reaches after the merge above
     }
+    if (rank == 0) search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 48), t);  // rank 0 stored the cluster's cells
+}
+
+// K5b as a kernel of its own, for large searches (small ones fold the pick into the search launches, see
+// search_cta_done): one warp per (capture, sat) row.
+__global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ cells, const int *__restrict__ slot_sat,
+                                                  acq_record *__restrict__ out, int n_rows, int n_slots, int n_dop,
+                                                  int dop_lo)
+{
+    pdl_wait();  // before the early exit: completion of this grid must imply completion of its predecessors
+    pick_rows<1>(cells, slot_sat, out, blockIdx.x * 4 + (threadIdx.x >> 5), n_rows, n_rows, n_slots, n_dop, dop_lo,
+                 threadIdx.x & 31);
 }
 
 #if defined(ACQ_VARIANT_L1_LDG) || defined(ACQ_VARIANT_L1_X3) || defined(ACQ_VARIANT_E1B_LDG)
@@ -1438,7 +1466,10 @@ cudaError_t search_kernels_configure()
     cudaError_t e;
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
-    if ((e = cudaFuncSetAttribute(k_search_l1_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+#ifdef ACQ_VARIANT_L1_STRIDED
+    if ((e = cudaFuncSetAttribute(k_search_l1_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+#endif
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
 #ifdef ACQ_VARIANT_L1_X3
     const int l1x = (int)search_l1_x3_smem();
@@ -1540,8 +1571,10 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 #elif defined(ACQ_VARIANT_L1_LDG)
     launch_k(a.K > 1 ? k_search_l1_ldg<true> : k_search_l1_ldg<false>, grid, 256, fft_smem3t_bytes() + 64 * sizeof(float), st,
              pdl, a);
+#elif defined(ACQ_VARIANT_L1_STRIDED)
+    launch_k(a.K > 1 ? k_search_l1_multi<true> : k_search_l1_multi<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #else
-    launch_k(a.K > 1 ? k_search_l1_multi : k_search_l1, grid, 256, search_l1_smem_bytes(), st, pdl, a);
+    launch_k(a.K > 1 ? k_search_l1_multi<true> : k_search_l1, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #endif
     return 1;
 }
@@ -1564,6 +1597,21 @@ int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, con
     RefineArgs a{Dp, Ep, rec, sat_type, out, n_slots, K, nvar, half_bin, ext_len, Q, n_shift, smax, cd_div};
     k_refine<<<n_rows, 256, 0, st>>>(a);
     return 1;
+}
+
+int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
+                    int dop_lo, cudaStream_t st, bool pdl)
+{
+    const int n_rows = n_cap * n_slots;
+    launch_k(k_best_dop, (n_rows + 3) / 4, 128, 0, st, pdl, cells, slot_sat, out, n_rows, n_slots, n_dop, dop_lo);
+    return 1;
+}
+
+int search_grid_ctas(long long n_tiles, bool e1b_cluster, int sm_count)
+{
+    if (n_tiles <= 0) return 0;
+    const long long cap = e1b_cluster ? sm_count / 4 : (long long)sm_count * 2;  // clusters: rank 0 stores the cells
+    return (int)(n_tiles < cap ? n_tiles : cap);
 }
 
 }  // namespace acq

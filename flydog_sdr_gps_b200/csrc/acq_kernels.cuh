@@ -22,17 +22,17 @@ struct SearchArgs {
     // copy i of a block delayed by a further i - smax samples; Doppler index h reads copy smax + s(b, h) of block b,
     // s = round-half-away(b h / cd_div).  n_shift == 1: off.
     int n_shift, smax, cd_div;
-    // best-over-Doppler pick, folded into the search kernels (search.cpp:455,495): the warp that stores the LAST cell
-    // of a (capture, satellite) row -- counted in row_count, which is zero between searches -- scans the row and
-    // writes its record.  records may be device memory or mapped pinned host memory.
+    // Best-over-Doppler pick (search.cpp:455,495).  Small searches fold it into the search launches: ctas_total > 0
+    // is the number of cell-storing CTAs of the WHOLE search (C/A and E1B launches together); the last of them to
+    // finish -- counted in *ctas_done, zero between searches -- picks all n_rows rows into `records` (device memory or
+    // mapped pinned host memory) and, if host_flag is set, stores `epoch` there (mapped) behind the records for a
+    // polling host.  ctas_total == 0: a k_best_dop launch follows instead.
     const int *slot_sat;      // [n_slots] table index of each output slot
     acq_record *records;      // [cap][n_slots]
-    unsigned *row_count;      // [cap][n_slots]
-    // completion signal for a polling host (all may be NULL/0): the warp that finishes the last of n_rows_total rows
-    // of the whole search (C/A and E1B launches together) stores `epoch` to *host_flag (mapped pinned host memory).
-    unsigned *rows_done;
+    unsigned *ctas_done;
     unsigned *host_flag;
-    unsigned n_rows_total, epoch;
+    unsigned ctas_total, epoch;
+    int n_rows;
     // balanced K = 1 C/A launch (k_search_l1): a tile split between two CTAs hands its partial accumulators over
     // through `partial` ([grid][16][256] float2); flags[g] == epoch once CTA g has stored its partial.
     float2 *partial;
@@ -68,6 +68,10 @@ int launch_fwd_fft(const float2 *x2, float2 *out, const float2 *tables, int n_ro
 int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len, int wrap_mode, cudaStream_t st);
 int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, bool pdl = false);
 int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st, bool pdl = false);
+int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
+                    int dop_lo, cudaStream_t st, bool pdl = false);
+// CTAs of a search launch that store cells (what SearchArgs::ctas_total sums over the launches of one search)
+int search_grid_ctas(long long n_tiles, bool e1b_cluster, int sm_count);
 // refinement of the records of the most recent search (one CTA per record)
 int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
                   int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, int n_shift, int smax, int cd_div,

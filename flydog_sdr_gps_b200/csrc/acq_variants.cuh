@@ -28,12 +28,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
     // parity slot and thread 0 merges them after the next tile's first sub-FFT barrier, so the reduction
     // costs no CTA barrier of its own (it matters at K = 1, where a tile is only four sub-FFTs).
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&](int q) {   // warp 0
-        Peak tot;
-        tot.p = tot.sum = 0.0f;
-        tot.n = 0;
-        if (t == 0) tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
-        finish_tile(p, pend_cap, pend_slot, pend_d, tot, L, t);
+    auto flush = [&](int q) {   // thread 0
+        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * q, red_i + 8 * q), L);
     };
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -47,7 +43,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
                 load_products(x, p, ti, b, k2, t);
                 subfft4096_inv3t(x, k2, __ldg(base + k2 * 256), buf, s, t, tw_taddr);
                 buf ^= 1;
-                if (t < 32 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
+                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
                 if (k2 == 0) {
 #pragma unroll
                     for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
@@ -84,7 +80,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
         par ^= 1;
     }
     __syncthreads();
-    if (t < 32 && pend_cap >= 0) flush(par ^ 1);
+    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
+    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
@@ -131,12 +128,8 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
     pdl_trigger_search();  // after the wait (see k_search_l1)
     int it = 0;
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&](int q) {   // warp 0
-        Peak tot;
-        tot.p = tot.sum = 0.0f;
-        tot.n = 0;
-        if (t == 0) tot = merge_warp_peaks(red_f + 16 * q, red_i + 8 * q);
-        finish_tile(p, pend_cap, pend_slot, pend_d, tot, L, t);
+    auto flush = [&](int q) {   // thread 0
+        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * q, red_i + 8 * q), L);
     };
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -149,7 +142,7 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
                 load_products(x, p, ti, b, k2, t);
                 subfft4096_inv4s(x, k2, bw, S1 + (it & 1) * kSub, t, T2, zaddr + kX3BaseCol, [] {});
                 it++;
-                if (t < 32 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
+                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
                 float2 z[16];
                 if (k2 == 0) {
 #pragma unroll
@@ -212,7 +205,8 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
         par ^= 1;
     }
     __syncthreads();
-    if (t < 32 && pend_cap >= 0) flush(par ^ 1);
+    if (t == 0 && pend_cap >= 0) flush(par ^ 1);
+    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
     tmem_free_cta<2 * kX3Cols>(tmem_base, t);
 }
 
@@ -282,8 +276,10 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_ldg(const SearchArgs p)
             }
         }
         const Peak tot = block_reduce_peak(best, red_f, red_i, t);
-        if (t < 32) finish_tile(p, ti.cap, ti.slot, ti.d, tot, L, t);
+        if (t == 0) store_cell(p, ti.cap, ti.slot, ti.d, tot, L);
     }
+    __syncthreads();
+    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);
 }
 

@@ -18,8 +18,8 @@ except Exception as e:
     print(sys.argv[1], 'failed', e)
 P
 done
-for v in devrec pdl0; do
-  for c in cfg1 cfg4; do
+for v in l1_strided devrec pdl0; do
+  for c in cfg1 cfg4 cfg5; do
     ACQ_B200_LIB=$PWD/flydog_sdr_gps_b200/csrc/variants/libacq_b200_$v.so timeout 300 python bench.py --config $c --no-cpu-baseline > $out/bench_${c}_$v.json 2>> $out/bench.err
     python - $out/bench_${c}_$v.json $v <<'P'
 import json,sys
