@@ -1,22 +1,27 @@
 #!/usr/bin/env python3
 """bench.py -- acquisition cells/s of the B200 engine on BASELINE.json's workloads.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one pass of the hot path (front end + PRN x Doppler x code-phase search + best-Doppler pick)
-over one batch of synthetic captures.  Default workload = BASELINE configs[1] (cfg2: 32 GPS PRNs, +-10 kHz at
-half-bin spacing = 161 Doppler indices, 20 non-coherent 4 ms blocks); every rank searches its own
-independent capture (weak scaling, no data-path collective; the 768-byte record arrays are gathered with
-NCCL inside the timed region when N > 1).
+A "step" is one pass of the hot path (front end + PRN x Doppler x code-phase search + best-Doppler pick) over one
+batch of synthetic captures.
 
-One JSON line on stdout (rank 0):
-  value      whole-job cells/s with the captures already resident in HBM (device timing, CUDA events, max over ranks)
-  e2e        the same metric through the reference-facing C-ABI call acq_search() with HOST buffers
-             (pinned), host->device and device->host copies inside the timed region
-  roofline   dominant kernel (fused correlate + inverse FFT + peak search) against the on-SM roofs measured
-             by micro-benchmark in this run (FP32 issue, shared-memory bandwidth) and against measured HBM
-  cpu_baseline  the oracle port timed on this box's host cores on a bounded sample (N = 1, rank 0)
-`--impl reference` times the reference's own CPU path instead (see reference_arm()).
+HEADLINE line = BASELINE configs[4], the receiver farm (cfg5): 1024 independent captures x 32 GPS PRNs x 41 Doppler bins
+(the reference's own search parameters, gps/search.cpp:465,530), 1024 captures IN TOTAL at every N -- strong scaling:
+rank r searches scenarios.shard(1024, r, N) through farm.CaptureFarm (the CUDA engine behind the C ABI) and the 24-byte
+records are gathered with NCCL inside the timed region.
+  value      whole-job cells/s with the captures already resident in HBM (CUDA events, max over ranks)
+  e2e        the same through host buffers: pinned captures -> H2D -> search -> NCCL gather -> D2H of all records
+  configs    cfg1..cfg4 of BASELINE.json, each from its own CUDA-event loop.  N = 1: one GPU, `e2e` through acq_search()
+             (the reference-facing C-ABI call, host buffers).  N > 1: the satellite list of the ONE capture is sharded
+             over the ranks (farm.SatFarm: capture given to every rank, records gathered) -- cfg4_prn_sharded is
+             BASELINE configs[3]; these are latency-bound by launch + gather, as SURVEY 8(e) predicts.
+  roofline   dominant kernel (fused correlate + inverse FFT + peak search) against the on-SM roofs measured by
+             micro-benchmark in this run and against measured HBM; `frac` = SURVEY 8(d)'s shared-memory byte model,
+             `frac_pipe_measured` = ncu's shared-memory wavefronts of the committed profile x 128 B over the live time
+  cpu_baseline  BASELINE.md rows B1 (literal search.cpp, one core) and B2 (forked over all cores) plus the OpenMP
+             oracle port, on a bounded sample of the same captures (N = 1, rank 0)
+`--impl reference` times the reference's own CPU path on the same workload instead (see reference_arm()).
 """
 import argparse
 import json
@@ -33,9 +38,12 @@ sys.path.insert(0, ROOT)
 
 METRIC = "acquisition cells/sec (PRN x Doppler x code-phase)"
 UNIT = "cells/s"
+HEADLINE = "cfg5"
+CAPTURES_TOTAL = 1024
 # algorithmic work per tile (one inverse FFT of one (sat, Doppler, block))
 FLOP_PER_TILE = {4092: 6 * 16384 + 5 * 16384 * 14 + 3 * 4092, 16368: 6 * 16384 + 5 * 16384 * 14 + 3 * 16368}
 SMEM_BYTES_PER_TILE = {4092: 131072 + 1048576 + 4092 * 8, 16368: 131072 + 1048576 + 16368 * 8}
+L2_NOTE = "256 MiB flush write between timed steps, outside the event pairs"
 
 
 def log(*a):
@@ -44,9 +52,9 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
-    nvidia-smi needs a few hundred ms to deliver its first sample, longer than a short timed region: it is started
-    before the warm-up, samples carry timestamps, and only those between mark_start() and mark_end() are reported."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe).
+    nvidia-smi needs a few hundred ms to deliver its first sample: it is started before the first warm-up, samples
+    carry timestamps, and a region reports the samples between its own start and end marks."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap,timestamp")
@@ -54,7 +62,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.t0 = self.t1 = None
+        self.rows = None
 
     def start(self):
         try:
@@ -63,12 +71,6 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
-
-    def mark_start(self):
-        self.t0 = time.time()
-
-    def mark_end(self):
-        self.t1 = time.time()
 
     @staticmethod
     def _epoch(stamp):
@@ -80,7 +82,8 @@ class ClockSampler:
 
     def stop(self):
         if not self.proc:
-            return None
+            self.rows = []
+            return
         time.sleep(0.05)
         self.proc.terminate()
         try:
@@ -94,134 +97,226 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
-                row = (float(f[1]), float(f[2]))
+                row = (float(f[1]), float(f[2]), float(f[3]))
             except ValueError:
                 continue
             rs = {name for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9])
                   if v.lower().startswith("active")}
             rows.append((self._epoch(f[9]) if len(f) > 9 else None, row, rs))
+        self.rows = rows
+
+    def region(self, t0, t1):
+        """Clock summary over [t0, t1] (time.time() stamps); a region shorter than the sampling period falls back to
+        every sample of the run and says so."""
+        rows = self.rows or []
         if not rows:
             return None
-        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None
-                  and self.t0 <= r[0] <= self.t1]
-        use = inside or rows  # a region shorter than the sampling period: fall back to every sample of the run
+        inside = [r for r in rows if r[0] is not None and t0 <= r[0] <= t1]
+        use = inside or rows
         reasons = set().union(*[r[2] for r in use])
         return {"sm_mhz": statistics.median([r[1][0] for r in use]), "sm_max_mhz": max(r[1][1] for r in use),
+                "power_w": statistics.median([r[1][2] for r in use]),
                 "reasons": sorted(reasons), "samples": len(use), "samples_in_timed_region": len(inside),
                 "samples_total": len(rows), "period_ms": 20}
 
 
-# ------------------------------------------------------------------------------------------ workload
-def build_workload(cfg, rank, captures_per_gpu):
-    """Synthetic captures for this rank (numpy, host).  Returns table, params kwargs, packed bytes [n_cap, bytes]."""
+# ------------------------------------------------------------------------------------------ workload description
+def config_dict(cfg, n_gpus):
+    """The `config` object of the JSON line: the workload only, identical for both arms."""
+    from flydog_sdr_gps_b200 import scenarios
+    table = scenarios.table(cfg)
+    kw = scenarios.params_kw(cfg)
+    n_dop = kw.get("dop_hi", 20) - kw.get("dop_lo", -20) + 1
+    k = kw.get("k_noncoh", 1)
+    n_cap = CAPTURES_TOTAL if cfg == "cfg5" else 1
+    cells = sum(n_dop * (16368 if r[3] == 3 else 4092) for r in table) * n_cap
+    return {"workload": cfg, "detail": scenarios.CONFIGS[cfg], "captures_total": n_cap, "sats": len(table),
+            "doppler_indices": n_dop, "k_noncoh": k, "cells_per_step": cells, "tiles_per_step": len(table) * n_dop * k * n_cap,
+            "n_gpus": n_gpus,
+            "sharding": ("%d captures sharded over %d ranks (strong scaling), records gathered" % (n_cap, n_gpus))
+            if cfg == "cfg5" else ("satellite list sharded over %d ranks, capture given to every rank" % n_gpus
+                                   if n_gpus > 1 else "single GPU"),
+            "l2": L2_NOTE}
+
+
+def farm_signals(c):
+    from flydog_sdr_gps_b200 import scenarios
+    return scenarios.signals("cfg5", c)
+
+
+def farm_captures_numpy(idx):
+    """Receiver-farm captures by index, numpy generator (CPU arms and small samples)."""
+    from flydog_sdr_gps_b200 import scenarios, synth
+    table = scenarios.table("cfg5")
+    return np.stack([synth.make_capture(77_000 + c, 1, table, farm_signals(c)) for c in idx])
+
+
+def single_capture(cfg):
     from flydog_sdr_gps_b200 import scenarios, synth
     table = scenarios.table(cfg)
     kw = scenarios.params_kw(cfg)
-    k = kw.get("k_noncoh", 1)
-    caps = [synth.make_capture(10_000 * rank + c, k, table, scenarios.signals(cfg if cfg != "cfg5" else "cfg1", rank * 1000 + c))
-            for c in range(captures_per_gpu)]
-    return table, kw, np.stack(caps)
+    return synth.make_capture(10_000 + int(cfg[3]), kw.get("k_noncoh", 1), table, scenarios.signals(cfg, int(cfg[3])))
 
 
-def cpu_baseline(cfg, table, kw, packed, budget_s=12.0):
-    """Oracle port on the host cores, bounded sample of the same workload (same capture bytes)."""
-    from oracle import oracle_py as O
-    O.build(ref=False)
-    nthreads = os.cpu_count() or 1
-    prm = O.default_params(**{k: v for k, v in kw.items()})
-    n_dop = prm.dop_hi - prm.dop_lo + 1
-    # size the sample: ~0.35 ms per tile per core
-    tiles_per_sat = n_dop * prm.k_noncoh
-    n_sats = max(1, min(len(table), int(budget_s * nthreads / (tiles_per_sat * 0.35e-3))))
-    if n_sats >= nthreads:
-        n_sats -= n_sats % nthreads
-    sel = np.arange(n_sats, dtype=np.int32)
-    O.search(packed[0], table, sel=sel[:1], params=prm, nthreads=1)  # plans, page-in
-    t0 = time.perf_counter()
-    O.search(packed[0], table, sel=sel, params=prm, nthreads=nthreads)
-    dt = time.perf_counter() - t0
-    cells = sum(n_dop * (16368 if table[s][3] == 3 else 4092) for s in sel)
-    return {"value": cells / dt, "unit": UNIT, "cores": min(nthreads, n_sats), "kind": "port",
-            "sample": "%d of %d PRNs of one %s capture, all %d Doppler indices, K=%d (%.1f s); "
-                      "oracle = search.cpp restated + in-repo FFT (FFTW unavailable)" % (
-                          n_sats, len(table), cfg, n_dop, prm.k_noncoh, dt),
-            "tiles_per_s": n_sats * tiles_per_sat / dt}
+# ------------------------------------------------------------------------------------------ CPU baselines
+_ref_pool_caps = None
 
 
 def _ref_worker(args):
-    packed, sats = args
+    cap_idx, sats = args
     from oracle import oracle_py as O
     t0 = time.perf_counter()
-    O.ref_search(packed, np.asarray(sats, np.int32))
+    O.ref_search(_ref_pool_caps[cap_idx], np.asarray(sats, np.int32))
     return time.perf_counter() - t0
 
 
-def literal_reference_rate(packed_block, n_procs, sats_per_proc=4):
-    """The unmodified search.cpp (oracle/_ref): Sample()+Correlate() per sat, forked over host cores
-    (processes, not threads: the reference keeps its buffers in file statics)."""
+class LiteralReference:
+    """The UNMODIFIED gps/search.cpp (oracle/_ref: Sample() + Correlate() per satellite, serial over the satellites
+    like SearchTask, gps/search.cpp:530-602), forked over host cores -- processes, not threads: the reference keeps its
+    buffers in file statics (gps/search.cpp:51-58,97).  FFT provider: the in-repo fp32 FFT (FFTW is not installed)."""
+
+    def __init__(self, captures, n_procs):
+        global _ref_pool_caps
+        import multiprocessing as mp
+        from oracle import oracle_py as O
+        O.ref()  # SearchInit once, inherited by fork
+        _ref_pool_caps = captures
+        self.n = n_procs
+        self.pool = mp.get_context("fork").Pool(n_procs) if n_procs > 1 else None
+        self.captures = captures
+
+    def run(self, jobs):
+        """jobs: list of (capture index, sat list).  Returns wall seconds."""
+        t0 = time.perf_counter()
+        if self.pool:
+            self.pool.map(_ref_worker, jobs, chunksize=1)
+        else:
+            for j in jobs:
+                _ref_worker(j)
+        return time.perf_counter() - t0
+
+    def close(self):
+        if self.pool:
+            self.pool.close()
+            self.pool.join()
+
+
+def fftw_probe():
+    """the CPU rows use FFTW if the box has it.  Record the attempt."""
+    import ctypes
+    for name in ("libfftw3f.so.3", "libfftw3f.so"):
+        try:
+            ctypes.CDLL(name)
+            return {"library": name, "available": True,
+                    "used": False, "note": "present, but oracle/_ref was built against the in-repo FFT shim"}
+        except OSError as e:
+            err = str(e)
+    return {"library": "libfftw3f.so.3", "available": False, "error": err,
+            "note": "rows are search.cpp + in-repo fp32 FFT (FFTW unavailable)"}
+
+
+def cpu_baseline_rows(cells_per_sat=41 * 4092):
+    """BASELINE.md section 3 on this box's host cores, bounded sample of the cfg5 captures (identical bytes)."""
     from oracle import oracle_py as O
-    if not O.have_ref():
-        return None
-    import multiprocessing as mp
-    O.ref()  # SearchInit once, inherited by fork
-    jobs = [(packed_block, [(p * sats_per_proc + k) % 32 for k in range(sats_per_proc)]) for p in range(n_procs)]
+    from flydog_sdr_gps_b200 import scenarios
+    cores = os.cpu_count() or 1
+    table = scenarios.table("cfg5")
+    out = {"fftw": fftw_probe(), "rows": {}}
+    O.build(ref=False)
+    caps = farm_captures_numpy(range(max(2, cores)))
+    if O.have_ref():
+        lit1 = LiteralReference(caps, 1)
+        lit1.run([(0, [0])])  # page-in
+        n1 = 16
+        dt = lit1.run([(0, list(range(n1)))])
+        out["rows"]["B1_literal_search_cpp_1core"] = {
+            "value": n1 * cells_per_sat / dt, "unit": UNIT, "cores": 1, "ms_per_sat": dt / n1 * 1e3,
+            "sample": "%d Navstar PRNs of one cfg5 capture, Sample()+Correlate() per sat (%.2f s)" % (n1, dt)}
+        lit = LiteralReference(caps, cores)
+        lit.run([(p, [0]) for p in range(cores)])
+        per = 16
+        dt = lit.run([(p, list(range(per))) for p in range(cores)] * 2)
+        out["rows"]["B2_literal_search_cpp_all_cores"] = {
+            "value": 2 * cores * per * cells_per_sat / dt, "unit": UNIT, "cores": cores,
+            "sample": "%d processes x 2 x %d PRNs, one cfg5 capture each (%.2f s)" % (cores, per, dt)}
+        lit.close()
+    prm = O.default_params()
+    O.search(caps[0], table, sel=np.arange(1, dtype=np.int32), params=prm, nthreads=1)
+    reps = 2
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(n_procs) as pool:
-        pool.map(_ref_worker, jobs)
+    for r in range(reps):
+        O.search(caps[r], table, params=prm, nthreads=cores)
     dt = time.perf_counter() - t0
-    cells = n_procs * sats_per_proc * 41 * 4092
-    return {"value": cells / dt, "unit": UNIT, "cores": n_procs,
-            "sample": "%d x %d Navstar sats, reference defaults (41 bins), one block" % (n_procs, sats_per_proc)}
+    out["rows"]["port_oracle_openmp_all_cores"] = {
+        "value": reps * 32 * cells_per_sat / dt, "unit": UNIT, "cores": min(cores, 32),
+        "sample": "%d cfg5 captures x 32 PRNs, OpenMP over satellites (%.2f s)" % (reps, dt)}
+    head = out["rows"].get("B2_literal_search_cpp_all_cores") or out["rows"]["port_oracle_openmp_all_cores"]
+    out.update({"value": head["value"], "unit": UNIT, "cores": head["cores"],
+                "kind": "reference" if "B2_literal_search_cpp_all_cores" in out["rows"] else "port",
+                "sample": head["sample"] + "; FFT = in-repo fp32 FFT behind the FFTW API (FFTW unavailable)"})
+    return out
 
 
 # ------------------------------------------------------------------------------------------ reference arm
 def reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.
-    The default workload (cfg2) uses extensions search.cpp cannot express (half-bins, K=20), so the timed
-    code is the oracle port of search.cpp (asserted bit-identical to the unmodified search.cpp at its
-    defaults by tests/test_oracle_cpu.py); the literal search.cpp rate on its own config is attached."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, on the headline
+    workload.  cfg5 is the reference's own search (32 Navstar PRNs, bins -20..+20, K = 1), so the timed code is the
+    UNMODIFIED gps/search.cpp (oracle/_ref), one process per core, each searching whole captures satellite by satellite
+    like SearchTask; each step is a bounded sample of the 1024 captures (one per core).  Without oracle/_ref (reference
+    tree absent at build time) the OpenMP oracle port runs instead and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    table, kw, packed = build_workload(args.config, 0, 1)
-    steps, warm = args.steps, args.warmup
     from oracle import oracle_py as O
+    from flydog_sdr_gps_b200 import scenarios
     O.build(ref=False)
-    nthreads = os.cpu_count() or 1
-    prm = O.default_params(**kw)
-    n_dop = prm.dop_hi - prm.dop_lo + 1
-    tiles_per_sat = n_dop * prm.k_noncoh
-    # each step = a bounded sample sized for ~3 s on all cores
-    n_sats = max(1, min(len(table), int(3.0 * nthreads / (tiles_per_sat * 0.35e-3))))
-    sel = np.arange(n_sats, dtype=np.int32)
-    cells = sum(n_dop * (16368 if table[s][3] == 3 else 4092) for s in sel)
-    for _ in range(min(warm, 1)):
-        O.search(packed[0], table, sel=sel, params=prm, nthreads=nthreads)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.search(packed[0], table, sel=sel, params=prm, nthreads=nthreads)
-    dt = (time.perf_counter() - t0) / steps
-    value = cells / dt
+    cores = os.cpu_count() or 1
+    table = scenarios.table(HEADLINE)
+    steps, warm = args.steps, args.warmup
+    caps = farm_captures_numpy(range(cores))
+    cells_cap = 32 * 41 * 4092
+    if O.have_ref():
+        kind = "reference"
+        lit = LiteralReference(caps, cores)
+        jobs = [(p, list(range(32))) for p in range(cores)]
+        sample = "each step: %d of the %d captures (one per core) x 32 PRNs x 41 bins, unmodified gps/search.cpp forked over %d processes" % (
+            cores, CAPTURES_TOTAL, cores)
+        for _ in range(min(warm, 1)):
+            lit.run(jobs)
+        dts = [lit.run(jobs) for _ in range(steps)]
+        lit.close()
+        n_caps_step = cores
+    else:
+        kind = "port"
+        prm = O.default_params()
+        n_caps_step = 2
+        sample = "each step: 2 of the %d captures x 32 PRNs x 41 bins, OpenMP oracle port (oracle/_ref not built)" % CAPTURES_TOTAL
+        for _ in range(min(warm, 1)):
+            O.search(caps[0], table, params=prm, nthreads=cores)
+        dts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            for c in range(n_caps_step):
+                O.search(caps[c % len(caps)], table, params=prm, nthreads=cores)
+            dts.append(time.perf_counter() - t0)
+    dt = sum(dts) / len(dts)
+    value = n_caps_step * cells_cap / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.config, "detail": __import__("flydog_sdr_gps_b200").scenarios.CONFIGS[args.config]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(nthreads, n_sats), "kind": "port",
-                             "sample": "each step: %d of %d PRNs x %d Doppler indices x K=%d of one capture" % (
-                                 n_sats, len(table), n_dop, prm.k_noncoh)},
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(HEADLINE, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": sample + "; FFT = in-repo fp32 FFT behind the FFTW API (FFTW unavailable)",
+                             "fftw": fftw_probe()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    lit = literal_reference_rate(packed[0][:8192], nthreads)
-    if lit:
-        line["literal_search_cpp"] = lit
     print(json.dumps(line), flush=True)
     return 0
 
 
-def cufft_point(torch, stream, batch=256, reps=20):
-    """cuFFT through torch.fft.ifft: `batch` unnormalised-size 16384-point complex64 inverse transforms per call,
-    input and output resident (32 MiB each way, L2-sized).  This is ONLY the transform: the engine's tile also
-    forms the product, the power, the non-coherent sum and the peak search, and never writes the lags."""
+def cufft_point(torch, batch, reps=20):
+    """cuFFT through torch.fft.ifft: `batch` unnormalised 16384-point complex64 inverse transforms per call, input and
+    output resident.  ONLY the transform: the engine's tile also forms the product, the power, the non-coherent sum and
+    the peak search, and never writes the lags."""
     x = torch.randn(batch, 16384, dtype=torch.complex64, device="cuda")
     for _ in range(3):
         y = torch.fft.ifft(x, norm="forward")
@@ -233,31 +328,128 @@ def cufft_point(torch, stream, batch=256, reps=20):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
-    del y
+    del y, x
     return {"what": "torch.fft.ifft (cuFFT) %d x 16384 complex64, out-of-place, transform only" % batch,
-            "ms_per_call": ms, "transforms_per_s": batch / (ms * 1e-3)}
+            "batch": batch, "ms_per_call": ms, "transforms_per_s": batch / (ms * 1e-3)}
 
 
 # ------------------------------------------------------------------------------------------ our arm
+class Timer:
+    """Device-side and end-to-end timing of a step function pair under the contract's rules."""
+
+    def __init__(self, torch, dist, world, flush):
+        self.torch, self.dist, self.world, self.flush = torch, dist, world, flush
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device(self, step, steps, warmup):
+        """K steps bracketed by CUDA events on the launching stream, L2 flushed before each (outside the event pair);
+        returns ms per step (max over ranks of the summed event times) and the wall-clock window."""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.time()
+        for a, b in evs:
+            self.flush.fill_(1)
+            a.record()
+            step()
+            b.record()
+        self.barrier()
+        t1 = time.time()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return self.max_over_ranks(ms) / steps, (t0, t1)
+
+    def wall(self, step, steps, warmup):
+        """End to end: K synchronous calls, wall clock, barrier + synchronize on both sides, max over ranks."""
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        self.torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return self.max_over_ranks(dt) / steps * 1e3
+
+
+def kernel_counters():
+    """ncu counters of the committed profiles, per tile (profiles/r2_kernel_counters.json; tools/ncu_summary.py)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_counters.json")))
+    except Exception:
+        return {}
+
+
+def roofline_of(cfg, table, n_dop, k, n_cap, search_ms, step_kern_ms, mb, peaks):
+    lags = [16368 if r[3] == 3 else 4092 for r in table]
+    flop = sum(k * n_dop * FLOP_PER_TILE[l] for l in lags) * n_cap
+    smem_b = sum(k * n_dop * SMEM_BYTES_PER_TILE[l] for l in lags) * n_cap
+    hbm_b = n_cap * k * 8192 + len(table) * 16384 * 8 + 24 * len(table) * n_cap
+    tiles = len(table) * n_dop * k * n_cap
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    sec = search_ms * 1e-3
+    fp32_ach, smem_ach, hbm_ach = flop / sec / 1e12, smem_b / sec / 1e12, hbm_b / sec / 1e9
+    ctr = kernel_counters().get(cfg) or {}
+    r = {
+        "bound": "smem",
+        "kernel": ctr.get("kernel", "k_search_l1 / k_search_l1_multi / k_search_e1b (conj-multiply + 16384-pt inverse FFT + |.|^2 + peak search)"),
+        "achieved": smem_ach * 1e3, "peak": mb["smem_tbs"] * 1e3, "unit": "GB/s", "frac": smem_ach / mb["smem_tbs"],
+        "peak_source": "shared-memory micro-benchmark in this run (acq_microbench: conflict-free 8-byte LDS+STS); "
+                       "nominal 148 SM x 128 B/clk x SM clock",
+        "algorithmic_bytes_per_launch": smem_b,
+        "model": "SURVEY 8(d): %d B of shared-memory traffic per tile (4-pass model); the kernel itself moves fewer" % SMEM_BYTES_PER_TILE[max(lags)],
+        "kernel_ms": search_ms, "kernel_share_of_step": search_ms / step_kern_ms if step_kern_ms else None,
+        "traffic": ctr.get("dram_bytes_per_tile") and ctr["dram_bytes_per_tile"] * tiles,
+        "achieved_smem": smem_ach, "achieved_fp32": fp32_ach, "achieved_hbm": hbm_ach,
+        "fp32": {"bound": "fp32", "achieved": fp32_ach, "peak": mb["ffma_tflops"], "unit": "TFLOP/s",
+                 "frac": fp32_ach / mb["ffma_tflops"], "algorithmic_flop_per_launch": flop,
+                 "peak_source": "FFMA micro-benchmark in this run; nominal 148 SM x 128 lanes x 2 x clock"},
+        "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": hbm_b},
+    }
+    if ctr.get("smem_wavefronts_per_tile"):
+        # what the L1/shared data pipe physically carried (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared of the
+        # committed profile, per tile) at 128 B per wavefront, over the live kernel time
+        pipe = ctr["smem_wavefronts_per_tile"] * tiles * 128 / sec / 1e12
+        r["frac_pipe_measured"] = pipe / mb["smem_tbs"]
+        r["pipe_measured"] = {"smem_wavefronts_per_tile": ctr["smem_wavefronts_per_tile"], "achieved_tbs": pipe,
+                              "fma_pipe_pct_ncu": ctr.get("fma_pipe_pct"), "lsu_pipe_pct_ncu": ctr.get("lsu_pipe_pct"),
+                              "profile": ctr.get("profile")}
+    return r
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
-    ap.add_argument("--captures-per-gpu", type=int, default=0, help="0 = 1 (cfg5: 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--captures", type=int, default=CAPTURES_TOTAL, help=argparse.SUPPRESS)  # smaller farm for quick runs
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cufft", action="store_true",
-                    help="also time torch.fft.ifft (cuFFT) on a batch of 16384-point transforms: the permitted "
-                         "timed comparison point (inverse FFT only, no product / power / peak search)")
+    ap.add_argument("--no-configs", action="store_true", help="headline only (skip the cfg1..cfg4 entries)")
+    ap.add_argument("--only", default="", help="comma list of the cfg1..cfg4 entries to run (default: all)")
+    ap.add_argument("--no-cufft", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import flydog_sdr_gps_b200 as F
+    from flydog_sdr_gps_b200 import farm, scenarios, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -269,187 +461,181 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    n_cap = args.captures_per_gpu or (128 if args.config == "cfg5" else 1)
-    table, kw, packed = build_workload(args.config, rank, n_cap)
-    eng = F.AcqEngine(table, F.default_params(**kw), device=local)
-    n_sel = len(table)
-    cells_step = eng.cells_per_search() * n_cap      # per GPU per step
-    tiles_step = eng.tiles_per_search() * n_cap
-    lags = {16368 if r[3] == 3 else 4092 for r in table}
-
-    # resident inputs / outputs
-    d_in = torch.from_numpy(packed.reshape(-1)).cuda()
-    d_out = torch.zeros(n_cap * n_sel * 24, dtype=torch.uint8, device="cuda")
-    gathered = torch.zeros(world * d_out.numel(), dtype=torch.uint8, device="cuda") if world > 1 else None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    h_in = torch.from_numpy(packed.reshape(-1)).pin_memory()
-    h_out = torch.zeros(n_cap * n_sel * 24, dtype=torch.uint8).pin_memory()
     # a non-default stream: its handle is non-NULL, so the engine launches on exactly this stream and
     # torch.cuda.Event timing brackets the engine's kernels (NULL would select the engine's own stream)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-
-    def step_device():
-        eng.search_device(d_in.data_ptr(), d_out.data_ptr(), n_cap, stream_ptr=stream.cuda_stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_out)
-
-    def step_e2e():
-        eng.search_ptr(h_in.data_ptr(), n_cap, h_out.data_ptr())
-        if world > 1:
-            # records are on the host already; a host gather of 768 B/rank is what a receiver farm would do
-            pass
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-
-    # ---- device-resident timing: K steps of the product path, L2 flushed between steps (flush outside the
-    # event pairs).  No events between the kernels here: the four launches of a step are chained by
-    # programmatic dependent launch, which an event record in between would switch off.
-    sampler.mark_start()
-    launches0 = eng.launch_count
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for a, b in evs:
-        flush.fill_(1)
-        a.record()
-        step_device()
-        b.record()
-    barrier()
-    launches = eng.launch_count - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    # ---- the same K steps once more with CUDA events between the kernels (on the launching stream): per-kernel
-    # durations for the roofline.  Still inside the clock-sampling window.
-    eng.set_profiling(True)
-    step_device()
-    barrier()
-    kern_ms = []
-    evs_p = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in evs_p:
-        flush.fill_(1)
-        a.record()
-        step_device()
-        b.record()
-        kern_ms.append(eng.kernel_ms())  # waits for this step (the flush of the next step is not timed anyway)
-    barrier()
-    eng.set_profiling(False)
-    prof_ms = sum(a.elapsed_time(b) for a, b in evs_p) / args.steps
-    sampler.mark_end()
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    ms_per_step = dev_ms / args.steps
-    value = world * cells_step / (ms_per_step * 1e-3)
-
-    # ---- end-to-end timing through acq_search (host buffers, copies inside)
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = world * cells_step * args.steps / e2e_s
-
-    # results sanity: device path == host path, bitwise
-    same = bool(torch.equal(d_out.cpu(), h_out))
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel
-    search_ms = statistics.mean(k["search"] for k in kern_ms)
-    step_kern_ms = statistics.mean(sum(k.values()) for k in kern_ms)
-    mb = F.microbench(local)
-    flop = sum(eng.params.k_noncoh * eng.n_dop * FLOP_PER_TILE[16368 if r[3] == 3 else 4092] for r in table) * n_cap
-    smem_b = sum(eng.params.k_noncoh * eng.n_dop * SMEM_BYTES_PER_TILE[16368 if r[3] == 3 else 4092] for r in table) * n_cap
-    hbm_b = n_cap * eng.params.k_noncoh * 8192 + len(table) * 16384 * 8 + 24 * n_sel * n_cap
+    T = Timer(torch, dist, world, flush)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    fp32_ach = flop / (search_ms * 1e-3) / 1e12
-    smem_ach = smem_b / (search_ms * 1e-3) / 1e12
-    hbm_ach = hbm_b / (search_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get(args.config)
-        traffic = traffic and traffic.get("bytes")
-    except Exception:
-        pass
-    # The binding roof is on-SM: ncu shows the L1/shared-memory data pipe as the busiest unit
-    # (profiles/), the FMA pipe second, HBM idle.  `achieved` uses SURVEY's algorithmic shared-memory byte
-    # model per tile; the kernel itself moves fewer bytes (3 exchange passes + output pruning).
-    roofline = {
-        "bound": "smem",
-        "kernel": "k_search_l1 / k_search_e1b (conj-multiply + 16384-pt inverse FFT + |.|^2 + peak search)",
-        "achieved": smem_ach * 1e3, "peak": mb["smem_tbs"] * 1e3, "unit": "GB/s", "frac": smem_ach / mb["smem_tbs"],
-        "peak_source": "shared-memory micro-benchmark in this run (acq_microbench: conflict-free 8-byte LDS+STS); "
-                       "nominal 148 SM x 128 B/clk",
-        "algorithmic_bytes_per_launch": smem_b, "model": "SURVEY 8(d): %d B of shared-memory traffic per tile" %
-        SMEM_BYTES_PER_TILE[max(lags)],
-        "kernel_ms": search_ms, "kernel_share_of_step": search_ms / step_kern_ms,
-        "traffic": traffic,
-        "achieved_smem": smem_ach, "achieved_fp32": fp32_ach, "achieved_hbm": hbm_ach,
-        "fp32": {"bound": "fp32", "achieved": fp32_ach, "peak": mb["ffma_tflops"], "unit": "TFLOP/s",
-                 "frac": fp32_ach / mb["ffma_tflops"], "algorithmic_flop_per_launch": flop,
-                 "peak_source": "FFMA micro-benchmark in this run; nominal 148 SM x 128 lanes x 2 x clock"},
-        "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": hbm_b},
-        "microbench": mb,
-    }
+
+    # ================================================================= headline: cfg5, 1024 captures, strong scaling
+    n_total = args.captures
+    table = scenarios.table(HEADLINE)
+    eng = F.AcqEngine(table, F.default_params(), device=local)
+    fm = farm.CaptureFarm(eng, n_total, eng.k_noncoh * eng.block_bytes, len(table), dist=dist)
+    t_gen = time.time()
+    idx = range(fm.lo, fm.hi)
+    caps_dev = synth.make_capture_batch_torch([77_000 + c for c in idx], 1, table, [farm_signals(c) for c in idx], "cuda")
+    fm.load(caps_dev.cpu().numpy())
+    del caps_dev
+    log("rank %d: %d captures generated in %.1f s" % (rank, fm.n_local, time.time() - t_gen))
+    cells_total = eng.cells_per_search() * n_total
+    tiles_total = eng.tiles_per_search() * n_total
+    launches0 = eng.launch_count
+    ms_per_step, window = T.device(fm.search_resident, args.steps, args.warmup)
+    launches = eng.launch_count - launches0 - 0
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    value = cells_total / (ms_per_step * 1e-3)
+    dev_records = fm.d_all.cpu().numpy().copy()
+    # per-kernel durations (CUDA events between the kernels on the launching stream), same window of clock samples
+    eng.set_profiling(True)
+    kern_ms = []
+    for _ in range(min(args.steps, 10)):
+        flush.fill_(1)
+        fm.search_resident()
+        kern_ms.append(eng.kernel_ms())
+    T.barrier()
+    eng.set_profiling(False)
+    # end to end through host buffers
+    e2e_ms = T.wall(fm.search, args.steps, 3)
+    rec = fm.search()
+    same = bool(np.array_equal(fm.h_all.numpy(), dev_records))
+    detected = int((rec["snr"] >= 16.0).sum())
+    # spot check against single searches through the C ABI (bitwise)
+    spot_ok = True
+    if fm.n_local:
+        one = eng.search(fm.h_in.numpy()[:8192])
+        spot_ok = bool(one[0].tobytes() == rec[fm.lo].tobytes())
+    t_end_head = time.time()
+
+    search_ms = statistics.mean(k["search"] for k in kern_ms)
+    step_kern_ms = statistics.mean(sum(k.values()) for k in kern_ms)
+    mb = F.microbench(local)
+
+    # ================================================================= cfg1..cfg4
+    entries = {}
+    todo = [] if args.no_configs else [c for c in ("cfg1", "cfg2", "cfg3", "cfg4") if not args.only or c in args.only.split(",")]
+    for cfg in todo:
+        tb = scenarios.table(cfg)
+        kw = scenarios.params_kw(cfg)
+        e = eng if cfg == "cfg1" else F.AcqEngine(tb, F.default_params(**kw), device=local)
+        cap = single_capture(cfg)
+        steps_c = max(args.steps, 100) if cfg != "cfg2" else args.steps
+        cells_c, tiles_c = e.cells_per_search(), e.tiles_per_search()
+        ent = {"cells_per_step": cells_c, "tiles_per_step": tiles_c, "steps": steps_c}
+        if world == 1:
+            d_in = torch.from_numpy(cap).cuda()
+            d_out = torch.zeros(len(tb) * 24, dtype=torch.uint8, device="cuda")
+            h_in = torch.from_numpy(cap).pin_memory()
+            h_out = torch.zeros(len(tb) * 24, dtype=torch.uint8).pin_memory()
+            l0 = e.launch_count
+            ms, win = T.device(lambda: e.search_device(d_in.data_ptr(), d_out.data_ptr(), 1, stream_ptr=stream.cuda_stream),
+                               steps_c, args.warmup)
+            ent["gpu_launches_per_step"] = (e.launch_count - l0) // (steps_c + args.warmup)
+            e2 = T.wall(lambda: e.search_ptr(h_in.data_ptr(), 1, h_out.data_ptr()), steps_c, 3)
+            ent["device_equals_host_path"] = bool(torch.equal(d_out.cpu(), h_out))
+            ent["e2e"] = {"value": cells_c / (e2 * 1e-3), "unit": UNIT, "ms_per_step": e2, "h2d_bytes_per_step": int(cap.size),
+                          "d2h_bytes_per_step": len(tb) * 24, "api": "acq_search (C ABI, host buffers)"}
+            ent["sharding"] = "single GPU"
+            e.set_profiling(True)
+            km = []
+            for _ in range(10):
+                flush.fill_(1)
+                e.search_device(d_in.data_ptr(), d_out.data_ptr(), 1, stream_ptr=stream.cuda_stream)
+                km.append(e.kernel_ms())
+            e.set_profiling(False)
+            nrec = h_out.numpy().view(F.RECORD_DTYPE)
+        else:
+            sf = farm.SatFarm(e, len(tb), cap.size, dist=dist)
+            sf.load(cap)
+            ms, win = T.device(sf.search_resident, steps_c, args.warmup)
+            e2 = T.wall(sf.search, steps_c, 3)
+            nrec = sf.search().copy()
+            ent["e2e"] = {"value": cells_c / (e2 * 1e-3), "unit": UNIT, "ms_per_step": e2, "h2d_bytes_per_step": sf.h2d_bytes,
+                          "d2h_bytes_per_step": sf.d2h_bytes,
+                          "api": "farm.SatFarm.search: H2D of the capture on every rank, acq_search_device on a slice of "
+                                 "the table, NCCL all_gather of the records, D2H"}
+            ent["sharding"] = "satellite list split over %d ranks (%d..%d per rank), capture given to every rank; " \
+                              "latency-bound: launch + NCCL gather of 24-byte records (SURVEY 8(e))" % (
+                                  world, min(sf.counts), max(sf.counts))
+            e.set_profiling(True)
+            km = []
+            for _ in range(10):
+                flush.fill_(1)
+                sf.search_resident()
+                km.append(e.kernel_ms())
+            T.barrier()
+            e.set_profiling(False)
+        thr = kw.get("thr_l1", 16.0)
+        ent.update({"value": cells_c / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "tiles_per_s": tiles_c / (ms * 1e-3),
+                    "kernel_ms": {k: statistics.mean(x[k] for x in km) for k in km[0]},
+                    "detected": int((nrec["snr"] >= thr).sum()), "window": win})
+        if rank == 0:
+            sm = statistics.mean(x["search"] for x in km)
+            n_cap_shard = 1
+            tb_local = tb if world == 1 else tb[scenarios.shard(len(tb), 0, world)[0]:scenarios.shard(len(tb), 0, world)[1]]
+            rf = roofline_of(cfg, tb_local, e.n_dop, e.k_noncoh, n_cap_shard, sm, statistics.mean(sum(x.values()) for x in km), mb, peaks)
+            ent["roofline"] = {"frac": rf["frac"], "frac_fp32": rf["fp32"]["frac"], "kernel_ms": sm,
+                               "frac_pipe_measured": rf.get("frac_pipe_measured"), "bound": "smem",
+                               "note": "search kernel(s) of rank 0's share"}
+        entries[cfg] = ent
+        if e is not eng:
+            e.close()
+    if world > 1 and "cfg4" in entries:
+        entries["cfg4_prn_sharded"] = dict(entries["cfg4"], what="BASELINE configs[3]: 82 PRNs of one capture sharded over the ranks")
+
+    if rank == 0:
+        sampler.stop()
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    for ent in entries.values():
+        ent["clocks"] = sampler.region(*ent.pop("window"))
+    share_tables = table  # every rank searches the whole table on its captures
+    n_cap_rank0 = fm.n_local
+    roofline = roofline_of(HEADLINE, share_tables, eng.n_dop, eng.k_noncoh, n_cap_rank0, search_ms, step_kern_ms, mb, peaks)
+    roofline["microbench"] = mb
+    cfgd = config_dict(HEADLINE, world)
+    if n_total != CAPTURES_TOTAL:
+        cfgd.update({"captures_total": n_total, "cells_per_step": cells_total, "tiles_per_step": tiles_total,
+                     "note": "reduced farm (--captures): not the BASELINE size"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config, "detail": F.scenarios.CONFIGS[args.config], "captures_per_gpu": n_cap,
-                   "sats": n_sel, "doppler_indices": eng.n_dop, "k_noncoh": eng.params.k_noncoh,
-                   "cells_per_step_per_gpu": cells_step, "tiles_per_step_per_gpu": tiles_step,
-                   "l2": "256 MiB flush write between timed steps, outside the event pairs",
-                   "sharding": "independent captures per rank; records gathered with NCCL all_gather" if world > 1
-                   else "single GPU"},
-        "tiles_per_s": world * tiles_step / (ms_per_step * 1e-3),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel()),
-                "d2h_bytes_per_step": int(h_out.numel()), "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "acq_search (C ABI, pinned host buffers)"},
-        "gpu_launches": int(launches),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfgd,
+        "tiles_per_s": tiles_total / (ms_per_step * 1e-3),
+        "timed_region_s": ms_per_step * args.steps * 1e-3,
+        "e2e": {"value": cells_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": fm.h2d_bytes * world if world == 1 else n_total * 8192,
+                "d2h_bytes_per_step": fm.d2h_bytes * world,
+                "api": "farm.CaptureFarm.search: pinned captures -> H2D -> acq_search_device -> NCCL all_gather of the "
+                       "records -> D2H of all %d records on every rank" % (n_total * len(table))},
+        "gpu_launches": int(launches_timed),
         "kernel_ms": {k: statistics.mean(x[k] for x in kern_ms) for k in kern_ms[0]},
-        "kernel_ms_pass": {"what": "second pass of the same K steps with CUDA events between the kernels "
-                                   "(which disables programmatic dependent launch between them)",
-                           "ms_per_step": prof_ms},
-        "device_equals_host_path": same,
-        "clocks": clocks,
+        "device_equals_host_path": same and spot_ok,
+        "detected_sats": detected,
+        "clocks": sampler.region(*window),
         "roofline": roofline,
+        "configs": entries,
     }
-    if args.cufft:
-        line["cufft_comparison"] = cufft_point(torch, stream)
+    if not args.no_cufft:
+        line["cufft_comparison"] = [cufft_point(torch, 4096), cufft_point(torch, 256)]
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.config, table, kw, packed)
+        line["cpu_baseline"] = cpu_baseline_rows()
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -166,10 +166,11 @@ using namespace acq;
 // polls a completion word there instead of waiting for the stream.  Above these sizes: plain copies and a stream wait.
 constexpr size_t kStagePackedMax = 256u << 10;  // bytes
 constexpr int kHostRecordRowsMax = 256;          // records (24 B each: single PCIe writes from the SMs)
-// Up to this many (capture, sat) rows the best-Doppler pick rides on the search launches (their last CTA picks all
-// rows: a few microseconds at most); above, a kernel of its own follows (nothing against a long search).
+// Up to this many (capture, sat) rows the best-Doppler pick is one CTA that polls the search CTAs' completion counter
+// (k_pick_small: no wait for the grids to drain; a few microseconds at most); above, k_best_dop follows the search the
+// ordinary way (nothing against a long search).
 constexpr int kFoldPickRowsMax = 256;
-static_assert(kHostRecordRowsMax <= kFoldPickRowsMax, "the completion word is raised by the folded pick");
+static_assert(kHostRecordRowsMax <= kFoldPickRowsMax, "the completion word is raised by k_pick_small");
 
 int free_engine(acq_engine *e)
 {
@@ -400,14 +401,10 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     // one-CTA-per-tile form has 2.9x the throughput (profiles/r1_e1b_cluster_ab.json).
     const bool e1b_cluster =
         K > 1 || ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && tiles_e1b <= e->sm_count / 4);
-    a.slot_sat = e->cur_slot_sat;
-    a.records = records_dev;
     a.ctas_done = e->d_ctas_done;
-    a.host_flag = fold ? flag_dev : nullptr;
-    a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, false, e->sm_count) +
-                                     search_grid_ctas(tiles_e1b, e1b_cluster, e->sm_count))
+    a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, kSearchL1, e->sm_count) +
+                                     search_grid_ctas(tiles_e1b, e1b_cluster ? kSearchE1bCluster : kSearchE1b, e->sm_count))
                         : 0u;
-    a.n_rows = n_rows;
     a.epoch = e->epoch;
     a.partial = e->d_partial;
     a.flags = e->d_flags;
@@ -419,8 +416,8 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         e->launches += launch_search(a, false, e->sm_count, st, pdl);
         // The C/A kernel raises its launch-dependents trigger only after its own wait for the forward FFT, so an E1B
         // launch chained to it by programmatic dependent launch starts with the capture spectra complete: it does
-        // not wait again, and its CTAs move in as the C/A kernel's last CTAs retire (the two write disjoint rows;
-        // with the pick folded in, nothing downstream needs the launches to finish in order).
+        // not wait again, and its CTAs move in as the C/A kernel's last CTAs retire (the two write disjoint rows, and
+        // k_pick_small counts finished CTAs of both launches: nothing downstream needs them to finish in order).
         if (pdl && fold) a.wait_prior = 0;
     }
     if (e->n_e1b > 0) {
@@ -430,7 +427,10 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         if (e1b_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st, pdl);
         else e->launches += launch_search(a, true, e->sm_count, st, pdl);
     }
-    if (!fold)
+    if (fold)
+        e->launches += launch_pick_small(e->d_cells, e->cur_slot_sat, records_dev, e->d_ctas_done, a.ctas_total, flag_dev,
+                                         e->epoch, n_rows, e->n_slots, e->n_dop, e->prm.dop_lo, st, pdl);
+    else
         e->launches += launch_best_dop(e->d_cells, e->cur_slot_sat, records_dev, n_captures, e->n_slots, e->n_dop,
                                        e->prm.dop_lo, st, pdl);
     if (prof) {

@@ -568,37 +568,18 @@ __device__ __forceinline__ void pick_rows(const acq_cell *cells, const int *__re
     }
 }
 
-// End of a search kernel's CTA.  Small searches (SearchArgs::ctas_total > 0) fold the best-Doppler pick into the
-// search launches: every CTA that stored cells bumps a counter once, after a fence; the CTA that brings it to
-// ctas_total -- the last one of the whole search, C/A and E1B launches together -- picks all rows (every cell was
-// stored and fenced before its writer's atomicAdd), zeroes the counter for the next search and, for a host that polls
-// mapped memory, raises the completion word behind the records.  No separate kernel, no launch gap, nothing per tile.
-// Call with all threads of the CTA, after the CTA's last cell store; `s_last` is a shared-memory word.
-__device__ __noinline__ void search_cta_done(const acq_cell *cells, const int *slot_sat, acq_record *records, unsigned *ctas_done,
-                                             unsigned ctas_total, unsigned *host_flag, unsigned epoch, int n_rows, int n_slots,
-                                             int n_dop, int dop_lo, unsigned *s_last, int t)
+// End of a search kernel's CTA that stored cells.  Small searches (SearchArgs::ctas_total > 0) do not wait for the
+// search grids to drain before the best-Doppler pick: every cell-storing CTA bumps a counter once, after a fence, and
+// k_pick_small -- launched behind the search by programmatic dependent launch, resident as soon as a search CTA has
+// retired -- polls that counter instead of waiting for grid completion.  (The pick itself cannot live in the search
+// kernels: ptxas balances its MOV / IMAD.MOV choice over the whole kernel, and the pick's integer code tips the hot
+// loop's 40 register moves per sub-FFT onto the FMA pipe -- measured -6 % on the K = 20 kernel.)
+__device__ __forceinline__ void search_cta_epilogue(const SearchArgs &p, int t)
 {
-    if (t == 0) {
+    if (p.ctas_total && t == 0) {
         __threadfence();  // this CTA's cells (all stored by this thread) before the count
-        *s_last = (atomicAdd(ctas_done, 1u) + 1u == ctas_total) ? 1u : 0u;
+        atomicAdd(p.ctas_done, 1u);
     }
-    __syncthreads();
-    if (!*s_last) return;
-    __threadfence();
-    pick_rows<4>(cells, slot_sat, records, t >> 5, 8, n_rows, n_slots, n_dop, dop_lo, t & 31);
-    if (host_flag) __threadfence_system();  // the records are in host memory before the word that announces them
-    __syncthreads();
-    if (t == 0) {
-        *ctas_done = 0;
-        if (host_flag) *reinterpret_cast<volatile unsigned *>(host_flag) = epoch;
-    }
-}
-
-__device__ __forceinline__ void search_cta_epilogue(const SearchArgs &p, unsigned *s_last, int t)
-{
-    if (p.ctas_total)
-        search_cta_done(p.cells, p.slot_sat, p.records, p.ctas_done, p.ctas_total, p.host_flag, p.epoch, p.n_rows, p.n_slots,
-                        p.n_dop, p.dop_lo, s_last, t);
 }
 
 // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471, support/simd.cpp:12-40).
@@ -887,7 +868,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     }
     __syncthreads();
     if (pend && t == 0) flush();
-    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
+    search_cta_epilogue(p, t);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
@@ -985,7 +966,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
-    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
+    search_cta_epilogue(p, t);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
@@ -1190,7 +1171,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
-    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
+    search_cta_epilogue(p, t);
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);
 }
 
@@ -1294,11 +1275,37 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 1) k_search_e1b
         // the peak slots are rewritten only after the next tile's first cluster barrier, which rank 0's
         // thread 0 reaches after the merge above
     }
-    if (rank == 0) search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 48), t);  // rank 0 stored the cluster's cells
+    if (rank == 0) search_cta_epilogue(p, t);  // rank 0 stored the cluster's cells
 }
 
-// K5b as a kernel of its own, for large searches (small ones fold the pick into the search launches, see
-// search_cta_done): one warp per (capture, sat) row.
+// K5b for small searches (up to a few hundred rows): ONE CTA, chained to the search launches by programmatic dependent
+// launch.  It does not wait for the search grids to complete (griddepcontrol.wait: grid drain + memory flush); thread 0
+// polls the counter the search CTAs bump after their last cell (search_cta_epilogue), so the pick starts a fence and an
+// atomic after the last cell is stored -- and C/A and E1B launches of one search need no ordering between them.
+// Then eight warps pick the rows, the counter is zeroed for the next search and, for a host that polls mapped memory,
+// the completion word is raised behind the records.
+__global__ void __launch_bounds__(256) k_pick_small(const acq_cell *cells, const int *__restrict__ slot_sat, acq_record *out,
+                                                    unsigned *ctas_done, unsigned ctas_total, unsigned *host_flag, unsigned epoch,
+                                                    int n_rows, int n_slots, int n_dop, int dop_lo)
+{
+    const int t = threadIdx.x;
+    if (t == 0) {
+        const volatile unsigned *done = ctas_done;
+        while (*done != ctas_total) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    pick_rows<4>(cells, slot_sat, out, t >> 5, 8, n_rows, n_slots, n_dop, dop_lo, t & 31);
+    if (host_flag) __threadfence_system();  // the records are in host memory before the word that announces them
+    __syncthreads();
+    if (t == 0) {
+        *ctas_done = 0;
+        if (host_flag) *reinterpret_cast<volatile unsigned *>(host_flag) = epoch;
+    }
+}
+
+// K5b for large searches: one warp per (capture, sat) row, after the search grids have completed.
 __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ cells, const int *__restrict__ slot_sat,
                                                   acq_record *__restrict__ out, int n_rows, int n_slots, int n_dop,
                                                   int dop_lo)
@@ -1551,11 +1558,23 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
     return 1;
 }
 
+// Grid of a search launch = the number of its CTAs that store cells (clusters: rank 0 stores for its cluster).
+// launch_search* and the host's SearchArgs::ctas_total both come from here.
+int search_grid_ctas(long long n_tiles, int kind, int sm_count)
+{
+    if (n_tiles <= 0 || n_tiles > kMaxTilesPerLaunch) return 0;
+    long long cap = (long long)sm_count * 2;  // two persistent CTAs per SM
+    if (kind == kSearchE1bCluster) cap = sm_count / 4;
+#ifdef ACQ_VARIANT_L1_X3
+    if (kind == kSearchL1) cap = (long long)sm_count * 3;
+#endif
+    return (int)(n_tiles < cap ? n_tiles : cap);
+}
+
 int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, bool pdl)
 {
-    if (a.n_tiles <= 0 || a.n_tiles > kMaxTilesPerLaunch) return 0;
-    const long long max_ctas = (long long)sm_count * 2;
-    const int grid = (int)(a.n_tiles < max_ctas ? a.n_tiles : max_ctas);
+    const int grid = search_grid_ctas(a.n_tiles, e1b ? kSearchE1b : kSearchL1, sm_count);
+    if (grid <= 0) return 0;
     if (e1b) {
 #ifdef ACQ_VARIANT_E1B_LDG
         launch_k(k_search_e1b_ldg, grid, 256, fft_smem3_bytes() + 64 * sizeof(float), st, pdl, a);
@@ -1565,9 +1584,7 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
         return 1;
     }
 #if defined(ACQ_VARIANT_L1_X3)
-    const long long ctas3 = (long long)sm_count * 3;
-    const int grid3 = (int)(a.n_tiles < ctas3 ? a.n_tiles : ctas3);
-    launch_k(a.K > 1 ? k_search_l1_x3<true> : k_search_l1_x3<false>, grid3, 256, search_l1_x3_smem(), st, pdl, a);
+    launch_k(a.K > 1 ? k_search_l1_x3<true> : k_search_l1_x3<false>, grid, 256, search_l1_x3_smem(), st, pdl, a);
 #elif defined(ACQ_VARIANT_L1_LDG)
     launch_k(a.K > 1 ? k_search_l1_ldg<true> : k_search_l1_ldg<false>, grid, 256, fft_smem3t_bytes() + 64 * sizeof(float), st,
              pdl, a);
@@ -1581,9 +1598,8 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 
 int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st, bool pdl)
 {
-    if (a.n_tiles <= 0 || a.n_tiles > kMaxTilesPerLaunch) return 0;
-    const long long max_clusters = sm_count / 4;
-    const int n_clusters = (int)(a.n_tiles < max_clusters ? a.n_tiles : max_clusters);
+    const int n_clusters = search_grid_ctas(a.n_tiles, kSearchE1bCluster, sm_count);
+    if (n_clusters <= 0) return 0;
     launch_k(a.K > 1 ? k_search_e1b_cluster<true> : k_search_e1b_cluster<false>, 4 * n_clusters, 256,
              search_e1b_cluster_smem_bytes(), st, pdl, a);
     return 1;
@@ -1607,11 +1623,13 @@ int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out,
     return 1;
 }
 
-int search_grid_ctas(long long n_tiles, bool e1b_cluster, int sm_count)
+int launch_pick_small(const acq_cell *cells, const int *slot_sat, acq_record *out, unsigned *ctas_done, unsigned ctas_total,
+                      unsigned *host_flag, unsigned epoch, int n_rows, int n_slots, int n_dop, int dop_lo, cudaStream_t st,
+                      bool pdl)
 {
-    if (n_tiles <= 0) return 0;
-    const long long cap = e1b_cluster ? sm_count / 4 : (long long)sm_count * 2;  // clusters: rank 0 stores the cells
-    return (int)(n_tiles < cap ? n_tiles : cap);
+    launch_k(k_pick_small, 1, 256, 0, st, pdl, cells, slot_sat, out, ctas_done, ctas_total, host_flag, epoch, n_rows, n_slots,
+             n_dop, dop_lo);
+    return 1;
 }
 
 }  // namespace acq

@@ -22,17 +22,11 @@ struct SearchArgs {
     // copy i of a block delayed by a further i - smax samples; Doppler index h reads copy smax + s(b, h) of block b,
     // s = round-half-away(b h / cd_div).  n_shift == 1: off.
     int n_shift, smax, cd_div;
-    // Best-over-Doppler pick (search.cpp:455,495).  Small searches fold it into the search launches: ctas_total > 0
-    // is the number of cell-storing CTAs of the WHOLE search (C/A and E1B launches together); the last of them to
-    // finish -- counted in *ctas_done, zero between searches -- picks all n_rows rows into `records` (device memory or
-    // mapped pinned host memory) and, if host_flag is set, stores `epoch` there (mapped) behind the records for a
-    // polling host.  ctas_total == 0: a k_best_dop launch follows instead.
-    const int *slot_sat;      // [n_slots] table index of each output slot
-    acq_record *records;      // [cap][n_slots]
+    // Small searches: ctas_total > 0 is the number of cell-storing CTAs of the WHOLE search (C/A and E1B launches
+    // together); each bumps *ctas_done (zero between searches) after its last cell, and k_pick_small polls it.
     unsigned *ctas_done;
-    unsigned *host_flag;
-    unsigned ctas_total, epoch;
-    int n_rows;
+    unsigned ctas_total;
+    unsigned epoch;           // search counter: value of the hand-over flags below
     // balanced K = 1 C/A launch (k_search_l1): a tile split between two CTAs hands its partial accumulators over
     // through `partial` ([grid][16][256] float2); flags[g] == epoch once CTA g has stored its partial.
     float2 *partial;
@@ -70,8 +64,14 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st, bool pdl = false);
 int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
                     int dop_lo, cudaStream_t st, bool pdl = false);
+// best-Doppler pick of a small search: one CTA that polls the search CTAs' counter (see k_pick_small); host_flag
+// (mapped pinned memory, or NULL) receives `epoch` once the records are written
+int launch_pick_small(const acq_cell *cells, const int *slot_sat, acq_record *out, unsigned *ctas_done, unsigned ctas_total,
+                      unsigned *host_flag, unsigned epoch, int n_rows, int n_slots, int n_dop, int dop_lo, cudaStream_t st,
+                      bool pdl = false);
 // CTAs of a search launch that store cells (what SearchArgs::ctas_total sums over the launches of one search)
-int search_grid_ctas(long long n_tiles, bool e1b_cluster, int sm_count);
+enum { kSearchL1 = 0, kSearchE1b = 1, kSearchE1bCluster = 2 };
+int search_grid_ctas(long long n_tiles, int kind, int sm_count);
 // refinement of the records of the most recent search (one CTA per record)
 int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
                   int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, int n_shift, int smax, int cd_div,

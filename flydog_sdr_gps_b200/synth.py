@@ -124,3 +124,42 @@ def make_captures_torch(seed, n_captures, n_blocks, sats, signals_per_capture, d
         bits = (s < 0).to(torch.uint8).view(-1, 8)
         out[c] = (bits * weights).sum(dim=1, dtype=torch.int32).to(torch.uint8)
     return out
+
+
+def make_capture_batch_torch(seeds, n_blocks, sats, signals_per_capture, device, group=64):
+    """Batched torch generator with ONE SEED PER CAPTURE: capture i depends only on seeds[i] and its signal list, so a
+    rank that generates just its shard of a sharded batch gets the same bytes as a rank that generates everything.
+    Returns a uint8 tensor [len(seeds), n_blocks*8192] on `device`.  (Same signal model as make_capture; the noise
+    comes from torch's generator, so the bytes differ from the numpy generator's for the same seed.)"""
+    import torch
+
+    n = n_blocks * BLOCK_SAMPLES
+    n_cap = len(seeds)
+    out = torch.empty((n_cap, n // 8), dtype=torch.uint8, device=device)
+    i = torch.arange(n, device=device, dtype=torch.int64)
+    fi = i.to(torch.float64)
+    quarter = 0.25 * (i & 3).to(torch.float64)
+    weights = (2 ** torch.arange(8, device=device, dtype=torch.int32)).to(torch.uint8)
+    g = torch.Generator(device=device)
+    chip_cache = {}
+    for g0 in range(0, n_cap, group):
+        g1 = min(n_cap, g0 + group)
+        s = torch.empty((g1 - g0, n), dtype=torch.float64, device=device)
+        for c in range(g0, g1):
+            g.manual_seed(int(seeds[c]))
+            s[c - g0] = torch.randn(n, generator=g, device=device, dtype=torch.float64)
+            for sat, tau, dop, cn0, phase in signals_per_capture[c]:
+                if sat not in chip_cache:
+                    ch, boc = sat_chips(sats[sat])
+                    chip_cache[sat] = (torch.from_numpy(1.0 - 2.0 * ch.astype(np.float64)).to(device), boc)
+                ch, boc = chip_cache[sat]
+                idx = i + int(tau)
+                cc = ch[(idx >> 4) % ch.numel()]
+                if boc:
+                    cc = torch.where((idx & 15) >= 8, -cc, cc)
+                amp = float(np.sqrt(4.0 * 10.0 ** (cn0 / 10.0) / FS))
+                cyc = torch.remainder(dop / FS * fi, 1.0) + quarter
+                s[c - g0] += amp * cc * torch.cos(2.0 * np.pi * cyc + phase)
+        bits = (s < 0).to(torch.uint8).view(g1 - g0, -1, 8)
+        out[g0:g1] = (bits * weights).sum(dim=2, dtype=torch.int32).to(torch.uint8)
+    return out
