@@ -115,9 +115,7 @@ struct acq_engine {
     acq_cell *d_cells = nullptr;
     acq_record *d_records = nullptr;
     unsigned *d_ctas_done = nullptr;   // finished search CTAs of a small search (folded best-Doppler pick); zero between searches
-    float2 *d_partial = nullptr;       // [2 * sm_count][16][256]: hand-over of split tiles (balanced K = 1 launch)
-    unsigned *d_flags = nullptr;       // [2 * sm_count]
-    unsigned epoch = 0;                // search counter: value of the hand-over flags and of the completion word
+    unsigned epoch = 0;                // search counter: value of the completion word
     // host path: pinned staging of small captures; records and the completion word in mapped pinned memory,
     // written by the search kernels themselves
     uint8_t *h_packed = nullptr;
@@ -188,8 +186,6 @@ int free_engine(acq_engine *e)
     cudaFree(e->d_cells);
     cudaFree(e->d_records);
     cudaFree(e->d_ctas_done);
-    cudaFree(e->d_partial);
-    cudaFree(e->d_flags);
     cudaFree(e->d_work_full);
     cudaFree(e->d_work_single);
     cudaFree(e->d_work);
@@ -405,9 +401,6 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, kSearchL1, e->sm_count) +
                                      search_grid_ctas(tiles_e1b, e1b_cluster ? kSearchE1bCluster : kSearchE1b, e->sm_count))
                         : 0u;
-    a.epoch = e->epoch;
-    a.partial = e->d_partial;
-    a.flags = e->d_flags;
     a.wait_prior = 1;
     if (e->n_l1 > 0) {
         a.work = e->cur_work;
@@ -648,10 +641,7 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     CUE(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
     CUE(cudaEventCreateWithFlags(&e->dev_done, cudaEventDisableTiming));
     CUE(search_kernels_configure());
-    // hand-over buffers of the balanced K = 1 launch, completion counters, mapped completion word
-    CUE(cudaMalloc(&e->d_partial, (size_t)2 * e->sm_count * 16 * 256 * sizeof(float2)));
-    CUE(cudaMalloc(&e->d_flags, (size_t)2 * e->sm_count * sizeof(unsigned)));
-    CUE(cudaMemset(e->d_flags, 0, (size_t)2 * e->sm_count * sizeof(unsigned)));
+    // completion counter of small searches, mapped completion word
     CUE(cudaMalloc(&e->d_ctas_done, sizeof(unsigned)));
     CUE(cudaMemset(e->d_ctas_done, 0, sizeof(unsigned)));
     CUE(cudaHostAlloc(&e->h_flag, sizeof(unsigned), cudaHostAllocMapped));

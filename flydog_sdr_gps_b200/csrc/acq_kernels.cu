@@ -454,7 +454,7 @@ __device__ __forceinline__ Peak block_reduce_peak(Peak v, float *red_f, int *red
 }
 
 struct TileIdx {
-    int sat, slot, cap, d, dop, v, wi;
+    int sat, slot, cap, d, dop, v;
     // The host keeps a launch below 2^31 tiles (launch_search), so the decomposition runs on 32-bit unsigned
     // divisions: every warp pays it once per tile, and a K = 1 tile is only four sub-FFTs long.
     __device__ __forceinline__ TileIdx(const SearchArgs &p, long long tile)
@@ -463,8 +463,7 @@ struct TileIdx {
         const unsigned cw = tl / nd;
         d = (int)(tl - cw * nd);
         cap = (int)(cw / nw);
-        wi = (int)(cw - (unsigned)cap * nw);
-        const int2 wk = p.work[wi];
+        const int2 wk = p.work[(int)(cw - (unsigned)cap * nw)];
         sat = wk.x;
         slot = wk.y;
         set_dop(p);
@@ -474,21 +473,6 @@ struct TileIdx {
         const int h = p.dop_lo + d;
         v = p.half_bin ? (h & 1) : 0;
         dop = p.half_bin ? ((h - v) >> 1) : h;
-    }
-    // the next tile in launch order, without divisions
-    __device__ __forceinline__ void advance(const SearchArgs &p)
-    {
-        if (++d == p.n_dop) {
-            d = 0;
-            if (++wi == p.n_work) {
-                wi = 0;
-                cap++;
-            }
-            const int2 wk = p.work[wi];
-            sat = wk.x;
-            slot = wk.y;
-        }
-        set_dop(p);
     }
 };
 
@@ -678,206 +662,15 @@ __device__ __forceinline__ Peak thread_peak_l1(const float (&pw)[16], int t)
     return best;
 }
 
-// k_search_l1 -- K = 1 (the reference's search): BALANCED over the resident CTAs.  A tile is four sub-FFT units
-// (one per input residue k2) whose outputs are accumulated in a fixed chain acc = ((x0 + x1 c1) + x2 c2) + x3 c3.
-// The launch's 4 n_tiles units are cut into gridDim.x equal contiguous ranges, so that e.g. the 1312 tiles of a
-// 32-PRN cold-start search keep all 296 CTAs busy for 17.7 units each instead of five rounds of whole tiles
-// (4.43 waves run as 5).  A tile cut by a range boundary is shared by two CTAs: CTA g runs its HEAD residues
-// 0..j-1 FIRST, stores the partial chain value (16 complex per thread) to `partial[g]` and raises flags[g]; CTA g+1
-// runs the TAIL residues j..3 LAST -- its sub-FFT does not depend on the partial -- then picks the partial up and
-// continues the very same chain, so every cell is bitwise what the unsplit tile computes (the records do not
-// depend on how a search is cut).  Head first / tail last means a waiter's flag was raised a whole range ago; all
-// CTAs of the launch are resident (grid <= 2 per SM) and a CTA only ever waits for its lower neighbour.
-__global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
-{
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const L1Smem m = l1_smem_carve(smem);
-    const FftSmem4 &s = m.s;
-    float *red_f = m.red_f;
-    int *red_i = m.red_i;
-    const int t = threadIdx.x;
-    constexpr int L = ACQ_LAGS_L1;
-    const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
-    const uint32_t tw_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);
-    subfft4_park_twiddles(p.tables, tw_taddr, t);
-    const float2 *bases = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
-    const uint32_t bar = smem_u32(s.bar);
-    if (t == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (p.wait_prior) pdl_wait();
-    pdl_trigger_search();  // after the wait: a search launch that follows this one need not wait for the front end itself
-
-    // this CTA's range of units [u0, u1): tail residues of tile tA-1 (nA of them), full tiles [tA, tB), head
-    // residues of tile tB (nB of them).  Ranges are at least four units long (grid <= n_tiles).
-    int tA, tB, nA, nB;
-    {
-        const unsigned long long U = 4ull * (unsigned long long)p.n_tiles;
-        const unsigned long long u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1ull) / gridDim.x;
-        tA = (int)((u0 + 3) >> 2);
-        tB = (int)(u1 >> 2);
-        nA = (int)(4ull * tA - u0);
-        nB = (int)(u1 - 4ull * tB);
-    }
-    // thread 0: stage the operands of unit (tn, k2n) -- D into S1 half `half`, E into the E buffer
-    auto issue = [&](const TileIdx &tn, int k2n, int half) {
-        const int r = (k2n - tn.dop) & 3;
-        const int q = (k2n - tn.dop - r) >> 2;
-        const float2 *Dk = p.Dp + d_row(p, tn, 0) * kN + k2n * kSub;
-        const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
-        fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
-        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
-        tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
-        tma_load_1d(smem_u32(s.S1 + half * kS1pElems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
-    };
-    // the unit after the last full tile (or after the head piece when there is no full tile): the tail piece
-    auto issue_tail = [&](int half) {
-        if (nA > 0) issue(TileIdx(p, tA - 1), 4 - nA, half);
-    };
-    int it = 0;  // units done: S1 half and mbarrier phase parity = it & 1
-    float2 bw;   // stage-A base of the next unit; subfft4096_inv4 leaves the base of residue k2+1 behind
-    {
-        const int k2_first = (nB > 0 || tA < tB) ? 0 : 4 - nA;
-        bw = __ldg(bases + k2_first * 256);
-        if (t == 0) issue(TileIdx(p, nB > 0 ? tB : (tA < tB ? tA : tA - 1)), k2_first, 0);
-    }
-    // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2 (search.cpp:471), operands from shared memory; then
-    // the sub-FFT.  `next` runs in thread 0 right after the CTA barrier: every warp is past its operand reads of this
-    // unit and past stage C of the previous one, so the next unit's operands may land.
-    auto unit = [&](const TileIdx &ti, const int k2, float2 (&x)[16], auto &&next) {
-        float2 *S1b = s.S1 + (it & 1) * kS1pElems;
-        const int r = (k2 - ti.dop) & 3;
-        const int q = (k2 - ti.dop - r) >> 2;
-        const float2 *Dk = S1b + t;
-        const float2 *Ek = s.E + ((p.Q + q) & 1) + t;
-        mbar_wait(bar, (uint32_t)(it & 1));
-#pragma unroll
-        for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
-        subfft4096_inv4<true>(x, k2, bw, S1b, t, tw_taddr, [&]() {
-            if (t == 0) next((it + 1) & 1);
-        });
-        it++;
-    };
-    // The cross-warp merge of a tile's peak is deferred to the next unit: the warp partials are left in a parity slot
-    // and warp 0 merges them after that unit's CTA barrier, so the reduction costs no barrier of its own (it matters
-    // at K = 1, where a tile is only four units).
-    int par = 0, pend_cap = 0, pend_slot = 0, pend_d = 0;
-    bool pend = false;
-    auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge)
-        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
-    };
-    auto tile_done = [&](const TileIdx &ti, const float2 (&acc)[16]) {
-        float pw[16];
-#pragma unroll
-        for (int n2 = 0; n2 < 16; n2++) pw[n2] = cpower(acc[n2]);
-        // parity slot `par` was last read (flush) during the previous tile, before >= 3 CTA barriers
-        warp_reduce_peak(thread_peak_l1(pw, t), red_f + 16 * par, red_i + 8 * par, t);
-        pend = true;
-        pend_cap = ti.cap;
-        pend_slot = ti.slot;
-        pend_d = ti.d;
-        par ^= 1;
-    };
-
-    float2 acc[16];
-    // ---- head residues of tile tB (continued by CTA blockIdx.x + 1)
-    if (nB > 0) {
-        const TileIdx ti(p, tB);
-#pragma unroll 1
-        for (int k2 = 0; k2 < nB; k2++) {
-            float2 x[16];
-            unit(ti, k2, x, [&](int half) {
-                if (k2 + 1 < nB) issue(ti, k2 + 1, half);
-                else if (tA < tB) issue(TileIdx(p, tA), 0, half);
-                else issue_tail(half);
-            });
-            if (k2 == 0) {
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
-            } else {
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
-            }
-        }
-        float2 *dst = p.partial + (size_t)blockIdx.x * (16 * 256) + t;
-#pragma unroll
-        for (int n2 = 0; n2 < 16; n2++) __stcg(dst + 256 * n2, acc[n2]);
-        __threadfence();
-        __syncthreads();
-        if (t == 0) *reinterpret_cast<volatile unsigned *>(p.flags + blockIdx.x) = p.epoch;
-        bw = __ldg(bases + ((tA < tB) ? 0 : (4 - nA)) * 256);
-    }
-    // ---- full tiles
-    if (tA < tB) {
-        TileIdx ti(p, tA);
-        for (int tile = tA; tile < tB; tile++) {
-            float2 x[16];
-#pragma unroll kK2Unroll
-            for (int k2 = 0; k2 < 4; k2++) {
-                unit(ti, k2, x, [&](int half) {
-                    if (k2 < 3) issue(ti, k2 + 1, half);
-                    else if (tile + 1 < tB) {
-                        TileIdx tn = ti;
-                        tn.advance(p);
-                        issue(tn, 0, half);
-                    } else issue_tail(half);
-                });
-                if (k2 == 0 && pend) {   // previous tile's peak
-                    if (t == 0) flush();
-                    pend = false;
-                }
-                if (k2 == 0) {
-#pragma unroll
-                    for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
-                } else {
-#pragma unroll
-                    for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
-                }
-            }
-            tile_done(ti, acc);
-            ti.advance(p);
-        }
-    }
-    // ---- tail residues of tile tA - 1 (begun by CTA blockIdx.x - 1)
-    if (nA > 0) {
-        const TileIdx ti(p, tA - 1);
-        const int k0 = 4 - nA;
-        if (tA < tB) bw = __ldg(bases + k0 * 256);
-#pragma unroll 1
-        for (int k2 = k0; k2 < 4; k2++) {
-            float2 x[16];
-            unit(ti, k2, x, [&](int half) {
-                if (k2 < 3) issue(ti, k2 + 1, half);
-            });
-            if (pend) {
-                if (t == 0) flush();
-                pend = false;
-            }
-            if (k2 == k0) {   // pick up the chain where CTA blockIdx.x - 1 left it (its flag went up a whole range ago)
-                const volatile unsigned *flag = p.flags + (blockIdx.x - 1);
-                while (*flag != p.epoch) {
-                }
-                __threadfence();
-                const float2 *src = p.partial + (size_t)(blockIdx.x - 1) * (16 * 256) + t;
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) acc[n2] = __ldcg(src + 256 * n2);
-            }
-#pragma unroll
-            for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
-        }
-        tile_done(ti, acc);
-    }
-    __syncthreads();
-    if (pend && t == 0) flush();
-    search_cta_epilogue(p, t);
-    tmem_free_cta<2 * kTwCols>(tmem_base, t);
-}
-
-// k_search_l1_multi<true> -- k_noncoh > 1: a tile runs K inverse FFTs whose powers are summed in registers,
-// P[n] += |r_b[(n + 16 b) mod N]|^2; the 16-lag-per-block code advance is removed in the front end by delaying block
-// b (see k_hb2).  Persistent CTAs stride over the tiles (a tile is 4 K units long: no balancing needed).
-// <false> is the same loop for K = 1 (whole tiles per CTA): the A/B form of k_search_l1, variant builds only.
+// k_search_l1<MULTI> -- persistent CTAs (two per SM) stride over the tiles.  MULTI (k_noncoh > 1): a tile runs K
+// inverse FFTs whose powers are summed in registers, P[n] += |r_b[(n + 16 b) mod N]|^2; the 16-lag-per-block code
+// advance is removed in the front end by delaying block b (see k_hb2).
+// (Tried in round 2 and dropped: a K = 1 form that cuts the 4 n_tiles sub-FFT units into equal contiguous ranges per
+// CTA and hands the partial accumulators of a split tile over through L2 -- "stream-K" -- so that 1312 tiles do not
+// run as five rounds on 296 CTAs.  Bitwise-equal cells, but 78.6 -> 81.4 us per cold-start search and no change on
+// the receiver farm: the last round already runs one CTA per SM, which is 1.6x faster per tile than two.)
 template <bool MULTI>
-__global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
+__global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const L1Smem m = l1_smem_carve(smem);
@@ -914,7 +707,10 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
     if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge)
+    // The cross-warp merge of a tile's peak is deferred to the next tile: the warp partials are left in a parity slot
+    // and thread 0 merges them after the next tile's first sub-FFT barrier, so the reduction costs no CTA barrier of
+    // its own (it matters at K = 1, where a tile is only four sub-FFTs).
+    auto flush = [&]() {
         store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
     };
 
@@ -1472,11 +1268,8 @@ cudaError_t search_kernels_configure()
 {
     cudaError_t e;
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
-    if ((e = cudaFuncSetAttribute(k_search_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
-    if ((e = cudaFuncSetAttribute(k_search_l1_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
-#ifdef ACQ_VARIANT_L1_STRIDED
-    if ((e = cudaFuncSetAttribute(k_search_l1_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
-#endif
+    if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
 #ifdef ACQ_VARIANT_L1_X3
     const int l1x = (int)search_l1_x3_smem();
@@ -1588,10 +1381,8 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 #elif defined(ACQ_VARIANT_L1_LDG)
     launch_k(a.K > 1 ? k_search_l1_ldg<true> : k_search_l1_ldg<false>, grid, 256, fft_smem3t_bytes() + 64 * sizeof(float), st,
              pdl, a);
-#elif defined(ACQ_VARIANT_L1_STRIDED)
-    launch_k(a.K > 1 ? k_search_l1_multi<true> : k_search_l1_multi<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #else
-    launch_k(a.K > 1 ? k_search_l1_multi<true> : k_search_l1, grid, 256, search_l1_smem_bytes(), st, pdl, a);
+    launch_k(a.K > 1 ? k_search_l1<true> : k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #endif
     return 1;
 }

@@ -26,11 +26,6 @@ struct SearchArgs {
     // together); each bumps *ctas_done (zero between searches) after its last cell, and k_pick_small polls it.
     unsigned *ctas_done;
     unsigned ctas_total;
-    unsigned epoch;           // search counter: value of the hand-over flags below
-    // balanced K = 1 C/A launch (k_search_l1): a tile split between two CTAs hands its partial accumulators over
-    // through `partial` ([grid][16][256] float2); flags[g] == epoch once CTA g has stored its partial.
-    float2 *partial;
-    unsigned *flags;
     // 1: wait for the preceding grids of the stream (griddepcontrol.wait).  0: this launch directly follows another
     // search launch of the same search, which has already waited (see launch_search).
     int wait_prior;

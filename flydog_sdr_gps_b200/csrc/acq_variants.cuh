@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_ldg(const SearchArgs p)
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush(par ^ 1);
-    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
+    search_cta_epilogue(p, t);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush(par ^ 1);
-    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
+    search_cta_epilogue(p, t);
     tmem_free_cta<2 * kX3Cols>(tmem_base, t);
 }
 
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_ldg(const SearchArgs p)
         if (t == 0) store_cell(p, ti.cap, ti.slot, ti.d, tot, L);
     }
     __syncthreads();
-    search_cta_epilogue(p, reinterpret_cast<unsigned *>(red_f + 49), t);
+    search_cta_epilogue(p, t);
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);
 }
 

@@ -13,6 +13,7 @@ struct acq_dropin {
     acq_host_iface host{};
     std::vector<acq_sat> sats;
     std::vector<char> busy;
+    std::vector<uint8_t> mask;  // empty: every satellite; else mask[sat] == 0 skips it (gps_debug / gps_e1b_only)
     int minimum_sig = 16;  // MIN_SIG (gps/gps.h:60), overridable with -gsig (search.cpp:82-84)
     int test_mode = 0;
     int refine = 0;  // acq_dropin_set_refine: hand ChanStart the interpolated code phase / nearest Doppler bin
@@ -30,6 +31,7 @@ const int E1B_MODE = 0x800;  // kiwi.config:269
 
 bool enabled(const acq_dropin *d, const acq_sat &s)
 {
+    if (!d->mask.empty() && !d->mask[&s - d->sats.data()]) return false;  // search.cpp:537-539
     if (s.type == ACQ_NAVSTAR && !d->acq_navstar) return false;  // search.cpp:533-535
     if (s.type == ACQ_QZSS && !d->acq_qzss) return false;
     if (s.type == ACQ_E1B && !d->acq_galileo) return false;
@@ -112,6 +114,20 @@ int acq_dropin_set_acq(acq_dropin *d, int navstar, int qzss, int galileo)
     d->acq_galileo = galileo;
     return ACQ_OK;
 }
+
+int acq_dropin_set_mask(acq_dropin *d, const uint8_t *mask, int n_sats)
+{
+    if (!d) return ACQ_ERR_ARG;
+    if (!mask) {
+        d->mask.clear();
+        return ACQ_OK;
+    }
+    if (n_sats != (int)d->sats.size()) return ACQ_ERR_ARG;
+    d->mask.assign(mask, mask + n_sats);
+    return ACQ_OK;
+}
+
+int acq_dropin_min_sig(const acq_dropin *d) { return d ? d->minimum_sig : ACQ_ERR_ARG; }
 
 int acq_dropin_set_refine(acq_dropin *d, int on)
 {

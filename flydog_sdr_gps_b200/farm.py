@@ -30,7 +30,7 @@ class _Farm:
         self.eng = engine
         self.dist = dist
         self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
-        self.device = torch.device(device if device is not None else ("cuda", engine.device))
+        self.device = torch.device(device) if device is not None else torch.device("cuda", engine.device)
         self.n_units = n_units
         self.lo, self.hi = shard(n_units, self.rank, self.world)
         self.n_local = self.hi - self.lo

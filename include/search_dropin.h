@@ -60,6 +60,11 @@ int acq_dropin_destroy(acq_dropin *d);
 int acq_dropin_params(acq_dropin *d, int argc, char *argv[]);
 /* gps.acq_Navstar / acq_QZSS / acq_Galileo (search.cpp:525,533-535) */
 int acq_dropin_set_acq(acq_dropin *d, int navstar, int qzss, int galileo);
+/* Per-satellite search mask for the adapter's debugging filters (gps_debug / gps_e1b_only, search.cpp:537-539):
+ * mask[sat] == 0 skips the satellite exactly like the reference's `continue`.  NULL clears the mask. */
+int acq_dropin_set_mask(acq_dropin *d, const uint8_t *mask, int n_sats);
+/* minimum_sig as SearchParams left it (MIN_SIG or -gsig N): the value SearchTask reports with STAT_PARAMS (search.cpp:521) */
+int acq_dropin_min_sig(const acq_dropin *d);
 /* Extension, off by default: hand ChanStart the acq_refine values -- ca_shift at FS-sample
  * resolution instead of lag * DECIM, lo_shift = the bin nearest to the interpolated Doppler.  Units and call
  * order are unchanged, so gps/channel.cpp needs no edit. */

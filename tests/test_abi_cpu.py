@@ -120,7 +120,7 @@ def test_product_library_reads_no_environment_and_holds_no_experiment_kernels():
     sass = subprocess.run(["cuobjdump", "-elf", _lib.lib_path()], capture_output=True, text=True).stdout
     for k in ("k_search_l1_ldg", "k_search_l1_x3", "k_search_e1b_ldg"):
         assert k not in sass, k
-    assert "k_search_l1_multi" in sass and "k_search_e1b" in sass
+    assert "k_search_l1" in sass and "k_search_e1b" in sass and "k_pick_small" in sass
 
 
 def test_product_never_imports_the_oracle():
@@ -167,7 +167,12 @@ def test_bench_reference_arm_contract():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "cells/s" and line["higher_is_better"] is True
-    assert line["metric"].startswith("acquisition cells/sec") and line["config"]["workload"] == "cfg2"
+    assert line["metric"].startswith("acquisition cells/sec") and line["config"]["workload"] == "cfg5"
+    assert line["config"]["captures_total"] == 1024 and line["scaling"] == "strong"
+    # both arms print the same `config` object (the workload only)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.config_dict("cfg5", 1)
     assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1 and line["gpu_launches"] == 0
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -261,7 +261,7 @@ def test_device_resident_api_on_torch_stream(nav_engine):
     n0 = nav_engine.launch_count
     nav_engine.search_device(d_in.data_ptr(), d_out.data_ptr(), 4)
     torch.cuda.synchronize()
-    assert nav_engine.launch_count - n0 == 3  # front end, forward FFT, search (128 rows: the pick rides on its last CTA)
+    assert nav_engine.launch_count - n0 == 4  # front end, forward FFT, search, best-Doppler pick (k_pick_small)
     # interleaving: a device-path search on a torch stream, then the host path, then another stream, with a selection
     # change in between -- the engine orders them on its shared scratch (records bitwise equal each time)
     st2 = torch.cuda.Stream()
@@ -275,7 +275,7 @@ def test_device_resident_api_on_torch_stream(nav_engine):
         torch.cuda.synchronize()
         assert d_out.cpu().numpy().tobytes() == host.tobytes()
         assert d_out2.cpu().numpy().tobytes() == host_sel.tobytes()
-    # large batch: more than 256 rows, so the pick is a launch of its own and the records come back by a copy
+    # large batch: more than 256 rows, so the pick is k_best_dop behind the drained search and the records come back by a copy
     big = np.concatenate([caps] * 3)
     n0 = nav_engine.launch_count
     rec_big = nav_engine.search(big)
