@@ -73,17 +73,19 @@ def _planes(s, sample_bits, mag_thr):
 F_L1 = 1575.42e6
 
 
-def make_capture(seed, n_blocks, sats, signals, sample_bits=1, mag_thr=0.98, code_doppler=False):
+def make_capture(seed, n_blocks, sats, signals, sample_bits=1, mag_thr=0.98, code_doppler=False, chip_source=None):
     """numpy generator.  signals: iterable of (sat, tau, doppler_hz, cn0_dbhz, phase).  Returns uint8[n_blocks*8192]
     (sample_bits=2: uint8[n_blocks*16384], 2-bit sign/magnitude with the same sign bits; mag_thr in noise sigmas --
     0.98 is the optimum of a 4-level quantiser with levels +-1, +-3, a magnitude duty cycle of about 1/3).
-    code_doppler=True also applies each signal's Doppler to its code rate (0.52 chip of drift over 80 ms at 10 kHz)."""
+    code_doppler=True also applies each signal's Doppler to its code rate (0.52 chip of drift over 80 ms at 10 kHz).
+    chip_source: optional callable(row) -> (chips, boc) replacing this module's code tables (the golden generator passes
+    the reference's own code classes, so that those fixtures do not depend on the product's tables)."""
     rng = np.random.Generator(np.random.Philox(int(seed)))
     n = n_blocks * BLOCK_SAMPLES
     i = np.arange(n, dtype=np.int64)
     s = rng.standard_normal(n)
     for sat, tau, dop, cn0, phase in signals:
-        chips, boc = sat_chips(sats[sat])
+        chips, boc = (chip_source or sat_chips)(sats[sat])
         # code_doppler: the code is stretched by the carrier offset like a real signal's (f/f_L1 chips per chip)
         idx = (np.floor(i * (1.0 + dop / F_L1)).astype(np.int64) if code_doppler else i) + int(tau)
         c = chips[(idx >> 4) % len(chips)].astype(np.int8)

@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "_build", "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_search.so")
+REF50_SO = os.path.join(HERE, "_ref", "libref_search_e1b50.so")  # same search.cpp over a 50-row Galileo table
 
 N = 16384
 BLOCK_BYTES = 8192
@@ -93,32 +94,82 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+def _bind_ref(path):
+    R = C.CDLL(path)
+    fp = C.POINTER(C.c_float)
+    u8 = C.POINTER(C.c_uint8)
+    i32 = C.POINTER(C.c_int32)
+    R.ref_init.restype = C.c_int
+    R.ref_n_sats.restype = C.c_int
+    R.ref_sat.argtypes = [C.c_int, i32, i32, i32, i32]
+    R.ref_code_spectrum.argtypes = [C.c_int, fp]
+    R.ref_code_baseband.argtypes = [C.c_int, fp]
+    R.ref_code_baseband.restype = C.c_int
+    R.ref_sample.argtypes = [u8, fp, fp]
+    R.ref_correlate.argtypes = [C.c_int, i32, i32]
+    R.ref_correlate.restype = C.c_float
+    R.ref_search.argtypes = [u8, i32, C.c_int, i32, i32, fp]
+    R.ref_search_task.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    R.ref_search_task.restype = C.c_int
+    R.ref_get_events.argtypes = [C.c_void_p, C.c_int]
+    R.ref_e1b_chips.argtypes = [C.c_int, u8]
+    R.ref_ca_chips.argtypes = [C.c_int, C.c_int, u8]
+    R.ref_init()
+    return R
+
+
 def ref():
     """The unmodified reference search.cpp behind stubs (None if oracle/_ref was not built)."""
     global _ref
     if _ref is None:
         if not have_ref():
             return None
-        R = C.CDLL(REF_SO)
-        fp = C.POINTER(C.c_float)
-        u8 = C.POINTER(C.c_uint8)
-        i32 = C.POINTER(C.c_int32)
-        R.ref_init.restype = C.c_int
-        R.ref_n_sats.restype = C.c_int
-        R.ref_sat.argtypes = [C.c_int, i32, i32, i32, i32]
-        R.ref_code_spectrum.argtypes = [C.c_int, fp]
-        R.ref_code_baseband.argtypes = [C.c_int, fp]
-        R.ref_code_baseband.restype = C.c_int
-        R.ref_sample.argtypes = [u8, fp, fp]
-        R.ref_correlate.argtypes = [C.c_int, i32, i32]
-        R.ref_correlate.restype = C.c_float
-        R.ref_search.argtypes = [u8, i32, C.c_int, i32, i32, fp]
-        R.ref_search_task.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
-        R.ref_search_task.restype = C.c_int
-        R.ref_get_events.argtypes = [C.c_void_p, C.c_int]
-        R.ref_init()
-        _ref = R
+        _ref = _bind_ref(REF_SO)
     return _ref
+
+
+_ref50 = None
+
+
+def ref50():
+    """The unmodified search.cpp over a table of all 50 Galileo E1-B codes (None if not built).  Same API as ref();
+    sat index = PRN - 1."""
+    global _ref50
+    if _ref50 is None:
+        if not os.path.exists(REF50_SO):
+            return None
+        _ref50 = _bind_ref(REF50_SO)
+    return _ref50
+
+
+def ref_e1b_chips(prn):
+    """4092 chips of E1-B PRN prn from the reference's E1BCODE (gps/e1bcode.h:63-92)."""
+    out = np.zeros(4092, np.uint8)
+    ref().ref_e1b_chips(int(prn), _u8(out))
+    return out
+
+
+def ref_ca_chips(t1, t2):
+    """1023 chips from the reference's CACODE (gps/cacode.h:23-64)."""
+    out = np.zeros(1023, np.uint8)
+    ref().ref_ca_chips(int(t1), int(t2), _u8(out))
+    return out
+
+
+def ref50_search(packed, sel):
+    """Sample()+Correlate() of the unmodified reference over the 50-row Galileo table (sat = PRN - 1)."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    sel = np.ascontiguousarray(sel, np.int32)
+    dop, lag, snr = np.zeros(len(sel), np.int32), np.zeros(len(sel), np.int32), np.zeros(len(sel), np.float32)
+    i32 = C.POINTER(C.c_int32)
+    ref50().ref_search(_u8(packed), sel.ctypes.data_as(i32), len(sel), dop.ctypes.data_as(i32), lag.ctypes.data_as(i32), _fp(snr))
+    return dop, lag, snr
+
+
+def ref50_code_spectrum(sat):
+    out = np.zeros(2 * N, np.float32)
+    ref50().ref_code_spectrum(sat, _fp(out))
+    return out.view(np.complex64)
 
 
 def _fp(a):

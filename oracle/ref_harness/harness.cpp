@@ -2,9 +2,9 @@
  * harness.cpp -- builds the UNMODIFIED reference search (gps/search.cpp) into a test oracle.
  *
  * TEST INFRASTRUCTURE ONLY.  No reference source is copied into this repository: the
- * reference translation unit is pulled in by path below, at build time, in the development
- * container (the build recipe is oracle/Makefile, target `ref`; outputs go to oracle/_ref/,
- * which is git-ignored).  Including the .cpp (rather than linking it) makes the file-static
+ * reference translation unit is pulled in below through the include path (-I$(REF) of
+ * oracle/Makefile, target `ref`: the same tree sats.cpp and simd.cpp are taken from), at build
+ * time, in the development container; outputs go to oracle/_ref/, which is git-ignored.  Including the .cpp (rather than linking it) makes the file-static
  * workers Sample() / Correlate() and the buffers fwd_buf / code[] visible to this harness
  * (reference gps/search.cpp:54,57,382,453).
  *
@@ -13,7 +13,7 @@
  * callees ChanReset / ChanStart / GPSstat (recorded into an event log), and FFTW (oracle FFT,
  * see stubs/fftw3.h).
  */
-#include "/root/reference/gps/search.cpp"
+#include "gps/search.cpp"
 
 #include "../orc_fft.h"
 
@@ -51,6 +51,21 @@ void TaskSleepID(int, int) {}
 void TaskWakeup(int) {}
 int CreateTaskF(ref_task_fn, void *, int, int) { return 7; }
 void GPSstat_init() {}
+
+#ifdef REF_SATS_E1B50
+/* Second build of this harness (oracle/_ref/libref_search_e1b50.so): the UNMODIFIED search.cpp over a satellite table
+ * holding all 50 Galileo E1-B memory codes (the reference's own Sats[] activates 23 of them, gps/sats.cpp:104-139), in
+ * place of the reference's gps/sats.cpp.  Gives reference-made goldens for every PRN of BASELINE configs[2]/[3]. */
+#define E1ROW(p) {p, 0, 0, E1B}
+SATELLITE Sats[] = {
+    E1ROW(1),  E1ROW(2),  E1ROW(3),  E1ROW(4),  E1ROW(5),  E1ROW(6),  E1ROW(7),  E1ROW(8),  E1ROW(9),  E1ROW(10),
+    E1ROW(11), E1ROW(12), E1ROW(13), E1ROW(14), E1ROW(15), E1ROW(16), E1ROW(17), E1ROW(18), E1ROW(19), E1ROW(20),
+    E1ROW(21), E1ROW(22), E1ROW(23), E1ROW(24), E1ROW(25), E1ROW(26), E1ROW(27), E1ROW(28), E1ROW(29), E1ROW(30),
+    E1ROW(31), E1ROW(32), E1ROW(33), E1ROW(34), E1ROW(35), E1ROW(36), E1ROW(37), E1ROW(38), E1ROW(39), E1ROW(40),
+    E1ROW(41), E1ROW(42), E1ROW(43), E1ROW(44), E1ROW(45), E1ROW(46), E1ROW(47), E1ROW(48), E1ROW(49), E1ROW(50),
+    {-1}
+};
+#endif
 
 /* ---------------------------------------------------------------- capture source (SPI stub) */
 static const uint8_t *g_capture;        /* current 8192-byte block */
@@ -180,6 +195,28 @@ void ref_sat(int i, int32_t *prn, int32_t *t1, int32_t *t2, int32_t *type)
     *t1 = Sats[i].T1;
     *t2 = Sats[i].T2;
     *type = (int32_t)Sats[i].type;
+}
+
+/* chips of Galileo E1-B PRN `prn` (1..50) as the reference's own E1BCODE class expands them from its hex strings
+ * (gps/e1bcode.h:63-92): 4092 values 0/1 */
+void ref_e1b_chips(int prn, uint8_t *out)
+{
+    E1BCODE c(prn);
+    for (int i = 0; i < E1B_CODELEN; i++) {
+        out[i] = (uint8_t)c.Chip();
+        c.Clock();
+    }
+}
+
+/* chips of the C/A code with G2 taps (t1, t2) -- or the G2 preset in t2 when t1 > 10 -- from the reference's CACODE
+ * (gps/cacode.h:23-64): 1023 values 0/1 */
+void ref_ca_chips(int t1, int t2, uint8_t *out)
+{
+    CACODE c(t1, t2);
+    for (int i = 0; i < L1_CODELEN; i++) {
+        out[i] = (uint8_t)c.Chip();
+        c.Clock();
+    }
 }
 
 /* first copy of the code spectrum (search.cpp:283) */

@@ -10,7 +10,7 @@ import flydog_sdr_gps_b200 as F
 from flydog_sdr_gps_b200 import _lib, scenarios, synth
 from flydog_sdr_gps_b200 import sats as S
 
-from parity import RTOL, compare_records
+from parity import RTOL, Margins, compare_records
 
 pytestmark = pytest.mark.gpu
 
@@ -81,82 +81,115 @@ def test_golden_reference_vectors(ref_engine, golden_search):
                               (golden_search["snr"][i] >= thr)[np.abs(golden_search["snr"][i] / thr - 1) > RTOL])
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
 def test_cfg1_cold_start(nav_engine, oracle, seed):
     table = S.navstar()
     cap = synth.make_capture(seed, 1, table, scenarios.signals("cfg1", seed))
     rec, grid = nav_engine.search(cap, want_grid=True)
     orec, ogrid = oracle.search(cap, table, want_grid=True)
-    compare_records(rec[0], orec, ogrid, -20, 16.0, ggrid=grid[0])
+    m = Margins("cfg1 seed %d" % seed)
+    compare_records(rec[0], orec, ogrid, -20, 16.0, ggrid=grid[0], margins=m)
+    m.report()
     assert (orec["snr"] >= 16).sum() >= 5
 
 
-def test_cfg2_weak_signal_half_bin_noncoherent(gpu_required, oracle):
+@pytest.fixture(scope="module")
+def cfg2_engine(gpu_required):
+    eng = F.AcqEngine(scenarios.table("cfg2"), F.default_params(**scenarios.params_kw("cfg2")))
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_cfg2_weak_signal_half_bin_noncoherent(cfg2_engine, oracle, seed):
+    """BASELINE configs[1]: 32 PRNs, 161 half-bins, K = 20 blocks, satellites at 30..35 dB-Hz; five captures."""
     table = scenarios.table("cfg2")
     kw = scenarios.params_kw("cfg2")
-    sig = scenarios.signals("cfg2", 1)
-    cap = synth.make_capture(21, kw["k_noncoh"], table, sig)
-    with F.AcqEngine(table, F.default_params(**kw)) as eng:
-        rec, grid = eng.search(cap, want_grid=True)
-    okw = {k: v for k, v in kw.items()}
-    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**okw), want_grid=True)
-    compare_records(rec[0], orec, ogrid, kw["dop_lo"], kw["thr_l1"], ggrid=grid[0], max_ties=1)
+    sig = scenarios.signals("cfg2", seed)
+    cap = synth.make_capture(20 + seed, kw["k_noncoh"], table, sig)
+    rec, grid = cfg2_engine.search(cap, want_grid=True)
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
+    m = Margins("cfg2 seed %d" % seed)
+    compare_records(rec[0], orec, ogrid, kw["dop_lo"], kw["thr_l1"], ggrid=grid[0], max_ties=1, margins=m)
+    m.report()
     found = {int(r["sat"]) for r in rec[0] if r["snr"] >= kw["thr_l1"]}
-    strong = {s[0] for s in sig if s[3] >= 32.5}
-    assert strong <= found
+    strong = {s[0] for s in sig if s[3] >= 33.0}
+    assert strong <= found, (strong, found)
 
 
-def test_cfg3_galileo_e1b(gpu_required, oracle):
+@pytest.fixture(scope="module")
+def cfg3_engine(gpu_required):
+    eng = F.AcqEngine(scenarios.table("cfg3"), F.default_params(**scenarios.params_kw("cfg3")))
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_cfg3_galileo_e1b(cfg3_engine, oracle, seed):
+    """BASELINE configs[2]: all 50 E1-B codes, 81 bins, 16368 lags; five captures."""
     table = scenarios.table("cfg3")
     kw = scenarios.params_kw("cfg3")
-    cap = synth.make_capture(31, 1, table, scenarios.signals("cfg3", 1))
-    with F.AcqEngine(table, F.default_params(**kw)) as eng:
-        rec, grid = eng.search(cap, want_grid=True)
+    cap = synth.make_capture(30 + seed, 1, table, scenarios.signals("cfg3", seed))
+    rec, grid = cfg3_engine.search(cap, want_grid=True)
     orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
-    compare_records(rec[0], orec, ogrid, kw["dop_lo"], 16.0, ggrid=grid[0], max_ties=1)
+    m = Margins("cfg3 seed %d" % seed)
+    compare_records(rec[0], orec, ogrid, kw["dop_lo"], 16.0, ggrid=grid[0], max_ties=1, margins=m)
+    m.report()
     assert (orec["snr"] >= 16).sum() >= 4
 
 
-def test_cfg4_combined_sharded_by_satellite(gpu_required, oracle):
-    """82 PRNs on one capture; sharding the satellite list over 'ranks' gives the same records."""
+@pytest.fixture(scope="module")
+def cfg4_engine(gpu_required):
+    eng = F.AcqEngine(scenarios.table("cfg4"))
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_cfg4_combined_sharded_by_satellite(cfg4_engine, oracle, seed):
+    """BASELINE configs[3]: 82 PRNs on one capture; sharding the satellite list over 'ranks' gives the same records."""
     table = scenarios.table("cfg4")
-    cap = synth.make_capture(41, 1, table, scenarios.signals("cfg4", 1))
-    with F.AcqEngine(table) as eng:
-        whole, grid = eng.search(cap, want_grid=True)
-        parts = []
-        for world in (2, 4, 8):
-            recs = []
-            for rank in range(world):
-                lo, hi = scenarios.shard(len(table), rank, world)
-                recs.append(eng.search(cap, sel=np.arange(lo, hi, dtype=np.int32))[0])
-            parts.append(np.concatenate(recs))
-    for p in parts:
-        assert p.tobytes() == whole[0].tobytes()  # bitwise identical however the list is split
+    eng = cfg4_engine
+    cap = synth.make_capture(40 + seed, 1, table, scenarios.signals("cfg4", seed))
+    whole, grid = eng.search(cap, want_grid=True)
+    for world in ((2, 4, 8) if seed == 1 else (8,)):
+        recs = []
+        for rank in range(world):
+            lo, hi = scenarios.shard(len(table), rank, world)
+            recs.append(eng.search(cap, sel=np.arange(lo, hi, dtype=np.int32))[0])
+        assert np.concatenate(recs).tobytes() == whole[0].tobytes()  # bitwise identical however the list is split
     orec, ogrid = oracle.search(cap, table, want_grid=True)
-    compare_records(whole[0], orec, ogrid, -20, 16.0, ggrid=grid[0], max_ties=1)
+    m = Margins("cfg4 seed %d" % seed)
+    compare_records(whole[0], orec, ogrid, -20, 16.0, ggrid=grid[0], max_ties=1, margins=m)
+    m.report()
 
 
 def test_cfg5_receiver_farm_properties(nav_engine, oracle):
-    """1024 captures x 32 PRNs in one call (5.5e9 cells): checked through properties plus an oracle sample."""
-    import torch
+    """BASELINE configs[4]: 1024 captures x 32 PRNs in one call (5.5e9 cells).  128 DISTINCT captures -- bench.py's own
+    (same seeds, same generator) -- each searched by the oracle too; the other 896 are copies, checked through
+    size-independent properties."""
+    import bench
     table = S.navstar()
-    n_cap = 1024
-    distinct = 16
-    sigs = [scenarios.signals("cfg5", s % distinct) for s in range(n_cap)]
-    base = synth.make_captures_torch(5, distinct, 1, table, sigs[:distinct], "cuda").cpu().numpy()
-    caps = base[np.arange(n_cap) % distinct]  # capture c is a copy of capture c % 16
+    n_cap, distinct = 1024, 128
+    sigs = [bench.farm_signals(c) for c in range(distinct)]
+    base = synth.make_capture_batch_torch([77_000 + c for c in range(distinct)], 1, table, sigs, "cuda").cpu().numpy()
+    caps = base[np.arange(n_cap) % distinct]  # capture c is a copy of capture c % 128
     rec = nav_engine.search(caps.reshape(-1))
     assert rec.shape == (n_cap, 32)
     # (i) independence: identical captures give bitwise identical records wherever they sit in the batch
     for c in range(distinct, n_cap):
         assert rec[c].tobytes() == rec[c % distinct].tobytes()
     # (ii) batch == one-at-a-time
-    for c in (0, 5, 15):
+    for c in (0, 5, 77, 127):
         assert nav_engine.search(caps[c])[0].tobytes() == rec[c].tobytes()
-    # (iii) oracle on a sample of the distinct captures
-    for c in (0, 7, 15):
+    # (iii) the oracle on EVERY distinct capture
+    m = Margins("cfg5, 128 distinct captures")
+    ties = 0
+    for c in range(distinct):
         orec, ogrid = oracle.search(caps[c], table, want_grid=True)
-        compare_records(rec[c], orec, ogrid, -20, 16.0, max_ties=1)
+        ties += compare_records(rec[c], orec, ogrid, -20, 16.0, max_ties=1, margins=m)
+    m.report()
+    assert ties <= 4
     # (iv) every strong injected satellite is detected at its injected lag / Doppler bin
     for c in range(distinct):
         for sat, tau, f, cn0, _ in sigs[c]:
@@ -164,6 +197,49 @@ def test_cfg5_receiver_farm_properties(nav_engine, oracle):
                 r = rec[c][sat]
                 assert r["snr"] >= 16 and abs(((r["lag"] - tau / 4.0 + 2046) % 4092) - 2046) <= 1
                 assert r["dop"] == int(np.round(f / F.BIN_HZ))
+
+
+def test_e1b_all_50_codes_against_reference_goldens(gpu_required):
+    """The engine over all 50 Galileo E1-B codes against the UNMODIFIED search.cpp run over a 50-row table
+    (oracle/_ref/libref_search_e1b50.so -> tests/golden/ref_e1b50.npz): code spectra of every PRN, and Correlate()'s
+    answers on a capture synthesised from the reference's own chips.  Independent of the oracle and of every code
+    table in this repository."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "ref_e1b50.npz"))
+    table = S.e1b(range(1, 51))
+    with F.AcqEngine(table) as eng:
+        for k in range(50):
+            c = eng.code_spectrum(k)
+            scale = np.abs(g["spec_bins"][k]).max()
+            assert np.abs(c[g["spec_idx"]] - g["spec_bins"][k]).max() / scale < 1e-5, k
+            assert abs(np.abs(c).astype(np.float64).sum() / g["spec_abs_sum"][k] - 1) < 1e-5, k
+        rec = eng.search(g["capture"])[0]
+    thr = 16.0
+    np.testing.assert_allclose(rec["snr"], g["snr"], rtol=RTOL)
+    clear = np.abs(g["snr"] / thr - 1) > RTOL
+    assert np.array_equal((rec["snr"] >= thr)[clear], (g["snr"] >= thr)[clear])
+    det = g["snr"] >= thr * (1 + RTOL)
+    assert np.array_equal(rec["dop"][det], g["dop"][det]) and np.array_equal(rec["lag"][det], g["lag"][det])
+    assert np.array_equal(rec["dop"], g["dop"]) and np.array_equal(rec["lag"], g["lag"])  # no tie on this fixture
+    print("e1b50: detected", int(det.sum()), "of 50; nearest to the threshold: snr", float(g["snr"][np.argmin(np.abs(g["snr"] - thr))]))
+
+
+def test_e1b_noise_only_capture_near_the_threshold(cfg3_engine, oracle):
+    """The E1B threshold (16, search.cpp:549) sits at the top of the noise distribution of a 16368-lag x 81-bin scan:
+    this noise-only capture (seed found by tools/find_threshold_capture.py) has its strongest false peak within 3 % of
+    16.  Engine and oracle must agree on which side every satellite falls, and the margin is printed."""
+    table = scenarios.table("cfg3")
+    kw = scenarios.params_kw("cfg3")
+    cap = synth.make_capture(scenarios.E1B_NEAR_THRESHOLD_SEED, 1, table, [])
+    rec, grid = cfg3_engine.search(cap, want_grid=True)
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
+    m = Margins("noise-only E1B capture near the threshold")
+    compare_records(rec[0], orec, ogrid, kw["dop_lo"], 16.0, ggrid=grid[0], max_ties=1, margins=m)
+    m.report()
+    top = float(orec["snr"].max())
+    assert abs(top / 16.0 - 1) < 0.03, top
+    assert np.array_equal(rec[0]["snr"] >= 16.0, orec["snr"] >= 16.0)
 
 
 def test_lag_and_doppler_sweep(nav_engine):

@@ -385,3 +385,54 @@ def test_code_doppler_compensation(oracle):
     prm = oracle.default_params(dop_lo=-40, dop_hi=40, k_noncoh=4, code_doppler=1)
     r = oracle.search(g, table, sel=[4], params=prm)
     assert r["dop"][0] == 38 and r["lag"][0] == 1250
+
+
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a, np.uint8).tobytes()).hexdigest()
+
+
+def test_code_tables_match_reference_sha256(oracle):
+    """Every code table in the repository -- the oracle's, the product's packed ICD table (csrc/e1b_codes.inc, as the
+    engine unpacks it) and the generator's copy (data/e1b_codes.bin) -- against SHA-256 digests of the chips the
+    REFERENCE's own E1BCODE / CACODE classes produce (tests/golden/ref_code_chips_sha256.json, tools/gen_golden.py
+    codes).  Runs without the reference tree: a packing error can no longer be common to oracle and product."""
+    import json
+    import re
+    from conftest import GOLDEN, ROOT
+    from flydog_sdr_gps_b200 import sats as S, synth
+    want = json.load(open(os.path.join(GOLDEN, "ref_code_chips_sha256.json")))
+    assert len(want["e1b"]) == 50 and len(want["ca"]) == 36
+    text = open(os.path.join(ROOT, "flydog_sdr_gps_b200", "csrc", "e1b_codes.inc")).read()
+    words = np.array([int(w, 16) for w in re.findall(r"0x([0-9a-fA-F]+)", text)], np.uint64).astype(np.uint32)
+    assert words.size == 50 * 128
+    for prn in range(1, 51):
+        w = words[(prn - 1) * 128: prn * 128]
+        inc_chips = ((w[np.arange(4092) >> 5] >> (np.arange(4092) & 31).astype(np.uint32)) & 1).astype(np.uint8)
+        for name, chips in (("oracle", oracle.e1b_chips(prn)), ("e1b_codes.inc", inc_chips), ("e1b_codes.bin", synth.e1b_chips(prn))):
+            assert _sha(chips) == want["e1b"][str(prn)], (name, prn)
+    for row in S.navstar() + S.qzss():
+        for name, chips in (("oracle", oracle.ca_chips(row[1], row[2])), ("synth", synth.ca_chips(row[1], row[2]))):
+            assert _sha(chips) == want["ca"][str(row[0])], (name, row)
+
+
+def test_all_50_e1b_codes_against_reference_goldens(oracle):
+    """The oracle over all 50 Galileo E1-B codes against the unmodified search.cpp run over a 50-row table
+    (oracle/_ref/libref_search_e1b50.so; fixture tests/golden/ref_e1b50.npz): code spectra and Correlate() answers
+    bit-identical (same FFT underneath)."""
+    from conftest import GOLDEN
+    from flydog_sdr_gps_b200 import sats as S
+    g = np.load(os.path.join(GOLDEN, "ref_e1b50.npz"))
+    table = S.e1b(range(1, 51))
+    for k in range(50):
+        c = oracle.code_spectrum(table[k])
+        assert np.array_equal(c[g["spec_idx"]], g["spec_bins"][k]), k
+        assert abs(np.abs(c).astype(np.float64).sum() - g["spec_abs_sum"][k]) <= 1e-9 * g["spec_abs_sum"][k]
+    rec = oracle.search(g["capture"], table)
+    assert np.array_equal(rec["dop"], g["dop"]) and np.array_equal(rec["lag"], g["lag"])
+    assert np.array_equal(rec["snr"], g["snr"])
+    injected = {int(s[0]) for s in g["signals"]}
+    assert injected <= {int(k) for k in np.nonzero(g["snr"] >= 16)[0]}
+    if oracle.ref50() is not None:   # live check where the reference build exists
+        dop, lag, snr = oracle.ref50_search(g["capture"], np.arange(50, dtype=np.int32))
+        assert np.array_equal(dop, g["dop"]) and np.array_equal(lag, g["lag"]) and np.array_equal(snr, g["snr"])

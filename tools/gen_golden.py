@@ -83,5 +83,49 @@ def main():
     print("wrote", out3, len(ev), "events;", int((ev["kind"] == 2).sum()), "ChanStart calls")
 
 
+def gen_codes_and_e1b50():
+    """Fixtures that pin the code tables to the REFERENCE's own code classes, independently of the product's packed
+    tables (csrc/e1b_codes.inc, data/e1b_codes.bin) and of the oracle's copy:
+      ref_code_chips_sha256.json  SHA-256 of the chip sequence (one byte per chip, 0/1) of every Galileo E1-B PRN 1..50
+                                  (E1BCODE, gps/e1bcode.h:63-92) and of every C/A row of Sats[] (CACODE, gps/cacode.h)
+      ref_e1b50.npz               the UNMODIFIED search.cpp over a table of all 50 E1-B codes (oracle/_ref/
+                                  libref_search_e1b50.so): code-spectrum fingerprints per PRN and Correlate()'s answers
+                                  on a capture whose signals were synthesised from the reference's chips"""
+    import hashlib
+    import json
+    O.build(ref=True)
+    assert O.have_ref() and O.ref50() is not None
+    sha = {"e1b": {}, "ca": {}}
+    for prn in range(1, 51):
+        sha["e1b"]["%d" % prn] = hashlib.sha256(O.ref_e1b_chips(prn).tobytes()).hexdigest()
+    for row in S.navstar() + S.qzss():
+        sha["ca"]["%d" % row[0]] = hashlib.sha256(O.ref_ca_chips(row[1], row[2]).tobytes()).hexdigest()
+    sha["_doc"] = "sha256 of the chips (uint8 0/1, one per chip) from the reference's E1BCODE / CACODE; tools/gen_golden.py codes"
+    out = os.path.join(ROOT, "tests", "golden", "ref_code_chips_sha256.json")
+    json.dump(sha, open(out, "w"), indent=1, sort_keys=True)
+    print("wrote", out)
+
+    table = S.e1b(range(1, 51))
+    rng = np.random.default_rng(20261018)
+    # PRNs outside the 23 the reference's Sats[] activates get most of the signals
+    inactive = [p for p in range(1, 51) if p not in S._E1B_ACTIVE]
+    prns = list(rng.choice(inactive, 5, replace=False)) + [11, 36]
+    sig = [(int(p - 1), int(rng.integers(0, 65472)), float(rng.integers(-19, 20)) * BIN_HZ, float(rng.uniform(45, 49)),
+            float(rng.uniform(0, 6.28))) for p in prns]
+    cap = synth.make_capture(7050, 1, table, sig, chip_source=lambda row: (O.ref_e1b_chips(row[0]), True))
+    sel = np.arange(50, dtype=np.int32)
+    dop, lag, snr = O.ref50_search(cap, sel)
+    print("e1b50 detected", [(int(k) + 1, int(dop[k]), int(lag[k]), round(float(snr[k]), 1)) for k in sel if snr[k] >= 16])
+    idx = np.sort(rng.choice(16384, 64, replace=False)).astype(np.int32)
+    spec = np.stack([O.ref50_code_spectrum(k) for k in range(50)])
+    out2 = os.path.join(ROOT, "tests", "golden", "ref_e1b50.npz")
+    np.savez_compressed(out2, capture=cap, signals=np.array(sig), dop=dop, lag=lag, snr=snr, spec_idx=idx,
+                        spec_bins=spec[:, idx], spec_abs_sum=np.abs(spec).astype(np.float64).sum(axis=1))
+    print("wrote", out2, os.path.getsize(out2), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "codes":
+        gen_codes_and_e1b50()
+    else:
+        main()
