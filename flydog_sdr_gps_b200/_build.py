@@ -59,8 +59,10 @@ VARIANTS = {
     "e1b_ldg": ["ACQ_VARIANT_E1B_LDG", "ACQ_FORCE_E1B_KERNEL=1"],  # one-CTA E1B search, operands straight from L2
     "e1b_cta": ["ACQ_FORCE_E1B_KERNEL=1"],   # always the one-CTA E1B form
     "e1b_cluster": ["ACQ_FORCE_E1B_KERNEL=2"],  # always the cluster/DSMEM E1B form
+    "trace": ["ACQ_TRACE"],                  # %globaltimer stamps per CTA (tools/trace_timeline.py)
     "pdl0": ["ACQ_FORCE_PDL=0"],
     "pdl1": ["ACQ_FORCE_PDL=1"],
+    "zcin": ["ACQ_ZC_INPUT=1"],              # front end reads small captures from mapped pinned memory (no H2D copy node)
     "devrec": ["ACQ_HOST_RECORDS=0"],        # records through device memory + copy, stream wait (no mapped memory, no polling)
 }
 

@@ -118,7 +118,7 @@ struct acq_engine {
     unsigned epoch = 0;                // search counter: value of the completion word
     // host path: pinned staging of small captures; records and the completion word in mapped pinned memory,
     // written by the search kernels themselves
-    uint8_t *h_packed = nullptr;
+    uint8_t *h_packed = nullptr, *dh_packed = nullptr;  // host / device address of the (mapped) staging buffer
     size_t cap_h_packed = 0;
     acq_record *h_records = nullptr, *dh_records = nullptr;  // host / device address of the same mapped buffer
     size_t cap_h_records = 0;
@@ -159,15 +159,21 @@ using namespace acq;
 #ifndef ACQ_HOST_RECORDS
 #define ACQ_HOST_RECORDS 1
 #endif
+//   ACQ_ZC_INPUT=0|1         small captures: host->device copy node (0) or read by the front end straight from the
+//                            mapped pinned staging buffer (1: its bulk copies then cross PCIe, no copy node)
+#ifndef ACQ_ZC_INPUT
+#define ACQ_ZC_INPUT 0
+#endif
 // Host path, small searches: the capture goes through an engine-owned pinned staging buffer (a pageable source would
 // make cudaMemcpyAsync synchronous), the kernels write the records straight into mapped pinned memory, and the host
 // polls a completion word there instead of waiting for the stream.  Above these sizes: plain copies and a stream wait.
 constexpr size_t kStagePackedMax = 256u << 10;  // bytes
+constexpr size_t kZeroCopyMax = 64u << 10;      // bytes the front end may fetch over PCIe itself (ACQ_ZC_INPUT)
 constexpr int kHostRecordRowsMax = 256;          // records (24 B each: single PCIe writes from the SMs)
 // Up to this many (capture, sat) rows the best-Doppler pick is one CTA that polls the search CTAs' completion counter
 // (k_pick_small: no wait for the grids to drain; a few microseconds at most); above, k_best_dop follows the search the
 // ordinary way (nothing against a long search).
-constexpr int kFoldPickRowsMax = 256;
+constexpr int kFoldPickRowsMax = acq::kPickSmallRowsMax;
 static_assert(kHostRecordRowsMax <= kFoldPickRowsMax, "the completion word is raised by k_pick_small");
 
 int free_engine(acq_engine *e)
@@ -256,9 +262,10 @@ int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool host_path)
     if (bytes <= kStagePackedMax && bytes > e->cap_h_packed) {
         if ((rc = drain(e))) return rc;
         if (e->h_packed) CU(cudaFreeHost(e->h_packed));
-        e->h_packed = nullptr;
+        e->h_packed = e->dh_packed = nullptr;
         e->cap_h_packed = 0;
-        CU(cudaHostAlloc(&e->h_packed, bytes, cudaHostAllocDefault));
+        CU(cudaHostAlloc(&e->h_packed, bytes, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer(&e->dh_packed, e->h_packed, 0));
         e->cap_h_packed = bytes;
     }
     if (ACQ_HOST_RECORDS && rows <= (size_t)kHostRecordRowsMax) {
@@ -487,8 +494,10 @@ int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int3
         memcpy(e->h_packed, packed, bytes);
         src = e->h_packed;
     }
-    CU(cudaMemcpyAsync(e->d_packed, src, bytes, cudaMemcpyHostToDevice, e->stream));
-    if ((rc = enqueue_search(e, e->d_packed, n_captures, host_records ? e->dh_records : e->d_records,
+    const uint8_t *packed_dev = e->d_packed;
+    if (ACQ_ZC_INPUT && src == e->h_packed && bytes <= kZeroCopyMax) packed_dev = e->dh_packed;
+    else CU(cudaMemcpyAsync(e->d_packed, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = enqueue_search(e, packed_dev, n_captures, host_records ? e->dh_records : e->d_records,
                              poll ? e->dh_flag : nullptr, e->stream)))
         return rc;
     e->last_captures = n_captures;

@@ -454,6 +454,26 @@ __device__ __forceinline__ void pdl_trigger_fft() { pdl_launch_dependents(); }
 #endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Timeline instrumentation of the experiment variant "trace" (tools/trace_timeline.py): thread 0 of every CTA stamps
+// %globaltimer at entry, after its wait for the preceding grid and at exit.  Compiled out of the product.
+#ifdef ACQ_TRACE
+constexpr int kTraceKernels = 6, kTraceCtas = 1024;
+enum { kTrFrontEnd = 0, kTrFwdFft = 1, kTrSearchL1 = 2, kTrSearchE1b = 3, kTrPick = 4, kTrE1bCluster = 5 };
+__device__ unsigned long long g_trace[kTraceKernels][kTraceCtas][4];
+__device__ __forceinline__ void trace_stamp(int kernel, int slot)
+{
+    const unsigned cta = blockIdx.x + gridDim.x * blockIdx.y;
+    if (threadIdx.x == 0 && cta < (unsigned)kTraceCtas) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[kernel][cta][slot] = t;
+    }
+}
+#define ACQ_TRACE_STAMP(kernel, slot) trace_stamp(kernel, slot)
+#else
+#define ACQ_TRACE_STAMP(kernel, slot)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {

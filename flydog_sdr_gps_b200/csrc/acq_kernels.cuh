@@ -66,6 +66,7 @@ int launch_pick_small(const acq_cell *cells, const int *slot_sat, acq_record *ou
                       bool pdl = false);
 // CTAs of a search launch that store cells (what SearchArgs::ctas_total sums over the launches of one search)
 enum { kSearchL1 = 0, kSearchE1b = 1, kSearchE1bCluster = 2 };
+constexpr int kPickSmallRowsMax = 256;  // rows k_pick_small stages in shared memory
 int search_grid_ctas(long long n_tiles, int kind, int sm_count);
 // refinement of the records of the most recent search (one CTA per record)
 int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
