@@ -54,6 +54,7 @@ def build(force=False, verbose=False, defines=(), out=None):
 # Experiment variants (A/B forms of the kernels and launch policy).  They are separate libraries: the product
 # library contains none of this code and reads no environment variable.
 VARIANTS = {
+    "l1_multi_tw": ["ACQ_VARIANT_L1_MULTI_TW"],  # K > 1 C/A search with the twiddles (not the code run) in tensor memory
     "l1_ldg": ["ACQ_VARIANT_L1_LDG"],        # C/A search, operands straight from L2
     "l1_x3": ["ACQ_VARIANT_L1_X3"],          # C/A search at three CTAs per SM (accumulators in tensor memory)
     "e1b_ldg": ["ACQ_VARIANT_E1B_LDG", "ACQ_FORCE_E1B_KERNEL=1"],  # one-CTA E1B search, operands straight from L2

@@ -193,6 +193,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[8])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float2 (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+          "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y),
+          "=f"(v[8].x), "=f"(v[8].y), "=f"(v[9].x), "=f"(v[9].y), "=f"(v[10].x), "=f"(v[10].y), "=f"(v[11].x), "=f"(v[11].y),
+          "=f"(v[12].x), "=f"(v[12].y), "=f"(v[13].x), "=f"(v[13].y), "=f"(v[14].x), "=f"(v[14].y), "=f"(v[15].x), "=f"(v[15].y)
+        : "r"(taddr)
+        : "memory");
+}
 // One warp allocates `cols` columns (power of two >= 32) for the CTA; every thread gets the base address.
 // Contains a __syncthreads().
 template <int COLS>
@@ -624,9 +636,29 @@ __device__ __forceinline__ void tmem_st1(uint32_t taddr, const float2 v)
 constexpr uint32_t kSwz = ACQ_SWZ128 ? 16u : 8u;
 constexpr int kSwzMask = ACQ_SWZ128 ? 7 : 15;
 
-template <class PostBarrier>
+// Where the stage-A base W16384^{4t + k2'} of the NEXT residue k2' = (k2 + 1) & 3 comes from: two TMEM columns per
+// residue (kernels with columns to spare), or the 8 KiB table in global memory (L1/L2-resident; kernels whose tensor
+// memory is full).  issue() runs before the CTA barrier, get() after stage B: the latency is hidden either way.
+struct BaseFromTmem {
+    uint32_t taddr;  // columns [taddr + 2 k2', +2)
+    float2 v;
+    __device__ __forceinline__ void issue(int k2) { tmem_ld1(taddr + 2 * ((k2 + 1) & 3), v); }
+    __device__ __forceinline__ float2 get()
+    {
+        tmem_wait_ld();
+        return v;
+    }
+};
+struct BaseFromGlobal {
+    const float2 *bases;  // this thread's column of the [4][256] table: bases[256 k2']
+    float2 v;
+    __device__ __forceinline__ void issue(int k2) { v = __ldg(bases + 256 * ((k2 + 1) & 3)); }
+    __device__ __forceinline__ float2 get() { return v; }
+};
+
+template <class BaseSrc, class PostBarrier>
 __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
-                                                 const float2 *T2s, const uint32_t base_taddr, PostBarrier &&post_barrier)
+                                                 const float2 *T2s, BaseSrc base_src, PostBarrier &&post_barrier)
 {
     radix16_inv(x);
     stage_a_store<256>(x, b, S1b + t);
@@ -639,8 +671,7 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
     const float2 *twp = T2s + k2 * (15 * 16) + (t & 15);
 #pragma unroll
     for (int i = 0; i < (ACQ_E1B_TW15 ? 15 : 8); i++) tw[i] = twp[i * 16];  // n1 = 1..8 (or all 15)
-    float2 bn;
-    tmem_ld1(base_taddr + 2 * ((k2 + 1) & 3), bn);
+    base_src.issue(k2);
     __syncthreads();
     post_barrier();
     float2 *row = S1b + (t >> 4) * 256;  // row n0 = t >> 4
@@ -651,8 +682,7 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
         for (int bb = 0; bb < 16; bb++) x[bb] = src[16 * bb];
     }
     radix16_inv(x);
-    tmem_wait_ld();
-    b = bn;
+    b = base_src.get();
     __syncwarp();  // the half-warp has consumed its row: reuse it as the B->C tile, element (n1, c) at 16 n1 + (c ^ n1)
     {
         const uint32_t wb = smem_u32(row + c);

@@ -788,6 +788,141 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
+// k_search_l1_multi -- k_noncoh > 1 with the CODE operand resident in tensor memory.  The code run E of a tile depends on
+// (satellite, Doppler, residue k2) but not on the block b, and a thread always reads the same 16 values of it
+// (E[256 a + t]): 4 residues x 16 complex = exactly the 128 TMEM columns a thread owns.  They are staged by TMA and
+// parked during block 0 and come back by one tcgen05.ld per sub-FFT for blocks 1..K-1 -- 19 of 20 in cfg2 -- so for those
+// neither the 32 KiB bulk copy of E nor its 16 shared-memory loads per thread touch the L1/shared data pipe, the
+// kernel's busiest unit (-20 % wavefronts per tile).  The stage-B twiddles, which k_search_l1<true> keeps in those
+// columns, move to a 7.5 KiB shared-memory table (15 broadcast loads per thread and sub-FFT: +6 %), the stage-A bases to
+// the 8 KiB global table (L1-resident).  106 KiB of shared memory per CTA, two CTAs per SM; same arithmetic in the same
+// order as k_search_l1<true>, so the cells are bitwise equal (tested against the variant that keeps the old form).
+struct L1MultiSmem {
+    float2 *S1;  // [2][4096]
+    float2 *E;   // [4098]
+    unsigned long long *bar;
+    float2 *T2;  // [4][15][16]
+    float *red_f;
+    int *red_i;
+};
+__host__ __device__ constexpr size_t l1_multi_smem_bytes()
+{
+    return sizeof(float2) * (size_t)(2 * kSub + kEBufElems) + 16 + sizeof(float2) * kT2Elems + 64 * sizeof(float);
+}
+
+__global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    L1MultiSmem s;
+    s.S1 = reinterpret_cast<float2 *>(smem);
+    s.E = s.S1 + 2 * kSub;
+    s.bar = reinterpret_cast<unsigned long long *>(s.E + kEBufElems);
+    s.T2 = reinterpret_cast<float2 *>(s.bar + 2);
+    s.red_f = reinterpret_cast<float *>(s.T2 + kT2Elems);  // [2 parities][16], then the TMEM slot at [48]
+    s.red_i = reinterpret_cast<int *>(s.red_f + 32);        // [2 parities][8]
+    float *red_f = s.red_f;
+    int *red_i = s.red_i;
+    const int t = threadIdx.x;
+    ACQ_TRACE_STAMP(kTrSearchL1, 0);
+    constexpr int L = ACQ_LAGS_L1;
+    const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
+    const uint32_t e_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);  // [k2][16 complex]
+    {   // stage-B twiddle table into shared memory
+        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
+        float4 *dst = reinterpret_cast<float4 *>(s.T2);
+        for (int i = t; i < kT2Elems / 2; i += 256) dst[i] = __ldg(src + i);
+    }
+    const float2 *bases = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
+    float2 bw = __ldg(bases);
+    const uint32_t bar = smem_u32(s.bar);
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (p.wait_prior) pdl_wait();
+    ACQ_TRACE_STAMP(kTrSearchL1, 1);
+    pdl_trigger_search();
+    // thread 0: stage the operands of sub-FFT (tn, bn, k2n) -- D into S1 half `half`; E only for block 0
+    auto issue = [&](const TileIdx &tn, int bn, int k2n, int half) {
+        const int r = (k2n - tn.dop) & 3;
+        const int q = (k2n - tn.dop - r) >> 2;
+        const float2 *Dk = p.Dp + d_row(p, tn, bn) * kN + k2n * kSub;
+        fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
+        if (bn == 0) {
+            const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
+            mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
+            tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+        } else {
+            mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * kSub));
+        }
+        tma_load_1d(smem_u32(s.S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+    };
+    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+    int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
+    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
+    auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge, see k_search_l1)
+        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
+    };
+
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileIdx ti(p, tile);
+        float P[16];
+        float2 acc[16];
+        for (int b = 0; b < p.K; b++) {
+            float2 x[16];
+#pragma unroll 1
+            for (int k2 = 0; k2 < 4; k2++) {
+                float2 *S1b = s.S1 + (it & 1) * kSub;
+                const float2 *Dk = S1b + t;
+                if (b == 0) {   // E from the staged run; park this thread's 16 values for the blocks to come
+                    const int r = (k2 - ti.dop) & 3;
+                    const int q = (k2 - ti.dop - r) >> 2;
+                    const float2 *Ek = s.E + ((p.Q + q) & 1) + t;
+                    mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+                    for (int a = 0; a < 16; a++) x[a] = Ek[256 * a];
+                    tmem_st16(e_taddr + 32 * k2, x);
+                    tmem_wait_st();
+                } else {
+                    tmem_ld16(e_taddr + 32 * k2, x);
+                    mbar_wait(bar, (uint32_t)(it & 1));
+                    tmem_wait_ld();
+                }
+                // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471)
+#pragma unroll
+                for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], x[a]);
+                subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, BaseFromGlobal{bases}, [&]() {
+                    if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                        if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
+                        else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
+                        else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
+                    }
+                });
+                it++;
+                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush();
+                if (k2 == 0) {
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
+                } else {
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
+                }
+            }
+            // block b was delayed by 16*b samples in the front end (k_front_end), so lag n lines up across blocks
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
+        }
+        warp_reduce_peak(thread_peak_l1(P, t), red_f + 16 * par, red_i + 8 * par, t);
+        pend_cap = ti.cap;
+        pend_slot = ti.slot;
+        pend_d = ti.d;
+        par ^= 1;
+    }
+    __syncthreads();
+    if (t == 0 && pend_cap >= 0) flush();
+    search_cta_epilogue(p, t);
+    ACQ_TRACE_STAMP(kTrSearchL1, 2);
+    tmem_free_cta<2 * kTwCols>(tmem_base, t);
+}
+
 // Tensor memory (TMEM, 256 KB per SM) as thread-private scratch.  The E1B combine needs the outputs of three
 // residues parked while the fourth is computed: 48 complex values per thread, 96 KiB per CTA.  In shared memory
 // that scratch limits the kernel to one CTA per SM and puts 96 extra loads/stores per thread and tile on the
@@ -897,7 +1032,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
 #pragma unroll
                 for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], Ek[256 * a]);
             }
-            subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, zaddr + kE1bBaseCol, [&]() {
+            subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, BaseFromTmem{zaddr + kE1bBaseCol}, [&]() {
                 if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
                     if (k2 < 3) issue(ti, k2 + 1, (it + 1) & 1);
                     else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, (it + 1) & 1);
@@ -1319,6 +1454,7 @@ cudaError_t search_kernels_configure()
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_multi_smem_bytes()))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
 #ifdef ACQ_VARIANT_L1_X3
     const int l1x = (int)search_l1_x3_smem();
@@ -1430,8 +1566,11 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 #elif defined(ACQ_VARIANT_L1_LDG)
     launch_k(a.K > 1 ? k_search_l1_ldg<true> : k_search_l1_ldg<false>, grid, 256, fft_smem3t_bytes() + 64 * sizeof(float), st,
              pdl, a);
-#else
+#elif defined(ACQ_VARIANT_L1_MULTI_TW)   // the K > 1 form that keeps the stage-B twiddles (not the code run) in tensor memory
     launch_k(a.K > 1 ? k_search_l1<true> : k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
+#else
+    if (a.K > 1) launch_k(k_search_l1_multi, grid, 256, l1_multi_smem_bytes(), st, pdl, a);
+    else launch_k(k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #endif
     return 1;
 }

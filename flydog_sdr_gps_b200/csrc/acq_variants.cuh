@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
 #pragma unroll 1
             for (int k2 = 0; k2 < 3; k2++) {
                 load_products(x, p, ti, b, k2, t);
-                subfft4096_inv4s(x, k2, bw, S1 + (it & 1) * kSub, t, T2, zaddr + kX3BaseCol, [] {});
+                subfft4096_inv4s(x, k2, bw, S1 + (it & 1) * kSub, t, T2, BaseFromTmem{zaddr + kX3BaseCol}, [] {});
                 it++;
                 if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
                 float2 z[16];
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
             }
             // last residue: the accumulation ends in the powers
             load_products(x, p, ti, b, 3, t);
-            subfft4096_inv4s(x, 3, bw, S1 + (it & 1) * kSub, t, T2, zaddr + kX3BaseCol, [] {});
+            subfft4096_inv4s(x, 3, bw, S1 + (it & 1) * kSub, t, T2, BaseFromTmem{zaddr + kX3BaseCol}, [] {});
             it++;
 #pragma unroll
             for (int h = 0; h < 2; h++) {

@@ -728,6 +728,26 @@ def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle):
         assert (ga[0] == ga[-1]).all()
 
 
+def test_code_resident_multi_kernel_equals_twiddle_resident_kernel(gpu_required, oracle):
+    """k_search_l1_multi (K > 1: the tile's code run parked in tensor memory after block 0, stage-B twiddles from a
+    shared-memory table) against k_search_l1<true> (twiddles in tensor memory, code run staged for every block; variant
+    library l1_multi_tw): the same arithmetic in the same order, so the whole per-Doppler table is bitwise equal --
+    K = 20 half-bins (cfg2), and K = 3 full bins over three captures with an asymmetric Doppler range."""
+    table = S.navstar()
+    cases = [(scenarios.params_kw("cfg2"), synth.make_capture(26, 20, table, scenarios.signals("cfg2", 6)), 1),
+             (dict(dop_lo=-7, dop_hi=30, k_noncoh=3, thr_l1=8.0), synth.make_capture(27, 3, table, scenarios.signals("cfg1", 7)), 3)]
+    for kw, cap, reps in cases:
+        out = {}
+        for kind, variant in (("code", None), ("tw", "l1_multi_tw")):
+            with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
+                out[kind] = eng.search(np.concatenate([cap] * reps), want_grid=True)
+        (ra, ga), (rb, gb) = out["code"], out["tw"]
+        for f in ("peak", "lag", "noise", "snr"):
+            assert np.array_equal(ga[f], gb[f]), f
+        assert ra.tobytes() == rb.tobytes()
+        assert (ga[0] == ga[-1]).all()
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_randomized_parameter_space(gpu_required, oracle, seed):
     """Seeded sweep over the parameter space the C ABI accepts -- Doppler range (symmetric or not), half-bins,
