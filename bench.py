@@ -155,7 +155,7 @@ def single_capture(cfg):
     from flydog_sdr_gps_b200 import scenarios, synth
     table = scenarios.table(cfg)
     kw = scenarios.params_kw(cfg)
-    return synth.make_capture(10_000 + int(cfg[3]), kw.get("k_noncoh", 1), table, scenarios.signals(cfg, int(cfg[3])))
+    return synth.make_capture(10_000 + int(cfg[3]) + len(cfg), kw.get("k_noncoh", 1), table, scenarios.signals(cfg, int(cfg[3])))
 
 
 # ------------------------------------------------------------------------------------------ CPU baselines
@@ -522,7 +522,7 @@ def main():
 
     # ================================================================= cfg1..cfg4
     entries = {}
-    todo = [] if args.no_configs else [c for c in ("cfg1", "cfg2", "cfg3", "cfg4") if not args.only or c in args.only.split(",")]
+    todo = [] if args.no_configs else [c for c in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg3_k4") if not args.only or c in args.only.split(",")]
     for cfg in todo:
         tb = scenarios.table(cfg)
         kw = scenarios.params_kw(cfg)
@@ -574,7 +574,7 @@ def main():
                 km.append(e.kernel_ms())
             T.barrier()
             e.set_profiling(False)
-        thr = kw.get("thr_l1", 16.0)
+        thr = kw.get("thr_e1b", 16.0) if cfg.startswith("cfg3") else kw.get("thr_l1", 16.0)
         ent.update({"value": cells_c / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "tiles_per_s": tiles_c / (ms * 1e-3),
                     "kernel_ms": {k: statistics.mean(x[k] for x in km) for k in km[0]},
                     "detected": int((nrec["snr"] >= thr).sum()), "window": win})

@@ -399,11 +399,9 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const bool fold = n_rows <= kFoldPickRowsMax;
     const long long tiles_l1 = (long long)n_captures * e->n_l1 * e->n_dop, tiles_e1b = (long long)n_captures * e->n_e1b * e->n_dop;
     // Cluster/DSMEM form of the E1B search when every tile can have a cluster of its own (one wave: 9 us per tile
-    // against 12.5 us for the one-CTA form, measured), when forced (variant builds), and always for non-coherent sums
-    // (its threads keep the block powers of their 16 lags in registers).  With more tiles than that the
-    // one-CTA-per-tile form has 2.9x the throughput (profiles/r1_e1b_cluster_ab.json).
-    const bool e1b_cluster =
-        K > 1 || ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && tiles_e1b <= e->sm_count / 4);
+    // against 12.5 us for the one-CTA form, measured) or when forced (variant builds).  With more tiles than that the
+    // one-CTA-per-tile forms (k_search_e1b, k_search_e1b_multi for non-coherent sums) have ~2.9x the throughput.
+    const bool e1b_cluster = ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && tiles_e1b <= e->sm_count / 4);
     a.ctas_done = e->d_ctas_done;
     a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, kSearchL1, e->sm_count) +
                                      search_grid_ctas(tiles_e1b, e1b_cluster ? kSearchE1bCluster : kSearchE1b, e->sm_count))

@@ -1131,6 +1131,192 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);
 }
 
+// k_search_e1b_multi -- Galileo E1B with k_noncoh > 1 on ONE CTA per tile (two per SM), replacing the cluster form for
+// non-coherent sums (which has 0.35x the throughput once there are more tiles than clusters).  A thread owns 64 lags
+// (16 values of n2 x 4 quarters m) whose block powers must survive from block to block: 64 floats on top of the 96
+// tensor-memory columns the three parked residues occupy.  They do not fit the thread's 128 columns, so the powers of
+// n2 >= 8 live in the 32 columns that remain and those of n2 < 8 in a thread-private 32 KiB shared-memory array that
+// takes the place of the code-run staging buffer; the code operand E comes straight from L2 instead (16 loads per
+// thread and sub-FFT, issued before the wait for the capture residue D, which is still TMA-staged one sub-FFT ahead),
+// and the stage-A bases from the 8 KiB global table.  Block b was delayed by 16 b samples in the front end, so lag n
+// lines up across blocks exactly as in k_search_l1_multi.  Same 106 KiB of shared memory as k_search_e1b.
+struct E1bMultiSmem {
+    float2 *S1;  // [2][4096]
+    float *Ps;   // [32][256] block powers of this thread's lags with n2 < 8: index 4 n2 + m
+    unsigned long long *bar;
+    float2 *T2;  // [4][15][16]
+    float *red_f;
+    int *red_i;
+};
+__host__ __device__ constexpr size_t e1b_multi_smem_bytes()
+{
+    return sizeof(float2) * (size_t)(2 * kSub) + sizeof(float) * 32 * 256 + 16 + sizeof(float2) * kT2Elems + 64 * sizeof(float);
+}
+constexpr int kE1bPowCol = 96;  // TMEM columns [96, 128): block powers of the lags with n2 >= 8, index 4 (n2 - 8) + m
+
+__global__ void __launch_bounds__(256, 2) k_search_e1b_multi(const SearchArgs p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    E1bMultiSmem s;
+    s.S1 = reinterpret_cast<float2 *>(smem);
+    s.Ps = reinterpret_cast<float *>(s.S1 + 2 * kSub);
+    s.bar = reinterpret_cast<unsigned long long *>(s.Ps + 32 * 256);
+    s.T2 = reinterpret_cast<float2 *>(s.bar + 2);
+    s.red_f = reinterpret_cast<float *>(s.T2 + kT2Elems);
+    s.red_i = reinterpret_cast<int *>(s.red_f + 32);
+    float *red_f = s.red_f;
+    int *red_i = s.red_i;
+    const int t = threadIdx.x;
+    constexpr int L = ACQ_LAGS_E1B;
+    ACQ_TRACE_STAMP(kTrSearchE1b, 0);
+    const uint32_t tmem_base = tmem_alloc_cta<kE1bTmemCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
+    {   // stage-B twiddle table into shared memory
+        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
+        float4 *dst = reinterpret_cast<float4 *>(s.T2);
+        for (int i = t; i < kT2Elems / 2; i += 256) dst[i] = __ldg(src + i);
+    }
+    const uint32_t zaddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * 128);
+    const float2 *bases = p.tables + kT2Elems + t;
+    float2 bw = __ldg(bases);
+    float *Pt = s.Ps + t;
+    const uint32_t bar = smem_u32(s.bar);
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (p.wait_prior) pdl_wait();
+    ACQ_TRACE_STAMP(kTrSearchE1b, 1);
+    pdl_trigger_search();
+    auto issue = [&](const TileIdx &tn, int bn, int k2n, int half) {  // thread 0: stage the capture residue of sub-FFT (tn, bn, k2n)
+        const float2 *Dk = p.Dp + d_row(p, tn, bn) * kN + k2n * kSub;
+        fence_proxy_async();
+        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * kSub));
+        tma_load_1d(smem_u32(s.S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+    };
+    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+    int it = 0;
+    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
+    auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge)
+        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
+    };
+    const int lag0 = lag_of3(t, 0);
+
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileIdx ti(p, tile);
+        float bp[4] = {0.0f, 0.0f, 0.0f, 0.0f}, bsum = 0.0f;   // last block: running maximum per quarter, sum
+        int bn2[4] = {0, 0, 0, 0};
+        for (int b = 0; b < p.K; b++) {
+            float2 x[16];
+#pragma unroll 1
+            for (int k2 = 0; k2 < 4; k2++) {
+                float2 *S1b = s.S1 + (it & 1) * kSub;
+                {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471); E straight from L2
+                    const int r = (k2 - ti.dop) & 3;
+                    const int q = (k2 - ti.dop - r) >> 2;
+                    const float2 *Eg = p.Ep + (size_t)(ti.sat * 4 + r) * p.ext_len + p.Q + q + t;
+                    const float2 *Dk = S1b + t;
+#pragma unroll
+                    for (int a = 0; a < 16; a++) x[a] = __ldg(Eg + 256 * a);
+                    mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+                    for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], x[a]);
+                }
+                subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, BaseFromGlobal{bases}, [&]() {
+                    if (t == 0) {
+                        if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
+                        else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
+                        else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
+                    }
+                });
+                it++;
+                if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush();  // previous tile's peak
+                if (k2 < 3) {
+                    float2 z[16];
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) z[n2] = (k2 == 0) ? x[r16(n2)] : cmul(x[r16(n2)], c_cC[k2][n2]);
+                    tmem_st16(zaddr + 32 * k2, z);
+                    tmem_wait_st();
+                }
+            }
+            // radix-4 combine over k2 for this block, power, accumulation over blocks; on the last block the peak
+            const bool first = (b == 0), last = (b + 1 == p.K);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) {
+                float2 za[4], zb[4], zc[4];
+                tmem_ld4(zaddr + 0 * 32 + 8 * c4, za);
+                tmem_ld4(zaddr + 1 * 32 + 8 * c4, zb);
+                tmem_ld4(zaddr + 2 * 32 + 8 * c4, zc);
+                float2 ph[8];   // previous sums of this quarter's 16 lags (index 4 i + m), as pairs
+                if (!first) {
+                    if (c4 >= 2) tmem_ld8(zaddr + kE1bPowCol + 16 * (c4 - 2), ph);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) ph[j] = make_float2(Pt[(16 * c4 + 2 * j) * 256], Pt[(16 * c4 + 2 * j + 1) * 256]);
+                    }
+                }
+                tmem_wait_ld();
+                float pw[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int n2 = 4 * c4 + i;
+                    float2 z0 = za[i], z1 = zb[i], z2 = zc[i];
+                    float2 z3 = cmul(x[r16(n2)], c_cC[3][n2]);
+                    radix4_inv(z0, z1, z2, z3);  // z_m = sum_k2 z_k2 * j^{k2*m}
+                    const float2 zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        const int idx = 4 * i + m;
+                        const float prev = first ? 0.0f : ((idx & 1) ? ph[idx >> 1].y : ph[idx >> 1].x);
+                        pw[idx] = first ? cpower(zz[m]) : prev + cpower(zz[m]);
+                    }
+                }
+                if (!last) {
+                    if (c4 >= 2) {
+                        float2 ps[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) ps[j] = make_float2(pw[2 * j], pw[2 * j + 1]);
+                        tmem_st8(zaddr + kE1bPowCol + 16 * (c4 - 2), ps);
+                        tmem_wait_st();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) Pt[(16 * c4 + j) * 256] = pw[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int n2 = 4 * c4 + i;
+#pragma unroll
+                        for (int m = 0; m < 4; m++) {
+                            // only the last 16 lags of the transform (m = 3, n2 = 15, t & 15 == 15) lie beyond L = 16368
+                            if (m < 3 || n2 < 15 || lag0 + 256 * 15 + 4096 * 3 < L) {
+                                if (pw[4 * i + m] > bp[m]) bp[m] = pw[4 * i + m], bn2[m] = n2;
+                                bsum += pw[4 * i + m];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // a thread's lags grow with n2 inside a quarter and with m across quarters: strict > in that order keeps the
+        // first maximum (search.cpp:488)
+        Peak best;
+        best.p = 0.0f;
+        best.n = 0x7fffffff;
+        best.sum = bsum;
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+            if (bp[m] > best.p) best.p = bp[m], best.n = lag0 + 256 * bn2[m] + 4096 * m;
+        warp_reduce_peak(best, red_f + 16 * par, red_i + 8 * par, t);
+        pend_cap = ti.cap;
+        pend_slot = ti.slot;
+        pend_d = ti.d;
+        par ^= 1;
+    }
+    __syncthreads();
+    if (t == 0 && pend_cap >= 0) flush();
+    search_cta_epilogue(p, t);
+    ACQ_TRACE_STAMP(kTrSearchE1b, 2);
+    tmem_free_cta<kE1bTmemCols>(tmem_base, t);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3-5, cluster form of the E1B search: one tile per thread-block CLUSTER of four CTAs.  CTA rank k2 runs the
 // 4096-point sub-FFT of input residue k2 (all four in parallel on four SMs) and publishes its twiddled output
@@ -1456,6 +1642,7 @@ cudaError_t search_kernels_configure()
     if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_multi_smem_bytes()))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_e1b_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e1b_multi_smem_bytes()))) return e;
 #ifdef ACQ_VARIANT_L1_X3
     const int l1x = (int)search_l1_x3_smem();
     if ((e = cudaFuncSetAttribute(k_search_l1_x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1x))) return e;
@@ -1557,7 +1744,8 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 #ifdef ACQ_VARIANT_E1B_LDG
         launch_k(k_search_e1b_ldg, grid, 256, fft_smem3_bytes() + 64 * sizeof(float), st, pdl, a);
 #else
-        launch_k(k_search_e1b, grid, 256, search_e1b_smem_bytes(), st, pdl, a);
+        if (a.K > 1) launch_k(k_search_e1b_multi, grid, 256, e1b_multi_smem_bytes(), st, pdl, a);
+        else launch_k(k_search_e1b, grid, 256, search_e1b_smem_bytes(), st, pdl, a);
 #endif
         return 1;
     }

@@ -13,6 +13,8 @@ CONFIGS = {
     "cfg3": "Galileo E1B: 50 PRNs, +-10 kHz full bins (81 bins), 16368 lags",
     "cfg4": "GPS+Galileo: 82 PRNs (32 C/A + 50 E1B), reference Doppler span, one capture",
     "cfg5": "receiver farm: 1024 independent captures x 32 GPS PRNs, reference Doppler span",
+    # not a BASELINE configuration: the Galileo search of cfg3 with non-coherent sums
+    "cfg3_k4": "Galileo E1B, 50 PRNs, 81 bins, K=4 non-coherent blocks (extension; one-CTA k_search_e1b_multi)",
 }
 
 
@@ -25,7 +27,7 @@ E1B_NEAR_THRESHOLD_SEED = 61133
 def table(cfg):
     if cfg in ("cfg1", "cfg2", "cfg5"):
         return S.navstar()
-    if cfg == "cfg3":
+    if cfg in ("cfg3", "cfg3_k4"):
         return S.e1b(range(1, 51))
     if cfg == "cfg4":
         return S.all_constellation_table()
@@ -39,6 +41,8 @@ def params_kw(cfg):
         return dict(dop_lo=-80, dop_hi=80, half_bin=1, k_noncoh=20, thr_l1=2.6)
     if cfg == "cfg3":
         return dict(dop_lo=-40, dop_hi=40)
+    if cfg == "cfg3_k4":
+        return dict(dop_lo=-40, dop_hi=40, k_noncoh=4, thr_e1b=6.0)
     return {}
 
 
@@ -62,7 +66,7 @@ def signals(cfg, seed):
         prns = rng.choice(32, 8, replace=False)
         return [(int(sat), int(rng.integers(0, 16368)), float(rng.uniform(-9500, 9500)), float(rng.uniform(30, 35)),
                  float(rng.uniform(0, 2 * np.pi))) for sat in prns]
-    if cfg == "cfg3":
+    if cfg in ("cfg3", "cfg3_k4"):
         prns = rng.choice(50, 6, replace=False)
         return [(int(sat), int(rng.integers(0, 65472)), float(rng.integers(-38, 39)) * BIN_HZ, float(rng.uniform(43, 48)),
                  float(rng.uniform(0, 2 * np.pi))) for sat in prns]

@@ -497,6 +497,28 @@ def test_e1b_noncoherent_blocks(gpu_required, oracle):
     assert {int(r["sat"]) for r in rec[0] if r["snr"] >= kw["thr_e1b"]} >= {2, 6}
 
 
+def test_e1b_one_cta_multi_kernel_equals_cluster_kernel(gpu_required, oracle):
+    """k_search_e1b_multi (K > 1 on one CTA per tile: block powers split between tensor memory and a shared-memory
+    array, code operand straight from L2) against the cluster/DSMEM form with K > 1 (variant library e1b_cluster): same
+    sub-FFTs, combine and block order, so peaks and lags are bitwise equal; only the order of the noise sum differs.
+    More tiles than resident CTAs; both against the oracle."""
+    table = scenarios.table("cfg3")[:16]
+    kw = dict(dop_lo=-20, dop_hi=20, k_noncoh=3, thr_e1b=7.0)
+    cap = synth.make_capture(39, 3, table, [(1, 30000, -6 * F.BIN_HZ, 42, 0.4), (7, 1000, 17 * F.BIN_HZ, 41, 1.4),
+                                            (12, 65000, 0.0, 40, 2.4)])
+    out = {}
+    for kind, variant in (("cta", None), ("cluster", "e1b_cluster")):
+        with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
+            out[kind] = eng.search(cap, want_grid=True)
+    (ra, ga), (rb, gb) = out["cta"], out["cluster"]
+    assert np.array_equal(ga["peak"], gb["peak"]) and np.array_equal(ga["lag"], gb["lag"])
+    np.testing.assert_allclose(ga["noise"], gb["noise"], rtol=2e-6)
+    assert np.array_equal(ra["lag"], rb["lag"]) and np.array_equal(ra["dop"], rb["dop"])
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(**kw), want_grid=True)
+    compare_records(ra[0], orec, ogrid, kw["dop_lo"], kw["thr_e1b"], ggrid=ga[0], max_ties=1)
+    assert {int(r["sat"]) for r in ra[0] if r["snr"] >= kw["thr_e1b"]} >= {1, 7, 12}
+
+
 def test_dropin_with_capture_file_source(gpu_required, golden_search, tmp_path):
     """GPS_SAMPLES_FROM_FILE path (gps/search.cpp:361-380): the shim's capture callback fed from a raw capture
     file gives the same detections as the golden per-capture answers, and the file's end stops the pass."""
