@@ -56,7 +56,8 @@ def build(force=False, verbose=False, defines=(), out=None):
 VARIANTS = {
     "l1_multi_tw": ["ACQ_VARIANT_L1_MULTI_TW"],  # K > 1 C/A search with the twiddles (not the code run) in tensor memory
     "l1_ldg": ["ACQ_VARIANT_L1_LDG"],        # C/A search, operands straight from L2
-    "l1_x3": ["ACQ_VARIANT_L1_X3"],          # C/A search at three CTAs per SM (accumulators in tensor memory)
+    "l1_x3": ["ACQ_VARIANT_L1_X3"],
+    "l1_x3t": ["ACQ_VARIANT_L1_X3", "ACQ_X3_TMA_D"],  # ... with the capture residue TMA-staged, the code run from L2 issued early          # C/A search at three CTAs per SM (accumulators in tensor memory)
     "e1b_ldg": ["ACQ_VARIANT_E1B_LDG", "ACQ_FORCE_E1B_KERNEL=1"],  # one-CTA E1B search, operands straight from L2
     "e1b_cta": ["ACQ_FORCE_E1B_KERNEL=1"],   # always the one-CTA E1B form
     "e1b_cluster": ["ACQ_FORCE_E1B_KERNEL=2"],  # always the cluster/DSMEM E1B form

@@ -721,8 +721,13 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
 #endif
         fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
+#ifdef ACQ_K1_E_LDG   // experiment: the code run straight from L2 (issued before the wait for D), only D staged
+        (void)Ek;
+        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * kSub));
+#else
         mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
         tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+#endif
         tma_load_1d(smem_u32(s.S1 + half * kS1pElems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
     };
     if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
@@ -749,10 +754,19 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                     const int r = (k2 - ti.dop) & 3;
                     const int q = (k2 - ti.dop - r) >> 2;
                     const float2 *Dk = S1b + t;
+#ifdef ACQ_K1_E_LDG
+                    const float2 *Eg = p.Ep + (size_t)(ti.sat * 4 + r) * p.ext_len + p.Q + q + t;
+#pragma unroll
+                    for (int a = 0; a < 16; a++) x[a] = __ldg(Eg + 256 * a);
+                    mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+                    for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], x[a]);
+#else
                     const float2 *Ek = s.E + ((p.Q + q) & 1) + t;
                     mbar_wait(bar, (uint32_t)(it & 1));
 #pragma unroll
                     for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
+#endif
                 }
                 subfft4096_inv4<true>(x, k2, bw, S1b, t, tw_taddr, [&]() {
                     if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one

@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
 #pragma unroll
     for (int k2 = 1; k2 < 4; k2++) tmem_st1(zaddr + kX3BaseCol + 2 * k2, __ldg(p.tables + kT2Elems + k2 * 256 + t));
     tmem_wait_st();
+#ifdef ACQ_X3_TMA_D   // capture residue D staged by TMA one sub-FFT ahead (idle half of S1), code run E from L2 issued before the wait
+    const uint32_t bar = smem_u32(red_f + 50);
+    if (t == 0) mbar_init(bar, 1);
+#endif
     __syncthreads();
     if (p.wait_prior) pdl_wait();
     pdl_trigger_search();  // after the wait (see k_search_l1)
@@ -131,16 +135,47 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
     auto flush = [&](int q) {   // thread 0
         store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * q, red_i + 8 * q), L);
     };
+#ifdef ACQ_X3_TMA_D
+    auto issue = [&](const TileIdx &tn, int bn, int k2n, int half) {
+        const float2 *Dk = p.Dp + d_row(p, tn, bn) * kN + k2n * kSub;
+        fence_proxy_async();
+        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * kSub));
+        tma_load_1d(smem_u32(S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+    };
+    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+#endif
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileIdx ti(p, tile);
         float pw[16];
+#ifdef ACQ_X3_TMA_D
+        auto products = [&](float2 (&x)[16], int b, int k2) {
+            const int r = (k2 - ti.dop) & 3;
+            const int q = (k2 - ti.dop - r) >> 2;
+            const float2 *Eg = p.Ep + (size_t)(ti.sat * 4 + r) * p.ext_len + p.Q + q + t;
+            const float2 *Dk = S1 + (it & 1) * kSub + t;
+#pragma unroll
+            for (int a = 0; a < 16; a++) x[a] = __ldg(Eg + 256 * a);
+            mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+            for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], x[a]);
+        };
+        auto next = [&](int b, int k2) {   // thread 0, right after the CTA barrier of sub-FFT (b, k2)
+            if (t != 0) return;
+            if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
+            else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
+            else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
+        };
+#else
+        auto products = [&](float2 (&x)[16], int b, int k2) { load_products(x, p, ti, b, k2, t); };
+        auto next = [&](int, int) {};
+#endif
         for (int b = 0; b < p.K; b++) {
             float2 x[16];
 #pragma unroll 1
             for (int k2 = 0; k2 < 3; k2++) {
-                load_products(x, p, ti, b, k2, t);
-                subfft4096_inv4s(x, k2, bw, S1 + (it & 1) * kSub, t, T2, BaseFromTmem{zaddr + kX3BaseCol}, [] {});
+                products(x, b, k2);
+                subfft4096_inv4s(x, k2, bw, S1 + (it & 1) * kSub, t, T2, BaseFromTmem{zaddr + kX3BaseCol}, [&] { next(b, k2); });
                 it++;
                 if (t == 0 && b == 0 && k2 == 0 && pend_cap >= 0) flush(par ^ 1);  // previous tile's peak
                 float2 z[16];
@@ -161,8 +196,8 @@ __global__ void __launch_bounds__(256, 3) k_search_l1_x3(const SearchArgs p)
                 tmem_wait_st();
             }
             // last residue: the accumulation ends in the powers
-            load_products(x, p, ti, b, 3, t);
-            subfft4096_inv4s(x, 3, bw, S1 + (it & 1) * kSub, t, T2, BaseFromTmem{zaddr + kX3BaseCol}, [] {});
+            products(x, b, 3);
+            subfft4096_inv4s(x, 3, bw, S1 + (it & 1) * kSub, t, T2, BaseFromTmem{zaddr + kX3BaseCol}, [&] { next(b, 3); });
             it++;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
