@@ -56,11 +56,12 @@ struct HbAcc {
 // search.cpp:386,422-423); I = bit ^ {1,1,0,0}[i&3], Q = bit ^ {1,0,0,1}[i&3]; value = bit ? -1 : +1
 // (search.cpp:62-66,172-175).  Past the end of the block both stages see zeros (search.cpp:145).
 // Second stage as k_hb2 (optional half-bin variant, block delay for non-coherent sums).
-// Chunk size: 1024 (16 CTAs per block).  Smaller chunks shorten the kernel itself for a single capture (10.8 -> 8.6 us
-// at 256 or 512) but the whole cold-start search got slower (76.9 -> 79.1 / 81.1 us, A/B on one box): the
-// programmatic-dependent-launch chain behind it starts later, so the product keeps 1024.
+// Chunk size: 256 samples of x2 per CTA (64 CTAs per block).  Measured on one cold-start search with the trace variant
+// (round 2, after the first stage went bit-parallel): the front end's last CTA exits at 3.9 us with 1024-sample
+// chunks, 2.4 us with 512, 1.6 us with 256, and the whole search ends 3 us earlier; the 30-sample window overlap costs
+// 6 % more first-stage work, nothing against a step of a batched search (front end < 1 % there).
 #ifndef ACQ_FE_OUT
-#define ACQ_FE_OUT 1024
+#define ACQ_FE_OUT 256
 #endif
 constexpr int kFeOut = ACQ_FE_OUT;             // x2 samples per CTA (a power of two, 256..1024)
 constexpr int kFeX1 = 2 * kFeOut + 30;         // x1 samples needed (2078 for 1024)
@@ -120,6 +121,30 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
     const int i_base = 4 * kFeOut * chunk;  // first capture sample of this chunk (= bit 0 of sbits)
     for (int m = t; m < kFeX1; m += 256) {
         const int r0 = 2 * m;  // chunk-relative sample index of the first tap
+        if (!MAG && i_base + r0 + 30 < ACQ_NSAMPLES) {
+            // Sign-only samples, window inside the block (all but the last 15 outputs of a block): the 31 bits under the
+            // taps come from two 32-bit shared loads and a funnel shift; XORing them with the fs/4 LO patterns of the
+            // window's phase (I: {1,1,0,0}, Q: {1,0,0,1} per sample, search.cpp:383-384; the window starts at phase 0
+            // or 2) leaves each tap's sign in one bit.  A tap product (+-1) * c is exactly +-c, so it is the tap with
+            // its sign bit flipped -- the same value __fmul_rn gives -- added in the reference's order with __fadd_rn.
+            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(sbits);
+            const uint32_t win = __funnelshift_r(w32[r0 >> 5], w32[(r0 >> 5) + 1], r0 & 31);
+            const bool ph2 = (r0 & 2) != 0;
+            const uint32_t sI = win ^ (ph2 ? 0xCCCCCCCCu : 0x33333333u), sQ = win ^ (ph2 ? 0x66666666u : 0x99999999u);
+            auto term = [](uint32_t sgn, int j, float c) {
+                return __int_as_float(__float_as_int(c) ^ (int)((sgn << (31 - j)) & 0x80000000u));
+            };
+            float re = term(sI, 0, c_hb[0]), im = term(sQ, 0, c_hb[0]);
+#pragma unroll
+            for (int j = 2; j <= 30; j += 2) {
+                re = __fadd_rn(re, term(sI, j, c_hb[j / 2]));
+                im = __fadd_rn(im, term(sQ, j, c_hb[j / 2]));
+            }
+            re = __fadd_rn(re, term(sI, 15, c_hb[16]));
+            im = __fadd_rn(im, term(sQ, 15, c_hb[16]));
+            x1s[m] = (2 * kFeOut * chunk + m < 32768) ? make_float2(re, im) : make_float2(0.0f, 0.0f);
+            continue;
+        }
         unsigned long long win = 0;
 #pragma unroll
         for (int k = 0; k < 5; k++) win |= (unsigned long long)sbits[(r0 >> 3) + k] << (8 * k);
@@ -1653,7 +1678,9 @@ cudaError_t search_kernels_configure()
     cudaError_t e;
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+#ifdef ACQ_VARIANT_L1_MULTI_TW
     if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+#endif
     if ((e = cudaFuncSetAttribute(k_search_l1_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_multi_smem_bytes()))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e1b_multi_smem_bytes()))) return e;

@@ -284,6 +284,28 @@ def test_selection_order_repeats_and_qzss(ref_engine, oracle):
     assert one[0].tobytes() == rec[2].tobytes()
 
 
+def test_sbas_rows_are_zero_like_the_reference(gpu_required, oracle):
+    """An SBAS row gets no replica (search.cpp:244): zero spectrum, record {lag 0, dop 0, snr 0}, and the row before it
+    reads zeros at negative Doppler in the reference's wrap mode.  Engine against the oracle, whole per-Doppler table."""
+    nav = S.navstar()
+    table = nav[:3] + [(120, 145, 0o1106, S.SBAS)] + nav[3:6]
+    cap = synth.make_capture(5, 1, nav, scenarios.signals("cfg1", 5))
+    with F.AcqEngine(table) as eng:
+        assert not eng.code_spectrum(3).any()
+        rec, grid = eng.search(cap, want_grid=True)
+    orec, ogrid = oracle.search(cap, table, want_grid=True)
+    # reference wrap: the zero row reads the next row's first bins at negative Doppler (search.cpp:471): cells at
+    # dop >= 0 are 0/0 -> NaN in both, the others small and equal to the oracle's
+    assert np.array_equal(grid[0][3]["peak"], ogrid[3]["peak"]) or np.allclose(grid[0][3]["peak"], ogrid[3]["peak"], rtol=RTOL)
+    assert (grid[0][3]["peak"][20:] == 0).all() and rec[0][3]["snr"] < 8
+    assert (rec[0][3]["dop"], rec[0][3]["lag"]) == (orec[3]["dop"], orec[3]["lag"])
+    keep = np.array([0, 1, 2, 4, 5, 6])
+    compare_records(rec[0][keep], orec[keep], ogrid[keep], -20, 16.0, ggrid=grid[0][keep], max_ties=1)
+    with F.AcqEngine(table, F.default_params(wrap_mode=F.WRAP_CIRCULAR)) as eng:
+        r = eng.search(cap)[0][3]
+    assert (r["sat"], r["lag"], r["dop"], r["peak"], r["noise"], r["snr"]) == (3, 0, 0, 0, 0, 0)
+
+
 def test_degenerate_captures(nav_engine, oracle):
     """All-zero and all-one bit captures (a dead front end) follow the reference arithmetic too."""
     table = S.navstar()

@@ -436,3 +436,27 @@ def test_all_50_e1b_codes_against_reference_goldens(oracle):
     if oracle.ref50() is not None:   # live check where the reference build exists
         dop, lag, snr = oracle.ref50_search(g["capture"], np.arange(50, dtype=np.int32))
         assert np.array_equal(dop, g["dop"]) and np.array_equal(lag, g["lag"]) and np.array_equal(snr, g["snr"])
+
+
+def test_sbas_rows_keep_the_reference_all_zero_spectrum(oracle):
+    """SearchInit builds replicas for Navstar / QZSS rows (search.cpp:244) and E1B rows (:306) only: an SBAS row of the
+    table keeps the all-zero code[] row of the reference's static array, so Correlate() can never detect it (snr = 0/0
+    fails `snr > max_snr`) -- and, in the reference's wrap mode, the satellite BEFORE it reads zeros instead of a next
+    row at negative Doppler."""
+    from flydog_sdr_gps_b200 import sats as S, scenarios, synth
+    nav = S.navstar()
+    table = nav[:3] + [(120, 145, 0o1106, S.SBAS)] + nav[3:5]
+    assert not oracle.code_spectrum(table[3]).any()
+    cap = synth.make_capture(5, 1, nav, scenarios.signals("cfg1", 5))
+    rec, grid = oracle.search(cap, table, want_grid=True)
+    # reference wrap: at negative Doppler the zero row still reads the first |dop| bins of the NEXT row (search.cpp:471),
+    # so its cells are not all zero there -- but it has no peak of its own and stays far below the threshold
+    assert (grid[3]["peak"][20:] == 0).all() and rec[3]["snr"] < 8
+    circ = oracle.search(cap, table, params=oracle.default_params(wrap_mode=oracle.WRAP_CIRCULAR))
+    assert circ[3]["snr"] == 0 and circ[3]["lag"] == 0 and circ[3]["dop"] == 0 and circ[3]["peak"] == 0
+    # the row before the SBAS row sees zeros past its end at negative Doppler: same as being last in the table
+    alone = oracle.search(cap, nav[:3], want_grid=True)[1]
+    assert np.array_equal(grid[2]["snr"], alone[2]["snr"])
+    # and it differs from what it would read if a real spectrum followed
+    follow = oracle.search(cap, nav[:5], want_grid=True)[1]
+    assert not np.array_equal(grid[2]["snr"][:20], follow[2]["snr"][:20])

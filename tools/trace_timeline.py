@@ -13,7 +13,8 @@ import flydog_sdr_gps_b200 as F
 from flydog_sdr_gps_b200 import _lib, scenarios, synth
 
 NAMES = ["front_end", "fwd_fft", "search_l1", "search_e1b", "pick", "e1b_cluster"]
-L = _lib.load_variant("trace")
+VARIANT = os.environ.get("TRACE_VARIANT", "trace")
+L = _lib.load_variant(VARIANT)
 L.acq_trace_read.argtypes = [C.c_void_p, C.c_int]
 total = L.acq_trace_read(None, 0)
 buf = np.zeros(total, np.uint64)
@@ -22,7 +23,7 @@ for cfg in sys.argv[1:] or ["cfg1"]:
     table = scenarios.table(cfg)
     kw = scenarios.params_kw(cfg)
     cap = synth.make_capture(1, kw.get("k_noncoh", 1), table, scenarios.signals(cfg, 1))
-    with F.AcqEngine(table, F.default_params(**kw), variant="trace") as eng:
+    with F.AcqEngine(table, F.default_params(**kw), variant=VARIANT) as eng:
         import time
         for _ in range(20):
             eng.search(cap)
