@@ -215,8 +215,9 @@ def fftw_probe():
             "note": "rows are search.cpp + in-repo fp32 FFT (FFTW unavailable)"}
 
 
-def cpu_baseline_rows(cells_per_sat=41 * 4092):
-    """BASELINE.md section 3 on this box's host cores, bounded sample of the cfg5 captures (identical bytes)."""
+def cpu_baseline_rows(cells_per_sat=41 * 4092, target_s=4.0):
+    """BASELINE.md section 3 on this box's host cores, bounded samples of the cfg5 captures (identical bytes as the GPU
+    arm's generator family): each row is sized from a short probe to about `target_s` seconds of wall time."""
     from oracle import oracle_py as O
     from flydog_sdr_gps_b200 import scenarios
     cores = os.cpu_count() or 1
@@ -224,28 +225,33 @@ def cpu_baseline_rows(cells_per_sat=41 * 4092):
     out = {"fftw": fftw_probe(), "rows": {}}
     O.build(ref=False)
     caps = farm_captures_numpy(range(max(2, cores)))
+    sats32 = list(range(32))
     if O.have_ref():
         lit1 = LiteralReference(caps, 1)
         lit1.run([(0, [0])])  # page-in
-        n1 = 16
-        dt = lit1.run([(0, list(range(n1)))])
+        probe = lit1.run([(0, sats32[:8])]) / 8                       # seconds per satellite on one core
+        n1 = max(1, min(64, int(target_s / (32 * probe))))            # whole captures
+        dt = lit1.run([(c % len(caps), sats32) for c in range(n1)])
         out["rows"]["B1_literal_search_cpp_1core"] = {
-            "value": n1 * cells_per_sat / dt, "unit": UNIT, "cores": 1, "ms_per_sat": dt / n1 * 1e3,
-            "sample": "%d Navstar PRNs of one cfg5 capture, Sample()+Correlate() per sat (%.2f s)" % (n1, dt)}
+            "value": n1 * 32 * cells_per_sat / dt, "unit": UNIT, "cores": 1, "ms_per_sat": dt / (n1 * 32) * 1e3,
+            "sample": "%d cfg5 captures x 32 Navstar PRNs, Sample()+Correlate() per sat, serial (%.2f s)" % (n1, dt)}
         lit = LiteralReference(caps, cores)
         lit.run([(p, [0]) for p in range(cores)])
-        per = 16
-        dt = lit.run([(p, list(range(per))) for p in range(cores)] * 2)
+        per = max(1, min(64, int(target_s / (32 * probe))))           # captures per process
+        dt = lit.run([(p, sats32) for p in range(cores)] * per)
         out["rows"]["B2_literal_search_cpp_all_cores"] = {
-            "value": 2 * cores * per * cells_per_sat / dt, "unit": UNIT, "cores": cores,
-            "sample": "%d processes x 2 x %d PRNs, one cfg5 capture each (%.2f s)" % (cores, per, dt)}
+            "value": per * cores * 32 * cells_per_sat / dt, "unit": UNIT, "cores": cores,
+            "sample": "%d processes x %d cfg5 captures x 32 PRNs (%.2f s)" % (cores, per, dt)}
         lit.close()
     prm = O.default_params()
     O.search(caps[0], table, sel=np.arange(1, dtype=np.int32), params=prm, nthreads=1)
-    reps = 2
+    t0 = time.perf_counter()
+    O.search(caps[0], table, params=prm, nthreads=cores)
+    probe = time.perf_counter() - t0
+    reps = max(2, min(256, int(target_s / probe)))
     t0 = time.perf_counter()
     for r in range(reps):
-        O.search(caps[r], table, params=prm, nthreads=cores)
+        O.search(caps[r % len(caps)], table, params=prm, nthreads=cores)
     dt = time.perf_counter() - t0
     out["rows"]["port_oracle_openmp_all_cores"] = {
         "value": reps * 32 * cells_per_sat / dt, "unit": UNIT, "cores": min(cores, 32),
@@ -278,14 +284,17 @@ def reference_arm(args):
     if O.have_ref():
         kind = "reference"
         lit = LiteralReference(caps, cores)
-        jobs = [(p, list(range(32))) for p in range(cores)]
-        sample = "each step: %d of the %d captures (one per core) x 32 PRNs x 41 bins, unmodified gps/search.cpp forked over %d processes" % (
-            cores, CAPTURES_TOTAL, cores)
+        one = [(p, list(range(32))) for p in range(cores)]
+        probe = lit.run(one)                                   # one capture per core
+        per = max(1, min(16, int(1.0 / max(probe, 1e-3))))     # captures per core and step: about a second per step
+        jobs = one * per
+        sample = "each step: %d of the %d captures (%d per core) x 32 PRNs x 41 bins, unmodified gps/search.cpp forked over %d processes" % (
+            per * cores, CAPTURES_TOTAL, per, cores)
         for _ in range(min(warm, 1)):
             lit.run(jobs)
         dts = [lit.run(jobs) for _ in range(steps)]
         lit.close()
-        n_caps_step = cores
+        n_caps_step = per * cores
     else:
         kind = "port"
         prm = O.default_params()
