@@ -486,7 +486,7 @@ __device__ __forceinline__ Peak block_reduce_peak(Peak v, float *red_f, int *red
 }
 
 struct TileIdx {
-    int sat, slot, cap, d, dop, v;
+    int sat, slot, cap, d, dop, v, wi;
     // The host keeps a launch below 2^31 tiles (launch_search), so the decomposition runs on 32-bit unsigned
     // divisions: every warp pays it once per tile, and a K = 1 tile is only four sub-FFTs long.
     __device__ __forceinline__ TileIdx(const SearchArgs &p, long long tile)
@@ -495,7 +495,23 @@ struct TileIdx {
         const unsigned cw = tl / nd;
         d = (int)(tl - cw * nd);
         cap = (int)(cw / nw);
-        const int2 wk = p.work[(int)(cw - (unsigned)cap * nw)];
+        wi = (int)(cw - (unsigned)cap * nw);
+        const int2 wk = p.work[wi];
+        sat = wk.x;
+        slot = wk.y;
+        set_dop(p);
+    }
+    // the tile `stride` further on, stride given as mixed-radix digits (sd, sw, sc) over (n_dop, n_work): no division
+    __device__ __forceinline__ void step(const SearchArgs &p, int sd, int sw, int sc)
+    {
+        d += sd;
+        int carry = d >= p.n_dop;
+        if (carry) d -= p.n_dop;
+        wi += sw + carry;
+        carry = wi >= p.n_work;
+        if (carry) wi -= p.n_work;
+        cap += sc + carry;
+        const int2 wk = p.work[wi];
         sat = wk.x;
         slot = wk.y;
         set_dop(p);
@@ -647,6 +663,24 @@ __device__ __forceinline__ void warp_reduce_peak(Peak v, float *slot_f, int *slo
     }
 }
 
+// The same with the maximum and its first index found by two warp-wide integer reductions (REDUX): powers are
+// non-negative floats, so their bit patterns order like unsigned integers; among the lanes that hold the maximum the
+// lowest lag wins (search.cpp:488).  The sum keeps the butterfly order of warp_reduce_peak: same bits.
+__device__ __forceinline__ void warp_reduce_peak_redux(Peak v, float *slot_f, int *slot_i, int t)
+{
+    const unsigned pbits = __float_as_uint(v.p);
+    const unsigned pmax = __reduce_max_sync(0xffffffffu, pbits);
+    const unsigned nmin = __reduce_min_sync(0xffffffffu, pbits == pmax ? (unsigned)v.n : 0xffffffffu);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v.sum += __shfl_xor_sync(0xffffffffu, v.sum, off);
+    const int w = t >> 5;
+    if ((t & 31) == 0) {
+        slot_f[w] = __uint_as_float(pmax);
+        slot_f[8 + w] = v.sum;
+        slot_i[w] = (int)nmin;
+    }
+}
+
 // Merge of the eight warp partials (one thread), after a CTA barrier that follows warp_reduce_peak.
 __device__ __forceinline__ Peak merge_warp_peaks(const float *slot_f, const int *slot_i)
 {
@@ -713,6 +747,9 @@ __device__ __forceinline__ Peak thread_peak_l1(const float (&pw)[16], int t)
 // CTA and hands the partial accumulators of a split tile over through L2 -- "stream-K" -- so that 1312 tiles do not
 // run as five rounds on 296 CTAs.  Bitwise-equal cells, but 78.6 -> 81.4 us per cold-start search and no change on
 // the receiver farm: the last round already runs one CTA per SM, which is 1.6x faster per tile than two.)
+#ifndef ACQ_L1_LEAN
+#define ACQ_L1_LEAN 1   // K = 1: tile indices advance without divisions, max / first index by REDUX (+0.3..1 % cfg5, -1.3 us cfg1; 0 = round-1 form)
+#endif
 template <bool MULTI>
 __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 {
@@ -765,8 +802,16 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
     };
 
+#if ACQ_L1_LEAN
+    // the launch stride gridDim.x as digits over (n_dop, n_work): tile indices advance without divisions
+    const int sd = (int)(gridDim.x % (unsigned)p.n_dop), sw = (int)((gridDim.x / (unsigned)p.n_dop) % (unsigned)p.n_work),
+              sc = (int)(gridDim.x / ((unsigned)p.n_dop * (unsigned)p.n_work));
+    TileIdx ti(p, blockIdx.x < p.n_tiles ? blockIdx.x : 0);
+#endif
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+#if !ACQ_L1_LEAN
         const TileIdx ti(p, tile);
+#endif
         float P[16];
         float2 acc[16];
         for (int b = 0; b < p.K; b++) {
@@ -797,7 +842,15 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                     if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
                         if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
                         else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
-                        else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
+                        else if (tile + gridDim.x < p.n_tiles) {
+#if ACQ_L1_LEAN
+                            TileIdx tn = ti;
+                            tn.step(p, sd, sw, sc);
+                            issue(tn, 0, 0, (it + 1) & 1);
+#else
+                            issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
+#endif
+                        }
                     }
                 });
                 it++;
@@ -814,11 +867,18 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 #pragma unroll
             for (int n2 = 0; n2 < 16; n2++) P[n2] = (!MULTI || b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
         }
+#if ACQ_L1_LEAN
+        warp_reduce_peak_redux(thread_peak_l1(P, t), red_f + 16 * par, red_i + 8 * par, t);
+#else
         warp_reduce_peak(thread_peak_l1(P, t), red_f + 16 * par, red_i + 8 * par, t);
+#endif
         pend_cap = ti.cap;
         pend_slot = ti.slot;
         pend_d = ti.d;
         par ^= 1;
+#if ACQ_L1_LEAN
+        ti.step(p, sd, sw, sc);
+#endif
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
