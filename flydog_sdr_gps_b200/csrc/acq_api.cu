@@ -373,7 +373,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     // Event records between the kernels (profiling) would serialise them anyway.
     const long long tiles_total = (long long)n_captures * e->n_slots * e->n_dop * K;
     const bool pdl = !prof && (ACQ_FORCE_PDL == 1 || (ACQ_FORCE_PDL < 0 && tiles_total <= 64LL * e->sm_count));
-    if (++e->epoch == 0) e->epoch = 1;
+    if (++e->epoch >= 0xfffffffeu) e->epoch = 1;
     if (prof) CU(cudaEventRecord(e->prof[0], st));
     e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
@@ -463,7 +463,9 @@ int poll_flag(acq_engine *e)
 {
     volatile unsigned *flag = e->h_flag;
     for (unsigned spins = 1;; spins++) {
-        if (*flag == e->epoch) return ACQ_OK;
+        const unsigned f = *flag;
+        if (f == e->epoch) return ACQ_OK;
+        if (f == 0xffffffffu) return fail(ACQ_ERR_CUDA, "search kernels did not complete (best-Doppler pick timed out)");
         if ((spins & 0x3ff) == 0) {
             const cudaError_t q = cudaStreamQuery(e->stream);
             if (q == cudaSuccess) return (*flag == e->epoch) ? ACQ_OK : fail(ACQ_ERR_CUDA, "search finished without its completion signal");

@@ -1536,9 +1536,24 @@ __global__ void __launch_bounds__(1024) k_pick_small(const acq_cell *cells, cons
     __shared__ __align__(16) acq_record s_rec[kPickSmallRowsMax];
     const int t = threadIdx.x;
     ACQ_TRACE_STAMP(kTrPick, 0);
+    __shared__ unsigned s_timed_out;
     if (t == 0) {
+        // Poll, but never hang the GPU: if the count does not arrive within 2 s (a search kernel that failed to run, a
+        // count left over by an aborted search) the pick goes ahead on what is there and announces the failure
+        // instead of the epoch; the counter is reset either way.
         const volatile unsigned *done = ctas_done;
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
+        s_timed_out = 0;
         while (*done != ctas_total) {
+            if ((++spins & 0x3fff) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > 2000000000ull) {
+                    s_timed_out = 1;
+                    break;
+                }
+            }
         }
         __threadfence();
     }
@@ -1564,7 +1579,7 @@ __global__ void __launch_bounds__(1024) k_pick_small(const acq_cell *cells, cons
     __syncthreads();
     if (t == 0) {
         *ctas_done = 0;
-        if (host_flag) *reinterpret_cast<volatile unsigned *>(host_flag) = epoch;
+        if (host_flag) *reinterpret_cast<volatile unsigned *>(host_flag) = s_timed_out ? 0xffffffffu : epoch;
     }
     ACQ_TRACE_STAMP(kTrPick, 2);
 }
