@@ -104,7 +104,7 @@ struct acq_engine {
     bool dev_pending = false;
     int64_t launches = 0;
     bool profiling = false, prof_valid = false;
-    cudaEvent_t prof[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t prof[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // persistent device data
     float2 *d_tables = nullptr, *d_rot = nullptr, *d_C = nullptr, *d_Ep = nullptr;
@@ -163,6 +163,10 @@ using namespace acq;
 //                            mapped pinned staging buffer (1: its bulk copies then cross PCIe, no copy node)
 #ifndef ACQ_ZC_INPUT
 #define ACQ_ZC_INPUT 0
+#endif
+//   ACQ_FE_PREFETCH=0        no L2 prefetch of the code rows behind the front end of a small search
+#ifndef ACQ_FE_PREFETCH
+#define ACQ_FE_PREFETCH 1
 #endif
 // Host path, small searches: the capture goes through an engine-owned pinned staging buffer (a pageable source would
 // make cudaMemcpyAsync synchronous), the kernels write the records straight into mapped pinned memory, and the host
@@ -375,7 +379,17 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const bool pdl = !prof && (ACQ_FORCE_PDL == 1 || (ACQ_FORCE_PDL < 0 && tiles_total <= 64LL * e->sm_count));
     if (++e->epoch >= 0xfffffffeu) e->epoch = 1;
     if (prof) CU(cudaEventRecord(e->prof[0], st));
-    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st);
+    // small searches: the code rows of the selected satellites are pulled into L2 while the front end runs (FePrefetch)
+    FePrefetch pf{};
+    if (ACQ_FE_PREFETCH && blocks <= 8 && e->n_slots <= 256) {
+        pf.Ep = e->d_Ep;
+        pf.work = e->cur_work;
+        pf.tables = e->d_tables;
+        pf.n_work = e->n_slots;
+        pf.ext_len = e->ext_len;
+        pf.table_bytes = (int)((kT2Elems + kBaseElems) * sizeof(float2));
+    }
+    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st, &pf);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
     e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar * e->n_shift, true, e->sm_count, st, pdl);
     if (prof) CU(cudaEventRecord(e->prof[2], st));
@@ -425,6 +439,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         if (e1b_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st, pdl);
         else e->launches += launch_search(a, true, e->sm_count, st, pdl);
     }
+    if (prof) CU(cudaEventRecord(e->prof[3], st));
     if (fold)
         e->launches += launch_pick_small(e->d_cells, e->cur_slot_sat, records_dev, e->d_ctas_done, a.ctas_total, flag_dev,
                                          e->epoch, n_rows, e->n_slots, e->n_dop, e->prm.dop_lo, st, pdl);
@@ -432,7 +447,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         e->launches += launch_best_dop(e->d_cells, e->cur_slot_sat, records_dev, n_captures, e->n_slots, e->n_dop,
                                        e->prm.dop_lo, st, pdl);
     if (prof) {
-        CU(cudaEventRecord(e->prof[3], st));
+        CU(cudaEventRecord(e->prof[4], st));
         e->prof_valid = true;
     }
     CU(cudaGetLastError());
@@ -962,9 +977,8 @@ int acq_get_kernel_ms(acq_engine *e, float *out, int n_out)
     if (!e || !out || n_out < 4) return fail(ACQ_ERR_ARG, "bad argument");
     if (!e->prof_valid) return fail(ACQ_ERR_ARG, "no profiled search yet (call acq_set_profiling first)");
     DeviceGuard g(e->device);
-    CU(cudaEventSynchronize(e->prof[3]));
-    for (int i = 0; i < 3; i++) CU(cudaEventElapsedTime(&out[i], e->prof[i], e->prof[i + 1]));
-    out[3] = 0.0f;  // the best-Doppler pick is part of the search kernels
+    CU(cudaEventSynchronize(e->prof[4]));
+    for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&out[i], e->prof[i], e->prof[i + 1]));
     return ACQ_OK;
 }
 

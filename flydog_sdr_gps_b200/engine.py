@@ -108,11 +108,10 @@ class AcqEngine:
         _check(self._L.acq_set_profiling(self._h, 1 if on else 0), self._L)
 
     def kernel_ms(self):
-        """Device time of each kernel of the most recent search (needs set_profiling(True)).  The best-Doppler pick
-        is part of the search kernels."""
+        """Device time of each kernel of the most recent search (needs set_profiling(True))."""
         out = (C.c_float * 4)()
         _check(self._L.acq_get_kernel_ms(self._h, out, 4), self._L)
-        return dict(zip(["front_end", "fwd_fft", "search"], [float(v) for v in out[:3]]))
+        return dict(zip(["front_end", "fwd_fft", "search", "best_dop"], [float(v) for v in out]))
 
     def device_info(self):
         d, s, c = C.c_int(), C.c_int(), C.c_int()

@@ -225,7 +225,7 @@ int64_t acq_launch_count(const acq_engine *e);
 /* Per-kernel device timing of the most recent search (CUDA events recorded on the launching stream
  * around each kernel when enabled).  acq_get_kernel_ms waits for that search and fills
  *   out[0] = capture front end (unpack + mix + both half-band stages), out[1] = forward FFT,
- *   out[2] = fused correlate + inverse FFT + peak search (all constellations), out[3] = best-Doppler pick
+ *   out[2] = fused correlate + inverse FFT + peak search (all constellations), out[3] = best-Doppler pick (k_pick_small / k_best_dop)
  * in milliseconds; n_out >= 4. */
 int acq_set_profiling(acq_engine *e, int enable);
 int acq_get_kernel_ms(acq_engine *e, float *out, int n_out);

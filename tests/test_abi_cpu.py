@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 from flydog_sdr_gps_b200 import _build, _lib, engine
@@ -176,3 +177,21 @@ def test_bench_reference_arm_contract():
     assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1 and line["gpu_launches"] == 0
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_workload_descriptions():
+    """bench.config_dict: the workload sizes of SURVEY 8(d) / BASELINE.md section 3, identical for both arms."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    want = {"cfg1": (5_368_704, 1_312), "cfg2": (21_081_984, 103_040), "cfg3": (66_290_400, 4_050), "cfg4": (38_923_104, 3_362),
+            "cfg5": (5_497_552_896, 1_343_488)}
+    for cfg, (cells, tiles) in want.items():
+        d = bench.config_dict(cfg, 1)
+        assert (d["cells_per_step"], d["tiles_per_step"]) == (cells, tiles), cfg
+        assert d["workload"] == cfg and d["l2"] == bench.L2_NOTE
+    assert bench.config_dict("cfg5", 8)["captures_total"] == 1024
+    # the farm's captures are defined by their index alone (a rank generating only its shard gets the same bytes)
+    assert bench.farm_signals(5) == bench.farm_signals(5) and bench.farm_signals(5) != bench.farm_signals(6)
+    a = bench.farm_captures_numpy([3])[0]
+    assert a.shape == (8192,) and np.array_equal(a, bench.farm_captures_numpy([2, 3])[1])
