@@ -64,7 +64,6 @@ VARIANTS = {
     "trace": ["ACQ_TRACE"],                  # %globaltimer stamps per CTA (tools/trace_timeline.py)
     "pdl0": ["ACQ_FORCE_PDL=0"],
     "pdl1": ["ACQ_FORCE_PDL=1"],
-    "nopf": ["ACQ_FE_PREFETCH=0"],           # no L2 prefetch of the code rows behind the front end of a small search
     "zcin": ["ACQ_ZC_INPUT=1"],              # front end reads small captures from mapped pinned memory (no H2D copy node)
     "devrec": ["ACQ_HOST_RECORDS=0"],        # records through device memory + copy, stream wait (no mapped memory, no polling)
 }

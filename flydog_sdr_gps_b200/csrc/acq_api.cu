@@ -164,10 +164,6 @@ using namespace acq;
 #ifndef ACQ_ZC_INPUT
 #define ACQ_ZC_INPUT 0
 #endif
-//   ACQ_FE_PREFETCH=0        no L2 prefetch of the code rows behind the front end of a small search
-#ifndef ACQ_FE_PREFETCH
-#define ACQ_FE_PREFETCH 1
-#endif
 // Host path, small searches: the capture goes through an engine-owned pinned staging buffer (a pageable source would
 // make cudaMemcpyAsync synchronous), the kernels write the records straight into mapped pinned memory, and the host
 // polls a completion word there instead of waiting for the stream.  Above these sizes: plain copies and a stream wait.
@@ -379,17 +375,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const bool pdl = !prof && (ACQ_FORCE_PDL == 1 || (ACQ_FORCE_PDL < 0 && tiles_total <= 64LL * e->sm_count));
     if (++e->epoch >= 0xfffffffeu) e->epoch = 1;
     if (prof) CU(cudaEventRecord(e->prof[0], st));
-    // small searches: the code rows of the selected satellites are pulled into L2 while the front end runs (FePrefetch)
-    FePrefetch pf{};
-    if (ACQ_FE_PREFETCH && blocks <= 8 && e->n_slots <= 256) {
-        pf.Ep = e->d_Ep;
-        pf.work = e->cur_work;
-        pf.tables = e->d_tables;
-        pf.n_work = e->n_slots;
-        pf.ext_len = e->ext_len;
-        pf.table_bytes = (int)((kT2Elems + kBaseElems) * sizeof(float2));
-    }
-    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st, &pf);
+    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st);
     if (prof) CU(cudaEventRecord(e->prof[1], st));
     e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar * e->n_shift, true, e->sm_count, st, pdl);
     if (prof) CU(cudaEventRecord(e->prof[2], st));

@@ -79,19 +79,8 @@ constexpr int kFeBytes = (kFeChunkBytes + 12 + 15) / 16 * 16 + 16;  // staged by
 template <bool MAG>
 __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ packed, float2 *__restrict__ x2,
                                                    const float2 *__restrict__ rot, int nvar, int K, int row0,
-                                                   int n_shift, int smax, const FePrefetch pf)
+                                                   int n_shift, int smax)
 {
-    if (blockIdx.x >= kN / kFeOut) {   // the prefetch CTA of a small search (see FePrefetch): no capture work
-        pdl_launch_dependents();
-        const int rows = blockIdx.y == 0 ? 4 * pf.n_work : 0;   // one per launch is enough
-        for (int i = threadIdx.x; i < rows; i += 256) {
-            const float2 *row = pf.Ep + (size_t)(pf.work[i >> 2].x * 4 + (i & 3)) * pf.ext_len;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(pf.ext_len * (int)sizeof(float2)) : "memory");
-        }
-        if (threadIdx.x == 0 && blockIdx.y == 0)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.tables), "r"(pf.table_bytes) : "memory");
-        return;
-    }
     __shared__ __align__(16) uint8_t sbits[kFeBytes + 16];
     __shared__ __align__(16) uint8_t mbits[MAG ? kFeBytes + 16 : 16];
     __shared__ __align__(8) unsigned long long bar;
@@ -1796,24 +1785,18 @@ cudaError_t search_kernels_configure()
 }
 
 int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, int sample_bits,
-                     int n_shift, int smax, cudaStream_t st, const FePrefetch *prefetch)
+                     int n_shift, int smax, cudaStream_t st)
 {
     int launched = 0;
-    FePrefetch pf{};
-    if (prefetch) pf = *prefetch;
     for (int b0 = 0; b0 < n_blocks; b0 += 32768) {  // gridDim.y <= 65535
         const int nb = (n_blocks - b0 < 32768) ? (n_blocks - b0) : 32768;
-        // the prefetch CTA rides on the first launch only (blockIdx.x == kN / kFeOut; every block row gets one, all but
-        // the first return at once)
-        const dim3 grid(kN / kFeOut + ((pf.n_work > 0 && b0 == 0) ? 1 : 0), nb);
-        FePrefetch pfl = pf;
-        if (b0 != 0) pfl.n_work = 0;
+        const dim3 grid(kN / kFeOut, nb);
         if (sample_bits == 2)
             k_front_end<true><<<grid, 256, 0, st>>>(packed + (size_t)b0 * 2 * ACQ_BLOCK_BYTES,
-                                                    x2 + (size_t)b0 * nvar * n_shift * kN, rot, nvar, K, b0, n_shift, smax, pfl);
+                                                    x2 + (size_t)b0 * nvar * n_shift * kN, rot, nvar, K, b0, n_shift, smax);
         else
             k_front_end<false><<<grid, 256, 0, st>>>(packed + (size_t)b0 * ACQ_BLOCK_BYTES,
-                                                     x2 + (size_t)b0 * nvar * n_shift * kN, rot, nvar, K, b0, n_shift, smax, pfl);
+                                                     x2 + (size_t)b0 * nvar * n_shift * kN, rot, nvar, K, b0, n_shift, smax);
         launched++;
     }
     return launched;

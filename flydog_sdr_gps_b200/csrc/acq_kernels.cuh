@@ -42,23 +42,12 @@ __host__ __device__ inline int code_shift(int b, int h, int cd_div)
 // A search launch decomposes its tile index with 32-bit arithmetic; acq_api.cu refuses larger searches.
 constexpr long long kMaxTilesPerLaunch = 0x7fffffffLL;
 
-// Optional L2 prefetch riding on the front-end launch of a small search: one extra CTA asks the TMA unit to pull the
-// extended code-spectrum rows of the satellites about to be searched (and the twiddle tables) into L2 while the front
-// end and the forward FFT run, so the search kernel's first wave does not wait for HBM when the rows have been
-// evicted since the last search (n_work == 0: off).
-struct FePrefetch {
-    const float2 *Ep;
-    const int2 *work;     // (sat, slot) pairs, as SearchArgs::work
-    const float2 *tables;
-    int n_work, ext_len, table_bytes;
-};
-
 // host-side launchers (all asynchronous on `st`; each returns the number of kernels it launched)
 cudaError_t launch_tables_init(const float2 *h_cC, const float *h_hb);
 // sample_bits: 1 = the reference's sign-only capture, 2 = sign plane + magnitude plane per block
 // n_shift/smax: copies of each output row, copy i delayed by a further i - smax samples (code-Doppler compensation)
 int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, int sample_bits,
-                     int n_shift, int smax, cudaStream_t st, const FePrefetch *prefetch = nullptr);
+                     int n_shift, int smax, cudaStream_t st);
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
 int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st);
 // pdl: launch with programmatic stream serialization (the grid may become resident while the previous kernel of
