@@ -242,6 +242,34 @@ def test_e1b_noise_only_capture_near_the_threshold(cfg3_engine, oracle):
     assert np.array_equal(rec[0]["snr"] >= 16.0, orec["snr"] >= 16.0)
 
 
+def test_farm_classes_with_the_cuda_engine(nav_engine, cfg4_engine):
+    """farm.CaptureFarm / farm.SatFarm (the plumbing bench.py's multi-GPU lines run through) on one GPU with the CUDA
+    engine: resident and end-to-end paths give the records of a plain acq_search, bitwise.  (World size 2 with uneven
+    shards is covered under gloo on CPU; NCCL runs are bench.py --gpus N.)"""
+    import torch
+    from flydog_sdr_gps_b200 import farm
+    table = S.navstar()
+    caps = np.stack([synth.make_capture(300 + c, 1, table, scenarios.signals("cfg5", c)) for c in range(5)])
+    want = nav_engine.search(caps.reshape(-1))
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        f = farm.CaptureFarm(nav_engine, 5, 8192, 32)
+        f.load(caps)
+        got = f.search().copy()
+        f.search_resident()
+        st.synchronize()
+        res = f.d_all.cpu().numpy().view(F.RECORD_DTYPE).reshape(5, 32)
+    assert got.tobytes() == want.tobytes() and res.tobytes() == want.tobytes()
+    assert (f.h2d_bytes, f.d2h_bytes) == (5 * 8192, 5 * 32 * 24)
+    t4 = scenarios.table("cfg4")
+    cap = synth.make_capture(41, 1, t4, scenarios.signals("cfg4", 1))
+    with torch.cuda.stream(st):
+        sf = farm.SatFarm(cfg4_engine, len(t4), 8192)
+        sf.load(cap)
+        rec = sf.search().copy()
+    assert rec.tobytes() == cfg4_engine.search(cap)[0].tobytes()
+
+
 def test_lag_and_doppler_sweep(nav_engine):
     """Round trip: inject one strong satellite at many (tau, Doppler); the record returns them."""
     table = S.navstar()
