@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu evidence of a round: launch list of the default bench command, one --set full capture per product search kernel.
-# Usage: bash tools/gpu_r2_ncu.sh <tag>
+# Usage: bash tools/gpu_ncu.sh <tag>
 tag=${1:-ncu}; out=gpurun_out/$tag; mkdir -p $out
 # launch list of the default bench command (our kernels + NCCL + the L2 flush fill; the synthetic-capture generator's
 # torch kernels are left out by the name filter)
