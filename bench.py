@@ -166,20 +166,23 @@ def _ref_worker(args):
     cap_idx, sats = args
     from oracle import oracle_py as O
     t0 = time.perf_counter()
-    O.ref_search(_ref_pool_caps[cap_idx], np.asarray(sats, np.int32))
+    O.ref_search(_ref_pool_caps[cap_idx], np.asarray(sats, np.int32), lib=O.ref_bench())
     return time.perf_counter() - t0
 
 
 class LiteralReference:
     """The UNMODIFIED gps/search.cpp (oracle/_ref: Sample() + Correlate() per satellite, serial over the satellites
     like SearchTask, gps/search.cpp:530-602), forked over host cores -- processes, not threads: the reference keeps its
-    buffers in file statics (gps/search.cpp:51-58,97).  FFT provider: the in-repo fp32 FFT (FFTW is not installed)."""
+    buffers in file statics (gps/search.cpp:51-58,97).  FFT provider: the in-repo fp32 FFT (FFTW is not installed).
+    Timed build: the reference's own optimisation level, -Ofast, with AVX2/FMA (oracle/_ref/libref_search_ofast.so; 2.8x
+    the strict parity build, identical decisions) where the host can run it -- `self.build` says which."""
 
     def __init__(self, captures, n_procs):
         global _ref_pool_caps
         import multiprocessing as mp
         from oracle import oracle_py as O
-        O.ref()  # SearchInit once, inherited by fork
+        O.ref_bench()  # SearchInit once, inherited by fork
+        self.build = O.REF_BENCH_BUILD
         _ref_pool_caps = captures
         self.n = n_procs
         self.pool = mp.get_context("fork").Pool(n_procs) if n_procs > 1 else None
@@ -232,6 +235,7 @@ def cpu_baseline_rows(cells_per_sat=41 * 4092, target_s=4.0):
         probe = lit1.run([(0, sats32[:8])]) / 8                       # seconds per satellite on one core
         n1 = max(1, min(64, int(target_s / (32 * probe))))            # whole captures
         dt = lit1.run([(c % len(caps), sats32) for c in range(n1)])
+        out["build"] = lit1.build
         out["rows"]["B1_literal_search_cpp_1core"] = {
             "value": n1 * 32 * cells_per_sat / dt, "unit": UNIT, "cores": 1, "ms_per_sat": dt / (n1 * 32) * 1e3,
             "sample": "%d cfg5 captures x 32 Navstar PRNs, Sample()+Correlate() per sat, serial (%.2f s)" % (n1, dt)}
@@ -259,7 +263,8 @@ def cpu_baseline_rows(cells_per_sat=41 * 4092, target_s=4.0):
     head = out["rows"].get("B2_literal_search_cpp_all_cores") or out["rows"]["port_oracle_openmp_all_cores"]
     out.update({"value": head["value"], "unit": UNIT, "cores": head["cores"],
                 "kind": "reference" if "B2_literal_search_cpp_all_cores" in out["rows"] else "port",
-                "sample": head["sample"] + "; FFT = in-repo fp32 FFT behind the FFTW API (FFTW unavailable)"})
+                "sample": head["sample"] + "; FFT = in-repo fp32 FFT behind the FFTW API (FFTW unavailable); build " +
+                str(out.get("build", "-O2 strict (oracle port)"))})
     return out
 
 
@@ -284,6 +289,7 @@ def reference_arm(args):
     if O.have_ref():
         kind = "reference"
         lit = LiteralReference(caps, cores)
+        build = lit.build
         one = [(p, list(range(32))) for p in range(cores)]
         probe = lit.run(one)                                   # one capture per core
         per = max(1, min(16, int(1.0 / max(probe, 1e-3))))     # captures per core and step: about a second per step
@@ -297,6 +303,7 @@ def reference_arm(args):
         n_caps_step = per * cores
     else:
         kind = "port"
+        build = "-O2 strict IEEE (oracle port)"
         prm = O.default_params()
         n_caps_step = 2
         sample = "each step: 2 of the %d captures x 32 PRNs x 41 bins, OpenMP oracle port (oracle/_ref not built)" % CAPTURES_TOTAL
@@ -314,8 +321,8 @@ def reference_arm(args):
             "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_dict(HEADLINE, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": sample + "; FFT = in-repo fp32 FFT behind the FFTW API (FFTW unavailable)",
-                             "fftw": fftw_probe()},
+                             "sample": sample + "; FFT = in-repo fp32 FFT behind the FFTW API (FFTW unavailable); build " + build,
+                             "build": build, "fftw": fftw_probe()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

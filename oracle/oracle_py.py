@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "_build", "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_search.so")
 REF50_SO = os.path.join(HERE, "_ref", "libref_search_e1b50.so")  # same search.cpp over a 50-row Galileo table
+REF_OFAST_SO = os.path.join(HERE, "_ref", "libref_search_ofast.so")  # same sources at the reference's own -Ofast (+AVX2/FMA)
 
 N = 16384
 BLOCK_BYTES = 8192
@@ -126,6 +127,33 @@ def ref():
             return None
         _ref = _bind_ref(REF_SO)
     return _ref
+
+
+_ref_bench = None
+REF_BENCH_BUILD = None
+
+
+def _cpu_has(*flags):
+    try:
+        words = set(open("/proc/cpuinfo").read().split())
+    except OSError:
+        return False
+    return all(f in words for f in flags)
+
+
+def ref_bench():
+    """The unmodified reference for TIMING (bench.py's CPU arms): the -Ofast + AVX2/FMA build where it exists and the host
+    CPU can run it (the reference's own build compiles gps/ with -Ofast), else the strict build.  Never used for parity.
+    REF_BENCH_BUILD says which."""
+    global _ref_bench, REF_BENCH_BUILD
+    if _ref_bench is None:
+        if os.path.exists(REF_OFAST_SO) and _cpu_has("avx2", "fma"):
+            _ref_bench = _bind_ref(REF_OFAST_SO)
+            REF_BENCH_BUILD = "-Ofast -mavx2 -mfma (gps/ is built with -Ofast in the reference, Makefile.comp.inc)"
+        else:
+            _ref_bench = ref()
+            REF_BENCH_BUILD = "-O2 strict IEEE (the parity build; no -Ofast/AVX2 build usable on this host)"
+    return _ref_bench
 
 
 _ref50 = None
@@ -343,8 +371,8 @@ def ref_sample(packed):
     return x2.view(np.complex64), D.view(np.complex64)
 
 
-def ref_search(packed, sel):
-    """Sample()+Correlate() of the unmodified reference for each sat index in sel."""
+def ref_search(packed, sel, lib=None):
+    """Sample()+Correlate() of the unmodified reference for each sat index in sel (lib: a handle from ref_bench())."""
     packed = np.ascontiguousarray(packed, np.uint8)
     assert packed.size == BLOCK_BYTES
     sel = np.ascontiguousarray(sel, np.int32)
@@ -352,8 +380,8 @@ def ref_search(packed, sel):
     lag = np.zeros(len(sel), np.int32)
     snr = np.zeros(len(sel), np.float32)
     i32 = C.POINTER(C.c_int32)
-    ref().ref_search(_u8(packed), sel.ctypes.data_as(i32), len(sel), dop.ctypes.data_as(i32),
-                     lag.ctypes.data_as(i32), _fp(snr))
+    (lib or ref()).ref_search(_u8(packed), sel.ctypes.data_as(i32), len(sel), dop.ctypes.data_as(i32),
+                              lag.ctypes.data_as(i32), _fp(snr))
     return dop, lag, snr
 
 

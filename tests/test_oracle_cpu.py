@@ -460,3 +460,21 @@ def test_sbas_rows_keep_the_reference_all_zero_spectrum(oracle):
     # and it differs from what it would read if a real spectrum followed
     follow = oracle.search(cap, nav[:5], want_grid=True)[1]
     assert not np.array_equal(grid[2]["snr"][:20], follow[2]["snr"][:20])
+
+
+def test_ofast_reference_build_gives_the_same_decisions(oracle, golden_search):
+    """oracle/_ref/libref_search_ofast.so -- the unmodified sources at the reference's own -Ofast (+AVX2/FMA), bench.py's
+    timed CPU baseline -- against the strict parity build on the golden captures: identical (dop, lag) for every
+    satellite that is not in a numerical tie, snr within 1e-5.  (Its floats are not reproducible bit for bit, which is
+    why it is never used for parity.)"""
+    if not (os.path.exists(oracle.REF_OFAST_SO) and oracle._cpu_has("avx2", "fma")):
+        pytest.skip("no -Ofast reference build usable on this host")
+    lib = oracle.ref_bench()
+    assert "Ofast" in oracle.REF_BENCH_BUILD
+    sel = np.arange(59, dtype=np.int32)
+    for i, cap in enumerate(golden_search["captures"][:2]):
+        dop, lag, snr = oracle.ref_search(cap, sel, lib=lib)
+        np.testing.assert_allclose(snr, golden_search["snr"][i], rtol=1e-5)
+        strong = golden_search["snr"][i] >= 16
+        assert np.array_equal(dop[strong], golden_search["dop"][i][strong])
+        assert np.array_equal(lag[strong], golden_search["lag"][i][strong])
