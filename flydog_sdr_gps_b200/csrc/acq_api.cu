@@ -467,6 +467,9 @@ int poll_flag(acq_engine *e)
         const unsigned f = *flag;
         if (f == e->epoch) return ACQ_OK;
         if (f == 0xffffffffu) return fail(ACQ_ERR_CUDA, "search kernels did not complete (best-Doppler pick timed out)");
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();  // a polite spin: the wait is tens of microseconds
+#endif
         if ((spins & 0x3ff) == 0) {
             const cudaError_t q = cudaStreamQuery(e->stream);
             if (q == cudaSuccess) return (*flag == e->epoch) ? ACQ_OK : fail(ACQ_ERR_CUDA, "search finished without its completion signal");
