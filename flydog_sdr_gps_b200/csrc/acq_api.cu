@@ -274,7 +274,9 @@ int ensure_scratch(acq_engine *e, int n_captures, int n_slots, bool host_path)
             if (e->h_records) CU(cudaFreeHost(e->h_records));
             e->h_records = e->dh_records = nullptr;
             e->cap_h_records = 0;
-            CU(cudaHostAlloc(&e->h_records, rows * sizeof(acq_record), cudaHostAllocMapped));
+            // sized for the tagged form a polling host reads (acq_record_tagged, 32 B); the plain 24-byte form fits too
+            CU(cudaHostAlloc(&e->h_records, rows * sizeof(acq_record_tagged), cudaHostAllocMapped));
+            memset(e->h_records, 0, rows * sizeof(acq_record_tagged));
             CU(cudaHostGetDevicePointer(&e->dh_records, e->h_records, 0));
             e->cap_h_records = rows;
         }
@@ -458,24 +460,39 @@ int check_tile_count(acq_engine *e, int n_captures)
     return ACQ_OK;
 }
 
-// Wait for a host-polled search: the kernels store `epoch` to the mapped completion word once the last record is
-// in host memory.  The stream is queried now and then so that a failed launch cannot hang the caller.
-int poll_flag(acq_engine *e)
+// Wait for a host-polled search and collect its records: k_pick_small writes every record into mapped memory as two
+// 16-byte halves that each end in the search's epoch (acq_record_tagged), so a half whose tag matches has arrived whole.
+// The stream is queried now and then so that a failed launch cannot hang the caller; the mapped word *h_flag is only
+// ever written to report that the pick gave up (0xffffffff).
+int poll_records(acq_engine *e, acq_record *out, size_t rows)
 {
-    volatile unsigned *flag = e->h_flag;
-    for (unsigned spins = 1;; spins++) {
-        const unsigned f = *flag;
-        if (f == e->epoch) return ACQ_OK;
-        if (f == 0xffffffffu) return fail(ACQ_ERR_CUDA, "search kernels did not complete (best-Doppler pick timed out)");
+    const volatile acq_record_tagged *h = reinterpret_cast<const volatile acq_record_tagged *>(e->h_records);
+    const unsigned epoch = e->epoch;
+    unsigned spins = 0;
+    for (size_t i = 0; i < rows; i++) {
+        while (h[i].tag0 != epoch || h[i].tag1 != epoch) {
+            if ((++spins & 0x3ff) == 0) {
+                if (*(volatile unsigned *)e->h_flag == 0xffffffffu) {
+                    *e->h_flag = 0;
+                    return fail(ACQ_ERR_CUDA, "search kernels did not complete (best-Doppler pick timed out)");
+                }
+                const cudaError_t q = cudaStreamQuery(e->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return fail(ACQ_ERR_CUDA, "search failed: %s", cudaGetErrorString(q));
+                if (q == cudaSuccess && (h[i].tag0 != epoch || h[i].tag1 != epoch))
+                    return fail(ACQ_ERR_CUDA, "search finished without delivering its records");
+            }
 #if defined(__x86_64__) || defined(__i386__)
-        __builtin_ia32_pause();  // a polite spin: the wait is tens of microseconds
+            __builtin_ia32_pause();  // a polite spin: the wait is tens of microseconds
 #endif
-        if ((spins & 0x3ff) == 0) {
-            const cudaError_t q = cudaStreamQuery(e->stream);
-            if (q == cudaSuccess) return (*flag == e->epoch) ? ACQ_OK : fail(ACQ_ERR_CUDA, "search finished without its completion signal");
-            if (q != cudaErrorNotReady) return fail(ACQ_ERR_CUDA, "search failed: %s", cudaGetErrorString(q));
         }
+        out[i].sat = h[i].sat;
+        out[i].lag = h[i].lag;
+        out[i].dop = h[i].dop;
+        out[i].peak = h[i].peak;
+        out[i].noise = h[i].noise;
+        out[i].snr = h[i].snr;
     }
+    return ACQ_OK;
 }
 
 int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int32_t *sel, int n_sel, acq_record *out,
@@ -516,12 +533,12 @@ int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int3
         return ACQ_OK;
     }
     if (poll) {
-        if ((rc = poll_flag(e))) return rc;
+        if ((rc = poll_records(e, out, rows))) return rc;
     } else {
         CU(cudaStreamSynchronize(e->stream));
+        if (host_records) memcpy(out, e->h_records, rows * sizeof(acq_record));
     }
     e->dev_pending = false;  // this search was ordered behind the last device-path search, so that one is complete too
-    if (host_records) memcpy(out, e->h_records, rows * sizeof(acq_record));
     return ACQ_OK;
 }
 

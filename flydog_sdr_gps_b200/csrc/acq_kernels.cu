@@ -1532,7 +1532,9 @@ __global__ void __launch_bounds__(1024) k_pick_small(const acq_cell *cells, cons
 {
     // Records are staged in shared memory and leave in 16-byte pieces: written one 4-byte member at a time straight into
     // mapped host memory they cost 0.17 us per record (every store its own PCIe write: 6.8 us of a 74 us cold-start
-    // search, 14 us for the 82 rows of the all-constellation search -- measured with the trace variant).
+    // search, 14 us for the 82 rows of the all-constellation search -- measured with the trace variant).  For a polling
+    // host every 16-byte piece carries the epoch (acq_record_tagged): the 2..3.5 us of system fence + completion word
+    // that used to close the kernel are gone.
     __shared__ __align__(16) acq_record s_rec[kPickSmallRowsMax];
     const int t = threadIdx.x;
     ACQ_TRACE_STAMP(kTrPick, 0);
@@ -1562,24 +1564,33 @@ __global__ void __launch_bounds__(1024) k_pick_small(const acq_cell *cells, cons
     pick_rows<4>(cells, slot_sat, s_rec, t >> 5, 32, n_rows, n_slots, n_dop, dop_lo, t & 31);
     __syncthreads();
     ACQ_TRACE_STAMP(kTrPick, 3);
-    const int n16 = n_rows * (int)sizeof(acq_record) / 16;  // 24-byte records: an even row count is a whole number of pieces
-    const uint4 *src = reinterpret_cast<const uint4 *>(s_rec);
-    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if (host_flag) {
+        // polled host: tagged 32-byte records, two 16-byte stores each (see acq_record_tagged); nothing to fence
         uint4 *dst = reinterpret_cast<uint4 *>(out);
-        for (int i = t; i < n16; i += 1024) dst[i] = src[i];
-        const int tail = n16 * 16;  // odd row count: the last 8 bytes
-        if (t == 0 && tail < n_rows * (int)sizeof(acq_record))
-            *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(out) + tail) =
-                *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(s_rec) + tail);
+        const unsigned tag = s_timed_out ? 0xffffffffu : epoch;   // a pick that gave up never announces records
+        for (int i = t; i < n_rows; i += 1024) {
+            const acq_record r = s_rec[i];
+            dst[2 * i] = make_uint4((unsigned)r.sat, (unsigned)r.lag, (unsigned)r.dop, tag);
+            dst[2 * i + 1] = make_uint4(__float_as_uint(r.peak), __float_as_uint(r.noise), __float_as_uint(r.snr), tag);
+        }
+        if (t == 0) {
+            *ctas_done = 0;
+            if (s_timed_out) *reinterpret_cast<volatile unsigned *>(host_flag) = 0xffffffffu;
+        }
     } else {
-        for (int i = t; i < n_rows; i += 1024) out[i] = s_rec[i];
-    }
-    // the records are in host memory before the word that announces them (only the threads that stored any need to fence)
-    if (host_flag && t <= n16) __threadfence_system();
-    __syncthreads();
-    if (t == 0) {
-        *ctas_done = 0;
-        if (host_flag) *reinterpret_cast<volatile unsigned *>(host_flag) = s_timed_out ? 0xffffffffu : epoch;
+        const int n16 = n_rows * (int)sizeof(acq_record) / 16;  // 24-byte records: an even row count is a whole number of pieces
+        const uint4 *src = reinterpret_cast<const uint4 *>(s_rec);
+        if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            uint4 *dst = reinterpret_cast<uint4 *>(out);
+            for (int i = t; i < n16; i += 1024) dst[i] = src[i];
+            const int tail = n16 * 16;  // odd row count: the last 8 bytes
+            if (t == 0 && tail < n_rows * (int)sizeof(acq_record))
+                *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(out) + tail) =
+                    *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(s_rec) + tail);
+        } else {
+            for (int i = t; i < n_rows; i += 1024) out[i] = s_rec[i];
+        }
+        if (t == 0) *ctas_done = 0;
     }
     ACQ_TRACE_STAMP(kTrPick, 2);
 }

@@ -59,14 +59,25 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 int launch_search_e1b_cluster(const SearchArgs &a, int sm_count, cudaStream_t st, bool pdl = false);
 int launch_best_dop(const acq_cell *cells, const int *slot_sat, acq_record *out, int n_cap, int n_slots, int n_dop,
                     int dop_lo, cudaStream_t st, bool pdl = false);
-// best-Doppler pick of a small search: one CTA that polls the search CTAs' counter (see k_pick_small); host_flag
-// (mapped pinned memory, or NULL) receives `epoch` once the records are written
+// best-Doppler pick of a small search: one CTA that polls the search CTAs' counter (see k_pick_small).  host_flag
+// (mapped pinned memory, or NULL) selects the polled-host form: `out` is then an acq_record_tagged array in mapped
+// memory (tags = epoch), and *host_flag is written only to report a failure (0xffffffff)
 int launch_pick_small(const acq_cell *cells, const int *slot_sat, acq_record *out, unsigned *ctas_done, unsigned ctas_total,
                       unsigned *host_flag, unsigned epoch, int n_rows, int n_slots, int n_dop, int dop_lo, cudaStream_t st,
                       bool pdl = false);
 // CTAs of a search launch that store cells (what SearchArgs::ctas_total sums over the launches of one search)
 enum { kSearchL1 = 0, kSearchE1b = 1, kSearchE1bCluster = 2 };
 constexpr int kPickSmallRowsMax = 256;  // rows k_pick_small stages in shared memory
+// A record as k_pick_small hands it to a POLLING host (mapped pinned memory): two 16-byte halves, each carrying the
+// search's epoch in its last word.  Each half arrives by one 16-byte store, so a host that sees the epoch in a half has
+// the whole half: no system fence and no separate completion word on the kernel's tail.
+struct acq_record_tagged {
+    int32_t sat, lag, dop;
+    uint32_t tag0;
+    float peak, noise, snr;
+    uint32_t tag1;
+};
+static_assert(sizeof(acq_record_tagged) == 32, "two 16-byte halves");
 int search_grid_ctas(long long n_tiles, int kind, int sm_count);
 // refinement of the records of the most recent search (one CTA per record)
 int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
