@@ -409,6 +409,32 @@ def test_device_resident_api_on_torch_stream(nav_engine):
     assert rec_big.tobytes() == (host.tobytes() * 3)
 
 
+def test_engine_lifetime_leaves_no_device_memory_behind(gpu_required):
+    """acq_create / searches through every host path / acq_destroy, thirty times: device memory returns to where it was
+    (scratch, mapped staging buffers, events and streams are all owned by the handle)."""
+    import torch
+    table = S.reference_table()
+    cap = synth.make_capture(11, 1, table, [(2, 4000, 4 * F.BIN_HZ, 48, 1.0)])
+    sel = np.array([2, 40], np.int32)
+
+    def cycle():
+        with F.AcqEngine(table) as eng:
+            r = eng.search(cap, sel=sel)                       # polled host path, tagged records
+            eng.search(np.concatenate([cap] * 200), sel=sel)   # 400 rows: device records, copy, k_best_dop
+            out = np.zeros((1, 2), F.RECORD_DTYPE)
+            eng.submit(cap, out, sel=sel)
+            eng.wait()
+            assert out.tobytes() == r.tobytes()
+            eng.refine(out)
+    cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(30):
+        cycle()
+    torch.cuda.synchronize()
+    assert free0 - torch.cuda.mem_get_info()[0] < (32 << 20)
+
+
 def test_error_paths(nav_engine):
     L = _lib.load()
     cap = np.zeros(8192, np.uint8)
