@@ -413,6 +413,10 @@ def roofline_of(cfg, table, n_dop, k, n_cap, search_ms, step_kern_ms, mb, peaks)
     flop = sum(k * n_dop * FLOP_PER_TILE[l] for l in lags) * n_cap
     smem_b = sum(k * n_dop * SMEM_BYTES_PER_TILE[l] for l in lags) * n_cap
     hbm_b = n_cap * k * 8192 + len(table) * 16384 * 8 + 24 * len(table) * n_cap
+    # what the search KERNEL itself must read when its inputs are not cache-resident: the capture spectra the forward FFT
+    # left behind (128 KiB per capture, block and half-bin variant) and the extended code rows (~128 KiB per satellite)
+    nvar = 2 if cfg == "cfg2" else 1
+    hbm_kernel_b = n_cap * k * nvar * 16384 * 8 + len(table) * 16384 * 8 + 16 * len(table) * n_dop * n_cap
     tiles = len(table) * n_dop * k * n_cap
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     sec = search_ms * 1e-3
@@ -434,7 +438,12 @@ def roofline_of(cfg, table, n_dop, k, n_cap, search_ms, step_kern_ms, mb, peaks)
                  "peak_source": "FFMA micro-benchmark in this run; nominal 148 SM x 128 lanes x 2 x clock"},
         "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": hbm_b},
+                "algorithmic_bytes_per_launch": hbm_b,
+                "search_kernel_input_bytes": hbm_kernel_b,
+                "note": "algorithmic_bytes_per_launch = SURVEY 8(d)'s unique bytes of the whole path (packed captures + code "
+                        "spectra + records); the search kernel's own inputs are the capture spectra the forward FFT wrote "
+                        "(search_kernel_input_bytes; beyond L2 for a 1024-capture farm), which `traffic` (ncu, cold caches) "
+                        "should be compared with. Either way HBM carries well under 1 % of its bandwidth here."},
     }
     if ctr.get("smem_wavefronts_per_tile"):
         # what the L1/shared data pipe physically carried (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared of the
