@@ -548,9 +548,10 @@ __device__ __forceinline__ void subfft4_park_twiddles(const float2 *__restrict__
 // box): +1.2 % on the K > 1 kernel (cfg2), +0.9 % on E1B (cfg3); on the K = 1 kernel -0.8 % with the rolled residue
 // loop, +1.5 % (cfg5) once that loop is unrolled by two -- every product kernel uses it now, the 8-byte swizzle
 // stays as the template's other branch.
-template <bool SWZ128, class PostBarrier>
+//   team_barrier(): the barrier of the 256 threads of this sub-FFT (the CTA barrier, or a named barrier of a team)
+template <bool SWZ128, class TeamBarrier, class PostBarrier>
 __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
-                                                const uint32_t tw_taddr, PostBarrier &&post_barrier)
+                                                const uint32_t tw_taddr, TeamBarrier &&team_barrier, PostBarrier &&post_barrier)
 {
     radix16_inv(x);
     stage_a_store<kRowElems>(x, b, S1b + t);
@@ -558,7 +559,7 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
     tmem_ld8(tw_taddr + 32 * k2, tw);        // n1 = 1..8, in flight across the barrier
     tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15, then the next residue's stage-A base
 #define TW_AT(i) ((i) < 8 ? tw[(i)] : tw2[(i) - 8])
-    __syncthreads();
+    team_barrier();
     post_barrier();
     float2 *row = S1b + (t >> 4) * kRowElems;  // row n0 = t >> 4
     const int c = t & 15;
@@ -618,6 +619,13 @@ __device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, f
 }
 #undef TW_AT
 
+template <bool SWZ128, class PostBarrier>
+__device__ __forceinline__ void subfft4096_inv4(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
+                                                const uint32_t tw_taddr, PostBarrier &&post_barrier)
+{
+    subfft4096_inv4<SWZ128>(x, k2, b, S1b, t, tw_taddr, [] { __syncthreads(); }, post_barrier);
+}
+
 // Form of subfft4096_inv4 for kernels whose tensor memory is taken by parked data (k_search_e1b: 96 of a thread's
 // 128 columns hold three residues): the stage-B twiddles W1024^{(4c+k2)*n1} come from a 7.5 KiB shared-memory
 // table T2s (read before the barrier / during stage B, broadcast between the two half-warps), the stage-A base
@@ -656,9 +664,10 @@ struct BaseFromGlobal {
     __device__ __forceinline__ float2 get() { return v; }
 };
 
-template <class BaseSrc, class PostBarrier>
+template <class BaseSrc, class TeamBarrier, class PostBarrier>
 __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
-                                                 const float2 *T2s, BaseSrc base_src, PostBarrier &&post_barrier)
+                                                 const float2 *T2s, BaseSrc base_src, TeamBarrier &&team_barrier,
+                                                 PostBarrier &&post_barrier)
 {
     radix16_inv(x);
     stage_a_store<256>(x, b, S1b + t);
@@ -672,7 +681,7 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
 #pragma unroll
     for (int i = 0; i < (ACQ_E1B_TW15 ? 15 : 8); i++) tw[i] = twp[i * 16];  // n1 = 1..8 (or all 15)
     base_src.issue(k2);
-    __syncthreads();
+    team_barrier();
     post_barrier();
     float2 *row = S1b + (t >> 4) * 256;  // row n0 = t >> 4
     const int c = t & 15;
@@ -724,6 +733,12 @@ __device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, 
     }
 #endif
     radix16_inv(x);
+}
+template <class BaseSrc, class PostBarrier>
+__device__ __forceinline__ void subfft4096_inv4s(float2 (&x)[16], const int k2, float2 &b, float2 *S1b, const int t,
+                                                 const float2 *T2s, BaseSrc base_src, PostBarrier &&post_barrier)
+{
+    subfft4096_inv4s(x, k2, b, S1b, t, T2s, base_src, [] { __syncthreads(); }, post_barrier);
 }
 
 }  // namespace acq
