@@ -55,7 +55,9 @@ def build(force=False, verbose=False, defines=(), out=None):
 # library contains none of this code and reads no environment variable.
 VARIANTS = {
     "l1_multi_tw": ["ACQ_VARIANT_L1_MULTI_TW"],  # K > 1 C/A search with the twiddles (not the code run) in tensor memory
-    "l1_sp": ["ACQ_L1_SP=1"],                # K = 1 C/A search software-pipelined across sub-FFTs, one CTA per SM
+    "l1_cta": ["ACQ_FORCE_L1_CTA=1"],        # K = 1 C/A search always by k_search_l1<false> (two CTAs per SM, thread 0 stages)
+    "l1_sp": ["ACQ_VARIANT_L1_SP"],          # K = 1 C/A search software-pipelined across sub-FFTs, one CTA per SM (measured: -3.7 %)
+    "l1_st": ["ACQ_VARIANT_L1_ST"],          # staging warps only (capture residue still staged per sub-FFT): +1.9 %
     "l1_ldg": ["ACQ_VARIANT_L1_LDG"],        # C/A search, operands straight from L2
     "l1_x3": ["ACQ_VARIANT_L1_X3"],
     "l1_x3t": ["ACQ_VARIANT_L1_X3", "ACQ_X3_TMA_D"],  # ... with the capture residue TMA-staged, the code run from L2 issued early          # C/A search at three CTAs per SM (accumulators in tensor memory)

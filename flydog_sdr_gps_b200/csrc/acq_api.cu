@@ -405,7 +405,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     // one-CTA-per-tile forms (k_search_e1b, k_search_e1b_multi for non-coherent sums) have ~2.9x the throughput.
     const bool e1b_cluster = ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && tiles_e1b <= e->sm_count / 4);
     a.ctas_done = e->d_ctas_done;
-    a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, K > 1 ? kSearchL1Multi : kSearchL1, e->sm_count) +
+    a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, search_kind_l1(K, e->prm.half_bin), e->sm_count) +
                                      search_grid_ctas(tiles_e1b, e1b_cluster ? kSearchE1bCluster : kSearchE1b, e->sm_count))
                         : 0u;
     a.wait_prior = 1;

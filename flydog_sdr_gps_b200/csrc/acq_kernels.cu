@@ -887,419 +887,21 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
 }
 
-// k_search_l1_sp -- the K = 1 C/A search as a SOFTWARE-PIPELINED chain of sub-FFTs, one 256-thread CTA per SM with the
-// whole register file (255 registers per thread).  k_search_l1 runs a sub-FFT as "operand loads -> products ->
-// stage A | CTA barrier | stage B -> stage C -> accumulate": between two barriers every warp of a CTA is in the same
-// phase, the L1/shared data pipe and the FMA pipe take turns, and only the second CTA of the SM fills the gaps (one CTA
-// alone needs LSU time + FMA time per sub-FFT: no overlap at all, ncu).  Here the interval between two CTA barriers holds
-// the SECOND half of sub-FFT j (stage B, stage C, accumulation) and the FIRST half of sub-FFT j + 1 (products, stage A)
-// as one branch-free instruction stream per thread, the loads of both issued at its head, so a warp's own FP work on one
-// sub-FFT covers its own shared-memory round trips of the other -- overlap inside every warp instead of between CTAs.
-// That needs the operands of j + 1 at the START of interval j, one interval earlier than k_search_l1 stages them: the
-// exchange buffer has three slots (D of j + 2 lands in the slot sub-FFT j - 1 has left) and the code run two, 160 KiB of
-// shared memory.  Same arithmetic in the same order as k_search_l1<false>: bitwise-equal cells (tested).
-#ifndef ACQ_L1_SP
-#define ACQ_L1_SP 0
-#endif
-#if ACQ_L1_SP
-constexpr int kSpSlots = 4;   // exchange slots (a sub-FFT's operands are staged three intervals ahead)
-struct SpSmem {
-    float2 *S1;  // [kSpSlots][16][256]
-    float2 *E;   // [2][4098]
-    unsigned long long *bar;  // [2]
-    float *red_f;
-    int *red_i;
-};
-__host__ __device__ constexpr size_t sp_smem_bytes()
-{
-    return sizeof(float2) * (size_t)(kSpSlots * kS1pElems + 2 * kEBufElems) + 16 + 64 * sizeof(float);
-}
-__device__ __forceinline__ SpSmem sp_smem_carve(unsigned char *smem)
-{
-    SpSmem m;
-    m.S1 = reinterpret_cast<float2 *>(smem);
-    m.E = m.S1 + kSpSlots * kS1pElems;
-    m.bar = reinterpret_cast<unsigned long long *>(m.E + 2 * kEBufElems);
-    m.red_f = reinterpret_cast<float *>(m.bar + 2);
-    m.red_i = reinterpret_cast<int *>(m.red_f + 32);
-    return m;
-}
-
-// Three warpgroups: two of FFT warps (232 registers per thread after setmaxnreg) and one whose first warp stages the
-// operands and stores the cells (40 registers; its other three warps only hold the warpgroup together).  A ninth warp
-// with the FFT warps' register count would not fit a scheduler's quarter of the register file.
-constexpr int kSpThreads = 384, kSpBarThreads = 288;
-__device__ __forceinline__ void sp_cta_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kSpBarThreads) : "memory"); }
-
-// Interval j (between CTA barriers j and j + 1) of an FFT warp, with x_{j+1} = the products of sub-FFT j + 1 in registers:
-//   gather of stage B (j)  |  stage A (j+1): radix-16, twiddles, exchange stores  |  operand loads of j + 2
-//   stage B (j): radix-16, twiddles, tile stores  |  tile loads  |  products of j + 2  |  stage C (j), accumulation
-// so every shared-memory round trip of one sub-FFT is covered by FP work of another that needs no load.  The operands
-// of sub-FFT i are staged three intervals ahead: four exchange slots, two code-run slots.
-struct SpCtx {
-    SpSmem m;
-    uint32_t bar0;
-    int sd, sw, sc;
-    __device__ __forceinline__ float2 *slot(int i) const { return m.S1 + (i & 3) * kS1pElems; }   // exchange slot of sub-FFT i
-};
-
-// The staging warp (lane 0 works): after CTA barrier j it stages the operands of sub-FFT j + 3 (D into the exchange slot
-// sub-FFT j - 1 has left, E into the slot sub-FFT j + 1's code run was read from) and, once per tile, merges the warp
-// partials of the finished tile and stores its cell.  None of this sits on an FFT warp's path to a barrier.
-__device__ __forceinline__ void sp_stage_warp(const SearchArgs &p, const SpCtx &cx, const bool lead)
-{
-    constexpr int L = ACQ_LAGS_L1;
-    float *red_f = cx.m.red_f;
-    int *red_i = cx.m.red_i;
-    TileIdx ti(p, blockIdx.x);
-    auto issue = [&](const TileIdx &tn, int k2n, int i) {
-        const int r = (k2n - tn.dop) & 3;
-        const int q = (k2n - tn.dop - r) >> 2;
-        const float2 *Dk = p.Dp + d_row(p, tn, 0) * kN + k2n * kSub;
-        const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
-        const uint32_t bar = cx.bar0 + 8u * (i & 1);
-        fence_proxy_async();  // generic-proxy accesses of these buffers (ordered by the CTA barrier) before the async writes
-        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
-        tma_load_1d(smem_u32(cx.m.E + (i & 1) * kEBufElems), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
-        tma_load_1d(smem_u32(cx.slot(i)), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
-    };
-    int j = 0, par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-    if (lead) {
-        issue(ti, 0, 0);
-        issue(ti, 1, 1);
-    }
-    __syncwarp();
-    sp_cta_barrier();   // P: the FFT warps have read the operands of sub-FFT 0 (E slot 0 is free)
-    if (lead) issue(ti, 2, 2);
-    __syncwarp();
-    sp_cta_barrier();   // barrier 0
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        TileIdx tn = ti;
-        if (tile + gridDim.x < p.n_tiles) tn.step(p, cx.sd, cx.sw, cx.sc);
-#pragma unroll 1
-        for (int k2 = 0; k2 < 4; k2++) {
-            if (lead) {
-                issue((k2 < 1) ? ti : tn, (k2 + 3) & 3, j + 3);   // sub-FFT j + 3
-                if (k2 == 0 && pend_cap >= 0)                     // the previous tile's peak (its partials precede the barrier)
-                    store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
-            }
-            __syncwarp();
-            sp_cta_barrier();
-            j++;
-        }
-        pend_cap = ti.cap;
-        pend_slot = ti.slot;
-        pend_d = ti.d;
-        par ^= 1;
-        ti = tn;
-    }
-    if (lead) {
-        if (pend_cap >= 0)
-            store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
-        mbar_wait(cx.bar0 + 8u * ((j + 2) & 1), (uint32_t)(((j + 2) >> 1) & 1));   // the last staged operands (never used) must have landed
-        if (p.ctas_total) {
-            __threadfence();  // this CTA's cells (all stored by this thread) before the count
-            atomicAdd(p.ctas_done, 1u);
-        }
-    }
-    __syncwarp();
-}
-
-// The eight FFT warps.
-__device__ __forceinline__ void sp_fft_warps(const SearchArgs &p, const SpCtx &cx, const int t, const uint32_t tw_taddr)
-{
-    float *red_f = cx.m.red_f;
-    int *red_i = cx.m.red_i;
-    const uint32_t bar0 = cx.bar0;
-    subfft4_park_twiddles(p.tables, tw_taddr, t);
-    TileIdx ti(p, blockIdx.x);
-    auto e_of = [&](const TileIdx &tn, int k2n, int i) {   // this thread's column of the staged code run of sub-FFT i
-        const int r = (k2n - tn.dop) & 3;
-        const int q = (k2n - tn.dop - r) >> 2;
-        return cx.m.E + (i & 1) * kEBufElems + ((p.Q + q) & 1) + t;
-    };
-    int j = 0, par = 0;
-    float2 xa[16];
-    {   // prologue: first half of sub-FFT 0, products of sub-FFT 1
-        const float2 bw = __ldg(p.tables + kT2Elems + t);  // W16384^{4t}: base of residue 0; later bases come from TMEM
-        const float2 *Dk = cx.slot(0) + t, *Ek = e_of(ti, 0, 0);
-        mbar_wait(bar0, 0);
-#pragma unroll
-        for (int a = 0; a < 16; a++) xa[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
-        sp_cta_barrier();   // P
-        radix16_inv(xa);
-        stage_a_store<kRowElems>(xa, bw, cx.slot(0) + t);
-        const float2 *Dk1 = cx.slot(1) + t, *Ek1 = e_of(ti, 1, 1);
-        mbar_wait(bar0 + 8, 0);
-#pragma unroll
-        for (int a = 0; a < 16; a++) xa[a] = cmul_conj_a(Dk1[kRowElems * a], Ek1[256 * a]);
-    }
-    sp_cta_barrier();   // barrier 0
-    float2 acc[16];
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        // the tile after this one (a CTA's last tile stages and half-transforms itself once more: branch-free intervals)
-        TileIdx tn = ti;
-        if (tile + gridDim.x < p.n_tiles) tn.step(p, cx.sd, cx.sw, cx.sc);
-#pragma unroll
-        for (int k2 = 0; k2 < 4; k2++) {
-            // ---- interval j: second half of sub-FFT j = (ti, k2), stage A of sub-FFT j + 1 (products in xa), products of j + 2
-            const TileIdx &t2 = (k2 < 2) ? ti : tn;   // tile of sub-FFT j + 2
-            float2 *Sc = cx.slot(j), *Sn = cx.slot(j + 1);
-            float2 tw[8], tw2[8];
-            tmem_ld8(tw_taddr + 32 * k2, tw);        // stage-B twiddles n1 = 1..8 of residue k2
-            tmem_ld8(tw_taddr + 32 * k2 + 16, tw2);  // n1 = 9..15, then the stage-A base of residue k2 + 1
-#define TW_AT(i) ((i) < 8 ? tw[(i)] : tw2[(i) - 8])
-            mbar_wait(bar0 + 8u * (j & 1), (uint32_t)(((j + 2) >> 1) & 1));   // operands of sub-FFT j + 2
-            float2 *row = Sc + (t >> 4) * kRowElems;  // row n0 = t >> 4 of sub-FFT j's exchange
-            const int c = t & 15;
-            float2 xb[16], d[16], e[16];
-            {
-                const float2 *src = row + c;
-#pragma unroll
-                for (int bb = 0; bb < 16; bb++) xb[bb] = src[16 * bb];
-            }
-            radix16_inv(xa);                                        // stage A of j + 1: needs no load
-            tmem_wait_ld();
-            stage_a_store<kRowElems>(xa, TW_AT(15), Sn + t);       // sixteenth twiddle slot of residue k2: the base of residue k2 + 1
-            {
-                const float2 *Dk = cx.slot(j + 2) + t, *Ek = e_of(t2, (k2 + 2) & 3, j + 2);
-#pragma unroll
-                for (int a = 0; a < 16; a++) d[a] = Dk[kRowElems * a];
-#pragma unroll
-                for (int a = 0; a < 16; a++) e[a] = Ek[256 * a];
-            }
-            radix16_inv(xb);                                        // stage B of j
-            __syncwarp();  // the half-warp has consumed its row: reuse it as the B->C tile (see subfft4096_inv4)
-            {
-                const uint32_t wb = smem_u32(row + c);
-                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wb), "f"(xb[r16(0)].x), "f"(xb[r16(0)].y) : "memory");
-#pragma unroll
-                for (int i = 0; i < 15; i++) {
-                    const int n1 = i + 1;
-                    const float2 v = cmul(xb[r16(n1)], TW_AT(i));
-                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((wb ^ (16u * (n1 & 7))) + 128u * n1), "f"(v.x), "f"(v.y) : "memory");
-                }
-            }
-            __syncwarp();
-            {
-                const uint32_t rb = smem_u32(row + 16 * c + 2 * (c & 7));
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(xb[2 * jj].x), "=f"(xb[2 * jj].y), "=f"(xb[2 * jj + 1].x), "=f"(xb[2 * jj + 1].y)
-                                 : "r"(rb ^ (16u * jj))
-                                 : "memory");
-            }
-#pragma unroll
-            for (int a = 0; a < 16; a++) xa[a] = cmul_conj_a(d[a], e[a]);   // products of j + 2 (search.cpp:471): cover the tile loads
-            radix16_inv(xb);                                        // stage C of j
-            if (k2 == 0) {
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) acc[n2] = xb[r16(n2)];
-            } else {
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(xb[r16(n2)], c_cC[k2][n2], acc[n2]);
-            }
-#undef TW_AT
-            if (k2 == 3) {
-                float P[16];
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) P[n2] = cpower(acc[n2]);
-                warp_reduce_peak_redux(thread_peak_l1(P, t), red_f + 16 * par, red_i + 8 * par, t);
-                par ^= 1;
-            }
-            sp_cta_barrier();
-            j++;
-        }
-        ti = tn;
-    }
-}
-
-__global__ void __launch_bounds__(kSpThreads, 1) k_search_l1_sp(const SearchArgs p)
-{
-    extern __shared__ __align__(1024) unsigned char smem[];
-    SpCtx cx;
-    cx.m = sp_smem_carve(smem);
-    const int t = threadIdx.x;
-    ACQ_TRACE_STAMP(kTrSearchL1, 0);
-    const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(cx.m.red_f + 48), t);
-    cx.bar0 = smem_u32(cx.m.bar);
-    if (t == 0) {
-        mbar_init(cx.bar0, 1);
-        mbar_init(cx.bar0 + 8, 1);
-    }
-    __syncthreads();
-    if (p.wait_prior) pdl_wait();
-    ACQ_TRACE_STAMP(kTrSearchL1, 1);
-    pdl_trigger_search();
-    cx.sd = (int)(gridDim.x % (unsigned)p.n_dop);
-    cx.sw = (int)((gridDim.x / (unsigned)p.n_dop) % (unsigned)p.n_work);
-    cx.sc = (int)(gridDim.x / ((unsigned)p.n_dop * (unsigned)p.n_work));
-    if (blockIdx.x < p.n_tiles) {   // (the launch never has more CTAs than tiles)
-        if (t >= 256) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-            if (t < kSpBarThreads) sp_stage_warp(p, cx, t == 256);
-        } else {
-            asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-            sp_fft_warps(p, cx, t, tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols));
-        }
-    }
-    ACQ_TRACE_STAMP(kTrSearchL1, 2);
-    tmem_free_cta<2 * kTwCols>(tmem_base, t);
-}
-#endif  // ACQ_L1_SP
-
-// k_search_l1_st -- k_search_l1<false> with STAGING WARPS.  In k_search_l1 thread 0 of a CTA issues the next sub-FFT's
-// bulk copies right after the CTA barrier (address arithmetic, proxy fence, expect_tx, two copies) and once per tile merges
-// the warp partials and stores the cell: ncu's warp samples put a third of a sub-FFT period of warp 0 on that path, and the
-// other seven warps wait for it at the next barrier (10 % of all warp samples are barrier stalls).  Here one CTA per SM
-// holds TWO teams of eight FFT warps -- each team is what a CTA of k_search_l1 is, with its own exchange and code-run
-// buffers, mbarrier, tensor-memory columns and named barrier -- plus one staging warp per team that takes part in the
-// team's barrier and does all of the above, so no FFT warp ever leaves the common instruction stream.  Five warpgroups:
-// the four of FFT warps raise their register count to 120 (setmaxnreg), the staging warpgroup drops to 24.
-// Same arithmetic in the same order as k_search_l1<false>: bitwise-equal cells (tested).
-#ifndef ACQ_L1_ST
-#define ACQ_L1_ST 0
-#endif
-#if ACQ_L1_ST
+// Staging warps (k_search_l1_dr below; measured first in the experiment form k_search_l1_st, acq_variants.cuh).  In
+// k_search_l1 thread 0 of a CTA issues the next sub-FFT's bulk copies right after the CTA barrier (address arithmetic, proxy
+// fence, expect_tx, the copies) and once per tile merges the warp partials and stores the cell: ncu's warp samples put a
+// third of a sub-FFT period of warp 0 on that path, and the other seven warps wait for it at the next barrier (10 % of all
+// warp samples were barrier stalls).  Here one CTA per SM holds TWO teams of eight FFT warps -- each team is what a CTA
+// of k_search_l1 is, with its own exchange and code-run buffers, mbarrier, tensor-memory columns and named barrier -- plus
+// one staging warp per team that takes part in the team's barrier and does all of the above, so no FFT warp ever leaves
+// the common instruction stream.  Five warpgroups: the launch allocates 96 registers per thread, the staging warpgroup
+// drops to 32 (setmaxnreg.dec) and the four FFT warpgroups rise to 112 with exactly what it released.
 constexpr int kStThreads = 640, kStTeamBar = 288;   // 2 x 256 FFT threads + a warpgroup of staging warps; team barrier = 8 + 1 warps
-__host__ __device__ constexpr size_t st_team_smem_bytes() { return (fft_smem4_bytes() + 64 * sizeof(float) + 1023) / 1024 * 1024; }
-__host__ __device__ constexpr size_t st_smem_bytes() { return 2 * st_team_smem_bytes(); }
 __device__ __forceinline__ void st_team_barrier(int team)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kStTeamBar) : "memory");
 }
 
-__global__ void __launch_bounds__(kStThreads, 1) k_search_l1_st(const SearchArgs p)
-{
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int t = threadIdx.x;
-    ACQ_TRACE_STAMP(kTrSearchL1, 0);
-    constexpr int L = ACQ_LAGS_L1;
-    __shared__ uint32_t tmem_slot;
-    const uint32_t tmem_base = tmem_alloc_cta<4 * kTwCols>(&tmem_slot, t);
-    if (t < 2) mbar_init(smem_u32(l1_smem_carve(smem + t * st_team_smem_bytes()).s.bar), 1);
-    __syncthreads();
-    if (p.wait_prior) pdl_wait();
-    ACQ_TRACE_STAMP(kTrSearchL1, 1);
-    pdl_trigger_search();
-    // a team strides over the tiles like a CTA of k_search_l1; team 1 takes the tiles after team 0's first ones, so a search of
-    // no more tiles than SMs runs one team per SM
-    const int team = (t < 512) ? (t >> 8) : ((t >> 5) & 1);
-    const unsigned vcta = (unsigned)team * gridDim.x + blockIdx.x, stride = 2u * gridDim.x;
-    const L1Smem m = l1_smem_carve(smem + team * st_team_smem_bytes());
-    const FftSmem4 &s = m.s;
-    const uint32_t bar = smem_u32(s.bar);
-    const int sd = (int)(stride % (unsigned)p.n_dop), sw = (int)((stride / (unsigned)p.n_dop) % (unsigned)p.n_work),
-              sc = (int)(stride / ((unsigned)p.n_dop * (unsigned)p.n_work));
-    if (t >= 512) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        if (t < 576 && vcta < p.n_tiles) {
-            // ---- staging warp of `team` (lane 0 works)
-            const bool lead = (t & 31) == 0;
-            float *red_f = m.red_f;
-            int *red_i = m.red_i;
-            auto issue = [&](const TileIdx &tn, int k2n, int half) {
-                const int r = (k2n - tn.dop) & 3;
-                const int q = (k2n - tn.dop - r) >> 2;
-                const float2 *Dk = p.Dp + d_row(p, tn, 0) * kN + k2n * kSub;
-                const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
-                fence_proxy_async();  // generic-proxy accesses of these buffers (ordered by the team barrier) before the async writes
-                mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
-                tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
-                tma_load_1d(smem_u32(s.S1 + half * kS1pElems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
-            };
-            TileIdx ti(p, vcta);
-            if (lead) issue(ti, 0, 0);
-            int it = 0, par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
-            for (long long tile = vcta; tile < p.n_tiles; tile += stride) {
-                TileIdx tn = ti;
-                const bool more = tile + stride < p.n_tiles;
-                if (more) tn.step(p, sd, sw, sc);
-#pragma unroll 1
-                for (int k2 = 0; k2 < 4; k2++) {
-                    __syncwarp();
-                    st_team_barrier(team);   // every FFT warp is past its operand reads of this sub-FFT and past stage C of the previous one
-                    if (lead) {
-                        if (k2 < 3) issue(ti, k2 + 1, (it + 1) & 1);
-                        else if (more) issue(tn, 0, (it + 1) & 1);
-                        if (k2 == 0 && pend_cap >= 0)   // the previous tile's peak: its warp partials precede this barrier
-                            store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
-                    }
-                    it++;
-                }
-                pend_cap = ti.cap;
-                pend_slot = ti.slot;
-                pend_d = ti.d;
-                par ^= 1;
-                ti = tn;
-            }
-            __syncwarp();
-            st_team_barrier(team);
-            if (lead) {
-                store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
-                __threadfence();  // this team's cells (all stored by this thread) before the CTA's count
-            }
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-        if (vcta < p.n_tiles) {
-            // ---- the eight FFT warps of `team`
-            const int tt = t & 255;
-            float *red_f = m.red_f;
-            int *red_i = m.red_i;
-            const uint32_t tw_taddr = tmem_base + (uint32_t)(team * 2 * kTwCols) + tmem_lane_base(tt) + (uint32_t)((tt >> 7) * kTwCols);
-            subfft4_park_twiddles(p.tables, tw_taddr, tt);
-            float2 bw = __ldg(p.tables + kT2Elems + tt);  // W16384^{4t}: base of residue 0; later bases come from TMEM
-            int it = 0, par = 0;
-            int dop = TileIdx(p, vcta).dop, d = TileIdx(p, vcta).d;
-            for (long long tile = vcta; tile < p.n_tiles; tile += stride) {
-                float P[16];
-                float2 acc[16];
-                float2 x[16];
-#pragma unroll kK2Unroll
-                for (int k2 = 0; k2 < 4; k2++) {
-                    float2 *S1b = s.S1 + (it & 1) * kS1pElems;
-                    {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471), operands from smem
-                        const int r = (k2 - dop) & 3;
-                        const int q = (k2 - dop - r) >> 2;
-                        const float2 *Dk = S1b + tt;
-                        const float2 *Ek = s.E + ((p.Q + q) & 1) + tt;
-                        mbar_wait(bar, (uint32_t)(it & 1));
-#pragma unroll
-                        for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
-                    }
-                    subfft4096_inv4<true>(x, k2, bw, S1b, tt, tw_taddr, [&] { st_team_barrier(team); }, [] {});
-                    it++;
-                    if (k2 == 0) {
-#pragma unroll
-                        for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
-                    } else {
-#pragma unroll
-                        for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
-                    }
-                }
-#pragma unroll
-                for (int n2 = 0; n2 < 16; n2++) P[n2] = cpower(acc[n2]);
-                warp_reduce_peak_redux(thread_peak_l1(P, tt), red_f + 16 * par, red_i + 8 * par, tt);
-                par ^= 1;
-                {   // the Doppler index of this team's next tile (the only tile coordinate an FFT warp needs): d advances by sd mod n_dop
-                    d += sd;
-                    if (d >= p.n_dop) d -= p.n_dop;
-                    const int h = p.dop_lo + d;
-                    const int v = p.half_bin ? (h & 1) : 0;
-                    dop = p.half_bin ? ((h - v) >> 1) : h;
-                }
-            }
-            st_team_barrier(team);   // the last tile's warp partials are in place
-        }
-    }
-    __syncthreads();
-    if (t == 0 && p.ctas_total) atomicAdd(p.ctas_done, 1u);   // both teams' cells are stored and fenced (staging warps, above)
-    ACQ_TRACE_STAMP(kTrSearchL1, 2);
-    tmem_free_cta<4 * kTwCols>(tmem_base, t);
-}
-#if ACQ_L1_ST == 2
 // k_search_l1_dr -- the staging-warp form with the CAPTURE operand resident in tensor memory.  The capture residue D of a
 // sub-FFT depends on (capture, residue k2) only, and a thread always reads the same 16 values of it (D[256 a + t]):
 // 4 residues x 16 complex = the 128 TMEM columns a thread owns.  A team takes a CONTIGUOUS range of tiles (capture-major
@@ -1434,7 +1036,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
                 float P[16];
                 float2 acc[16];
                 float2 x[16];
-#pragma unroll kK2Unroll
+                // rolled: at 112 registers the loop unrolled by two spills (28.75 M against 27.7 M tiles/s on cfg5, measured)
+#pragma unroll 1
                 for (int k2 = 0; k2 < 4; k2++) {
                     float2 *S1b = s.S1 + (it & 1) * kSub;
                     const int r = (k2 - dop) & 3;
@@ -1486,8 +1089,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
     ACQ_TRACE_STAMP(kTrSearchL1, 2);
     tmem_free_cta<4 * kTwCols>(tmem_base, t);
 }
-#endif  // ACQ_L1_ST == 2
-#endif  // ACQ_L1_ST
+
 
 // k_search_l1_multi -- k_noncoh > 1 with the CODE operand resident in tensor memory.  The code run E of a tile depends on
 // (satellite, Doppler, residue k2) but not on the block b, and a thread always reads the same 16 values of it
@@ -2208,7 +1810,8 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
                  threadIdx.x & 31);
 }
 
-#if defined(ACQ_VARIANT_L1_LDG) || defined(ACQ_VARIANT_L1_X3) || defined(ACQ_VARIANT_E1B_LDG)
+#if defined(ACQ_VARIANT_L1_LDG) || defined(ACQ_VARIANT_L1_X3) || defined(ACQ_VARIANT_E1B_LDG) || defined(ACQ_VARIANT_L1_SP) || \
+    defined(ACQ_VARIANT_L1_ST)
 #include "acq_variants.cuh"  // A/B forms: experiment builds only (tools/build_variants.py)
 #endif
 
@@ -2366,14 +1969,12 @@ cudaError_t search_kernels_configure()
     cudaError_t e;
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
-#if ACQ_L1_SP
+    if ((e = cudaFuncSetAttribute(k_search_l1_dr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dr_smem_bytes()))) return e;
+#ifdef ACQ_VARIANT_L1_SP
     if ((e = cudaFuncSetAttribute(k_search_l1_sp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem_bytes()))) return e;
 #endif
-#if ACQ_L1_ST
+#ifdef ACQ_VARIANT_L1_ST
     if ((e = cudaFuncSetAttribute(k_search_l1_st, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem_bytes()))) return e;
-#endif
-#if ACQ_L1_ST == 2
-    if ((e = cudaFuncSetAttribute(k_search_l1_dr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dr_smem_bytes()))) return e;
 #endif
 #ifdef ACQ_VARIANT_L1_MULTI_TW
     if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
@@ -2463,14 +2064,24 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
 
 // Grid of a search launch = the number of its CTAs that store cells (clusters: rank 0 stores for its cluster).
 // launch_search* and the host's SearchArgs::ctas_total both come from here.
+// Which C/A search kernel a search runs: non-coherent sums -> k_search_l1_multi; K = 1 on full bins -> k_search_l1_dr
+// (the capture spectrum, the same for every Doppler index of a capture, stays in tensor memory); K = 1 on half-bins ->
+// k_search_l1<false> (odd and even half-bins read different capture spectra, so nothing could stay resident).
+#ifndef ACQ_FORCE_L1_CTA
+#define ACQ_FORCE_L1_CTA 0   // variant l1_cta: always k_search_l1<false> for K = 1 (the kernel-equivalence tests)
+#endif
+int search_kind_l1(int K, int half_bin)
+{
+    if (K > 1) return kSearchL1Multi;
+    return (half_bin || ACQ_FORCE_L1_CTA) ? kSearchL1 : kSearchL1Dr;
+}
+
 int search_grid_ctas(long long n_tiles, int kind, int sm_count)
 {
     if (n_tiles <= 0 || n_tiles > kMaxTilesPerLaunch) return 0;
     long long cap = (long long)sm_count * 2;  // two persistent CTAs per SM
     if (kind == kSearchE1bCluster) cap = sm_count / 4;
-#if ACQ_L1_SP || ACQ_L1_ST
-    if (kind == kSearchL1) cap = sm_count;   // one CTA per SM (k_search_l1_st: two teams in it)
-#endif
+    if (kind == kSearchL1Dr) cap = sm_count;   // one CTA per SM, two teams in it
 #ifdef ACQ_VARIANT_L1_X3
     if (kind == kSearchL1) cap = (long long)sm_count * 3;
 #endif
@@ -2479,7 +2090,8 @@ int search_grid_ctas(long long n_tiles, int kind, int sm_count)
 
 int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, bool pdl)
 {
-    const int grid = search_grid_ctas(a.n_tiles, e1b ? kSearchE1b : (a.K > 1 ? kSearchL1Multi : kSearchL1), sm_count);
+    const int kind = e1b ? kSearchE1b : search_kind_l1(a.K, a.half_bin);
+    const int grid = search_grid_ctas(a.n_tiles, kind, sm_count);
     if (grid <= 0) return 0;
     if (e1b) {
 #ifdef ACQ_VARIANT_E1B_LDG
@@ -2499,15 +2111,13 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
     launch_k(a.K > 1 ? k_search_l1<true> : k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #else
     if (a.K > 1) launch_k(k_search_l1_multi, grid, 256, l1_multi_smem_bytes(), st, pdl, a);
-#if ACQ_L1_SP
-    else launch_k(k_search_l1_sp, grid, kSpThreads, sp_smem_bytes(), st, pdl, a);
-#elif ACQ_L1_ST == 2
-    else launch_k(k_search_l1_dr, grid, kStThreads, dr_smem_bytes(), st, pdl, a);
-#elif ACQ_L1_ST
-    else launch_k(k_search_l1_st, grid, kStThreads, st_smem_bytes(), st, pdl, a);
-#else
-    else launch_k(k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
+#if defined(ACQ_VARIANT_L1_SP)
+    else if (kind == kSearchL1Dr) launch_k(k_search_l1_sp, grid, kSpThreads, sp_smem_bytes(), st, pdl, a);
+#elif defined(ACQ_VARIANT_L1_ST)
+    else if (kind == kSearchL1Dr) launch_k(k_search_l1_st, grid, kStThreads, st_smem_bytes(), st, pdl, a);
 #endif
+    else if (kind == kSearchL1Dr) launch_k(k_search_l1_dr, grid, kStThreads, dr_smem_bytes(), st, pdl, a);
+    else launch_k(k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #endif
     return 1;
 }

@@ -116,10 +116,10 @@ def test_product_library_reads_no_environment_and_holds_no_experiment_kernels():
         assert "getenv" not in open(os.path.join(csrc, f)).read(), f
     syms = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
     # (the statically linked CUDA runtime imports getenv for its own CUDA_* variables: only the sources can be checked)
-    for k in ("k_search_l1_ldg", "k_search_l1_x3", "k_search_e1b_ldg"):
+    for k in ("k_search_l1_ldg", "k_search_l1_x3", "k_search_e1b_ldg", "k_search_l1_sp", "k_search_l1_st"):
         assert k not in syms, k
     sass = subprocess.run(["cuobjdump", "-elf", _lib.lib_path()], capture_output=True, text=True).stdout
-    for k in ("k_search_l1_ldg", "k_search_l1_x3", "k_search_e1b_ldg"):
+    for k in ("k_search_l1_ldg", "k_search_l1_x3", "k_search_e1b_ldg", "k_search_l1_sp", "k_search_l1_st"):
         assert k not in sass, k
     assert "k_search_l1" in sass and "k_search_e1b" in sass and "k_pick_small" in sass
 

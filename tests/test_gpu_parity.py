@@ -826,6 +826,38 @@ def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle):
         assert (ga[0] == ga[-1]).all()
 
 
+def test_capture_resident_kernel_equals_cta_kernel(gpu_required, oracle):
+    """k_search_l1_dr (the K = 1 full-bin product kernel: one CTA per SM, two teams of FFT warps with a staging warp each,
+    contiguous tile ranges, the capture residue parked in tensor memory for all tiles of a capture) against
+    k_search_l1<false> (two CTAs per SM striding over the tiles, both operands staged per sub-FFT; variant library l1_cta):
+    the same arithmetic in the same order, so the whole per-Doppler table is bitwise equal.  Shapes: one capture (every team
+    starts inside the capture), 40 captures (capture boundaries inside team ranges), 600 two-tile captures (several
+    boundaries per range, alternating captures so that a residue left over from the neighbour would show), fewer tiles than
+    SMs (one team per SM), a single tile."""
+    table = S.navstar()
+    cap = synth.make_capture(3, 1, table, scenarios.signals("cfg1", 3))
+    cap2 = synth.make_capture(5, 1, table, scenarios.signals("cfg1", 5))
+    cases = [({}, [cap], None), ({}, [cap, cap2] * 20, None),
+             (dict(dop_lo=3, dop_hi=4), [cap, cap2] * 300, np.array([2], np.int32)),
+             (dict(dop_lo=-3, dop_hi=1), [cap2], np.array([2], np.int32)),
+             (dict(dop_lo=0, dop_hi=0), [cap], np.array([6], np.int32)),
+             (dict(dop_lo=-20, dop_hi=20), [cap2, cap], np.array([2, 6, 10, 13, 18], np.int32))]
+    for kw, caps, sel in cases:
+        out = {}
+        for kind, variant in (("dr", None), ("cta", "l1_cta")):
+            with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
+                out[kind] = eng.search(np.concatenate(caps), sel=sel, want_grid=True)
+        (ra, ga), (rb, gb) = out["dr"], out["cta"]
+        for f in ("peak", "lag", "noise", "snr"):
+            assert np.array_equal(ga[f], gb[f]), (kw, len(caps), f)
+        assert ra.tobytes() == rb.tobytes()
+    # half-bin K = 1 searches stay on k_search_l1<false> (odd and even half-bins read different capture spectra)
+    with F.AcqEngine(table, F.default_params(half_bin=1, dop_lo=-9, dop_hi=9)) as eng:
+        rec, grid = eng.search(cap, want_grid=True)
+    orec, ogrid = oracle.search(cap, table, params=oracle.default_params(half_bin=1, dop_lo=-9, dop_hi=9), want_grid=True)
+    compare_records(rec[0], orec, ogrid, -9, 16.0, ggrid=grid[0], max_ties=1)
+
+
 def test_code_resident_multi_kernel_equals_twiddle_resident_kernel(gpu_required, oracle):
     """k_search_l1_multi (K > 1: the tile's code run parked in tensor memory after block 0, stage-B twiddles from a
     shared-memory table) against k_search_l1<true> (twiddles in tensor memory, code run staged for every block; variant
