@@ -55,6 +55,7 @@ def build(force=False, verbose=False, defines=(), out=None):
 # library contains none of this code and reads no environment variable.
 VARIANTS = {
     "l1_multi_tw": ["ACQ_VARIANT_L1_MULTI_TW"],  # K > 1 C/A search with the twiddles (not the code run) in tensor memory
+    "l1_mst": ["ACQ_VARIANT_L1_MST"],        # K > 1 C/A search in the two-team form with staging warps (measured: no gain)
     "l1_cta": ["ACQ_FORCE_L1_CTA=1"],        # K = 1 C/A search always by k_search_l1<false> (two CTAs per SM, thread 0 stages)
     "l1_sp": ["ACQ_VARIANT_L1_SP"],          # K = 1 C/A search software-pipelined across sub-FFTs, one CTA per SM (measured: -3.7 %)
     "l1_st": ["ACQ_VARIANT_L1_ST"],          # staging warps only (capture residue still staged per sub-FFT): +1.9 %

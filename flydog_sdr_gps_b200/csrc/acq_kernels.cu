@@ -896,10 +896,44 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 // one staging warp per team that takes part in the team's barrier and does all of the above, so no FFT warp ever leaves
 // the common instruction stream.  Five warpgroups: the launch allocates 96 registers per thread, the staging warpgroup
 // drops to 32 (setmaxnreg.dec) and the four FFT warpgroups rise to 112 with exactly what it released.
-constexpr int kStThreads = 640, kStTeamBar = 288;   // 2 x 256 FFT threads + a warpgroup of staging warps; team barrier = 8 + 1 warps
-__device__ __forceinline__ void st_team_barrier(int team)
+constexpr int kStThreads = 640, kStHandOver = 288;   // 2 x 256 FFT threads + a warpgroup of staging warps; hand-over = 8 + 1 warps
+// Named barriers of a team (ids 1..3 for team 0, 4..6 for team 1):
+//   A (256 threads): the FFT warps' own barrier, one per sub-FFT;
+//   B (288): hand-over to the staging warp.  Every FFT warp ARRIVES (no wait) just before it waits on A, and the staging
+//      warp SYNCs: it runs on once all eight have reached this sub-FFT's barrier, i.e. are past their operand reads of this
+//      sub-FFT and past stage C of the one before, and stages the next sub-FFT's operands.  An FFT warp cannot reach the
+//      next sub-FFT's barrier before the staging warp has passed (that sub-FFT's operands are staged only after it), so
+//      the phases of B cannot mix;
+//   C (288): the same hand-over once more after a team's last sub-FFT (the last tile's warp partials are in place).
+// All waiting participants of a barrier execute the same instruction: compute-sanitizer's synccheck rejects a bar.sync
+// reached from two code locations (tools/exp/mb_namedbar.cu), which rules out the simplest form -- the staging warp inside
+// barrier A, one barrier instruction per FFT warp: 5.84 ms on cfg5 with 128 captures, against 5.97 ms for this form,
+// 6.02 ms with the arrive moved up behind the products, 6.18 ms with one warp arriving after A, 6.29 ms with the staging
+// warp polling a shared-memory mbarrier, and 6.30 ms for k_search_l1<false>.
+__device__ __forceinline__ void st_fft_sync(int team)         // barrier A
 {
-    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kStTeamBar) : "memory");
+    if (team == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 4, 256;" ::: "memory");
+}
+__device__ __forceinline__ void st_fft_arrive(int team)       // barrier B, FFT warps
+{
+    if (team == 0) asm volatile("bar.arrive 2, %0;" ::"n"(kStHandOver) : "memory");
+    else asm volatile("bar.arrive 5, %0;" ::"n"(kStHandOver) : "memory");
+}
+__device__ __forceinline__ void st_fft_done(int team)         // barrier C, FFT warps
+{
+    if (team == 0) asm volatile("bar.arrive 3, %0;" ::"n"(kStHandOver) : "memory");
+    else asm volatile("bar.arrive 6, %0;" ::"n"(kStHandOver) : "memory");
+}
+__device__ __forceinline__ void st_stage_wait(int team)       // barrier B, staging warp
+{
+    if (team == 0) asm volatile("bar.sync 2, %0;" ::"n"(kStHandOver) : "memory");
+    else asm volatile("bar.sync 5, %0;" ::"n"(kStHandOver) : "memory");
+}
+__device__ __forceinline__ void st_stage_wait_done(int team)  // barrier C, staging warp
+{
+    if (team == 0) asm volatile("bar.sync 3, %0;" ::"n"(kStHandOver) : "memory");
+    else asm volatile("bar.sync 6, %0;" ::"n"(kStHandOver) : "memory");
 }
 
 // k_search_l1_dr -- the staging-warp form with the CAPTURE operand resident in tensor memory.  The capture residue D of a
@@ -988,7 +1022,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
 #pragma unroll 1
                 for (int k2 = 0; k2 < 4; k2++) {
                     __syncwarp();
-                    st_team_barrier(team);   // every FFT warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                    st_stage_wait(team);   // every FFT warp is past its operand reads of this sub-FFT and past stage C of the previous one
                     if (lead) {
                         if (k2 < 3) issue(ti, fresh, k2 + 1, (it + 1) & 1);
                         else if (more) issue(tn, fresh_n, 0, (it + 1) & 1);
@@ -1005,7 +1039,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
                 fresh = fresh_n;
             }
             __syncwarp();
-            st_team_barrier(team);
+            st_stage_wait_done(team);   // the last tile's warp partials are in place
             if (lead) {
                 store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
                 __threadfence();  // this team's cells (all stored by this thread) before the CTA's count
@@ -1031,7 +1065,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
             int d = t0.d, dop = t0.dop;
             unsigned left = per_cap - tile0 % per_cap;   // tiles of this team's range before the next capture begins
             bool fresh = true;
-            asm volatile("bar.sync %0, 256;" ::"r"(team + 3) : "memory");   // the twiddle table is in place (FFT warps only)
+            st_fft_sync(team);   // the twiddle table is in place
             for (unsigned i = 0; i < my_tiles; i++) {
                 float P[16];
                 float2 acc[16];
@@ -1058,7 +1092,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
                     // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471)
 #pragma unroll
                     for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(x[a], Ek[256 * a]);
-                    subfft4096_inv4s(x, k2, bw, S1b, tt, s.T2, BaseFromGlobal{bases}, [&] { st_team_barrier(team); }, [] {});
+                    subfft4096_inv4s(x, k2, bw, S1b, tt, s.T2, BaseFromGlobal{bases}, [&] { st_fft_arrive(team); st_fft_sync(team); }, [] {});
                     it++;
                     if (k2 == 0) {
 #pragma unroll
@@ -1081,7 +1115,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
                     if (fresh) left = per_cap;
                 }
             }
-            st_team_barrier(team);   // the last tile's warp partials are in place
+            st_fft_done(team);   // the last tile's warp partials are in place
         }
     }
     __syncthreads();
@@ -1811,7 +1845,7 @@ __global__ void __launch_bounds__(128) k_best_dop(const acq_cell *__restrict__ c
 }
 
 #if defined(ACQ_VARIANT_L1_LDG) || defined(ACQ_VARIANT_L1_X3) || defined(ACQ_VARIANT_E1B_LDG) || defined(ACQ_VARIANT_L1_SP) || \
-    defined(ACQ_VARIANT_L1_ST)
+    defined(ACQ_VARIANT_L1_ST) || defined(ACQ_VARIANT_L1_MST)
 #include "acq_variants.cuh"  // A/B forms: experiment builds only (tools/build_variants.py)
 #endif
 
@@ -1970,6 +2004,9 @@ cudaError_t search_kernels_configure()
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_l1_dr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dr_smem_bytes()))) return e;
+#ifdef ACQ_VARIANT_L1_MST
+    if ((e = cudaFuncSetAttribute(k_search_l1_mst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dr_smem_bytes()))) return e;
+#endif
 #ifdef ACQ_VARIANT_L1_SP
     if ((e = cudaFuncSetAttribute(k_search_l1_sp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem_bytes()))) return e;
 #endif
@@ -2072,6 +2109,12 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
 #endif
 int search_kind_l1(int K, int half_bin)
 {
+#if defined(ACQ_VARIANT_L1_X3) || defined(ACQ_VARIANT_L1_LDG) || defined(ACQ_VARIANT_L1_MULTI_TW)
+    return kSearchL1;   // these experiment builds run every C/A search on their own 256-thread kernels
+#endif
+#ifdef ACQ_VARIANT_L1_MST
+    if (K > 1) return kSearchL1Mst;
+#endif
     if (K > 1) return kSearchL1Multi;
     return (half_bin || ACQ_FORCE_L1_CTA) ? kSearchL1 : kSearchL1Dr;
 }
@@ -2081,7 +2124,7 @@ int search_grid_ctas(long long n_tiles, int kind, int sm_count)
     if (n_tiles <= 0 || n_tiles > kMaxTilesPerLaunch) return 0;
     long long cap = (long long)sm_count * 2;  // two persistent CTAs per SM
     if (kind == kSearchE1bCluster) cap = sm_count / 4;
-    if (kind == kSearchL1Dr) cap = sm_count;   // one CTA per SM, two teams in it
+    if (kind == kSearchL1Dr || kind == kSearchL1Mst) cap = sm_count;   // one CTA per SM, two teams in it
 #ifdef ACQ_VARIANT_L1_X3
     if (kind == kSearchL1) cap = (long long)sm_count * 3;
 #endif
@@ -2110,6 +2153,10 @@ int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, 
 #elif defined(ACQ_VARIANT_L1_MULTI_TW)   // the K > 1 form that keeps the stage-B twiddles (not the code run) in tensor memory
     launch_k(a.K > 1 ? k_search_l1<true> : k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #else
+#ifdef ACQ_VARIANT_L1_MST
+    if (kind == kSearchL1Mst) launch_k(k_search_l1_mst, grid, kStThreads, dr_smem_bytes(), st, pdl, a);
+    else
+#endif
     if (a.K > 1) launch_k(k_search_l1_multi, grid, 256, l1_multi_smem_bytes(), st, pdl, a);
 #if defined(ACQ_VARIANT_L1_SP)
     else if (kind == kSearchL1Dr) launch_k(k_search_l1_sp, grid, kSpThreads, sp_smem_bytes(), st, pdl, a);

@@ -66,7 +66,7 @@ int launch_pick_small(const acq_cell *cells, const int *slot_sat, acq_record *ou
                       unsigned *host_flag, unsigned epoch, int n_rows, int n_slots, int n_dop, int dop_lo, cudaStream_t st,
                       bool pdl = false);
 // CTAs of a search launch that store cells (what SearchArgs::ctas_total sums over the launches of one search)
-enum { kSearchL1 = 0, kSearchE1b = 1, kSearchE1bCluster = 2, kSearchL1Multi = 3, kSearchL1Dr = 4 };
+enum { kSearchL1 = 0, kSearchE1b = 1, kSearchE1bCluster = 2, kSearchL1Multi = 3, kSearchL1Dr = 4, kSearchL1Mst = 5 };
 int search_kind_l1(int K, int half_bin);   // which C/A search kernel (and so which grid) a search uses
 constexpr int kPickSmallRowsMax = 256;  // rows k_pick_small stages in shared memory
 // A record as k_pick_small hands it to a POLLING host (mapped pinned memory): two 16-byte halves, each carrying the

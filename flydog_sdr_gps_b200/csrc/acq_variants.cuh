@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_st(const SearchArgs
 #pragma unroll 1
                 for (int k2 = 0; k2 < 4; k2++) {
                     __syncwarp();
-                    st_team_barrier(team);   // every FFT warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                    st_stage_wait(team);   // every FFT warp is past its operand reads of this sub-FFT and past stage C of the previous one
                     if (lead) {
                         if (k2 < 3) issue(ti, k2 + 1, (it + 1) & 1);
                         else if (more) issue(tn, 0, (it + 1) & 1);
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_st(const SearchArgs
                 ti = tn;
             }
             __syncwarp();
-            st_team_barrier(team);
+            st_stage_wait_done(team);
             if (lead) {
                 store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
                 __threadfence();  // this team's cells (all stored by this thread) before the CTA's count
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_st(const SearchArgs
 #pragma unroll
                         for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[kRowElems * a], Ek[256 * a]);
                     }
-                    subfft4096_inv4<true>(x, k2, bw, S1b, tt, tw_taddr, [&] { st_team_barrier(team); }, [] {});
+                    subfft4096_inv4<true>(x, k2, bw, S1b, tt, tw_taddr, [&] { st_fft_arrive(team); st_fft_sync(team); }, [] {});
                     it++;
                     if (k2 == 0) {
 #pragma unroll
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_st(const SearchArgs
                     dop = p.half_bin ? ((h - v) >> 1) : h;
                 }
             }
-            st_team_barrier(team);   // the last tile's warp partials are in place
+            st_fft_done(team);   // the last tile's warp partials are in place
         }
     }
     __syncthreads();
@@ -722,3 +722,164 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_st(const SearchArgs
     tmem_free_cta<4 * kTwCols>(tmem_base, t);
 }
 #endif  // ACQ_VARIANT_L1_ST
+
+// k_search_l1_mst -- k_search_l1_multi in the two-team form with staging warps (see k_search_l1_dr): a team is what a CTA
+// of k_search_l1_multi is (code run parked in tensor memory after block 0, stage-B twiddles from a shared table), its
+// staging warp issues the bulk copies -- D for every block, E for block 0 -- and stores the cells.  Teams stride over the
+// tiles like the CTAs of k_search_l1_multi.  Same arithmetic in the same order: bitwise-equal cells (tested).
+// Measured (cfg2, same box): 3.660 ms against 3.649 ms for k_search_l1_multi -- no gain: at 112 registers the block powers
+// P[16] spill, and K = 20 blocks per tile leave thread 0's per-tile work little weight.  Experiment builds only.
+#ifdef ACQ_VARIANT_L1_MST
+__global__ void __launch_bounds__(kStThreads, 1) k_search_l1_mst(const SearchArgs p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int t = threadIdx.x;
+    ACQ_TRACE_STAMP(kTrSearchL1, 0);
+    constexpr int L = ACQ_LAGS_L1;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t tmem_base = tmem_alloc_cta<4 * kTwCols>(&tmem_slot, t);
+    if (t < 2) mbar_init(smem_u32(dr_smem_carve(smem + t * dr_team_smem_bytes()).bar), 1);
+    __syncthreads();
+    if (p.wait_prior) pdl_wait();
+    ACQ_TRACE_STAMP(kTrSearchL1, 1);
+    pdl_trigger_search();
+    const int team = (t < 512) ? (t >> 8) : ((t >> 5) & 1);
+    const unsigned vcta = (unsigned)team * gridDim.x + blockIdx.x, stride = 2u * gridDim.x;
+    const DrSmem s = dr_smem_carve(smem + team * dr_team_smem_bytes());
+    const uint32_t bar = smem_u32(s.bar);
+    const int sd = (int)(stride % (unsigned)p.n_dop), sw = (int)((stride / (unsigned)p.n_dop) % (unsigned)p.n_work),
+              sc = (int)(stride / ((unsigned)p.n_dop * (unsigned)p.n_work));
+    if (t >= 512) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (t < 576 && vcta < p.n_tiles) {
+            // ---- staging warp of `team` (lane 0 works)
+            const bool lead = (t & 31) == 0;
+            float *red_f = s.red_f;
+            int *red_i = s.red_i;
+            auto issue = [&](const TileIdx &tn, int bn, int k2n, int half) {   // D always, E for block 0
+                const float2 *Dk = p.Dp + d_row(p, tn, bn) * kN + k2n * kSub;
+                fence_proxy_async();  // generic-proxy accesses of these buffers (ordered by the team barrier) before the async writes
+                if (bn == 0) {
+                    const int r = (k2n - tn.dop) & 3;
+                    const int q = (k2n - tn.dop - r) >> 2;
+                    const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
+                    mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kSub + kEBufElems)));
+                    tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+                } else {
+                    mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * kSub));
+                }
+                tma_load_1d(smem_u32(s.S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+            };
+            TileIdx ti(p, vcta);
+            if (lead) issue(ti, 0, 0, 0);
+            int it = 0, par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
+            for (long long tile = vcta; tile < p.n_tiles; tile += stride) {
+                TileIdx tn = ti;
+                const bool more = tile + stride < p.n_tiles;
+                if (more) tn.step(p, sd, sw, sc);
+                for (int b = 0; b < p.K; b++) {
+#pragma unroll 1
+                    for (int k2 = 0; k2 < 4; k2++) {
+                        __syncwarp();
+                        st_stage_wait(team);   // every FFT warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                        if (lead) {
+                            if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
+                            else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
+                            else if (more) issue(tn, 0, 0, (it + 1) & 1);
+                            if (b == 0 && k2 == 0 && pend_cap >= 0)   // the previous tile's peak: its warp partials precede this barrier
+                                store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
+                        }
+                        it++;
+                    }
+                }
+                pend_cap = ti.cap;
+                pend_slot = ti.slot;
+                pend_d = ti.d;
+                par ^= 1;
+                ti = tn;
+            }
+            __syncwarp();
+            st_stage_wait_done(team);
+            if (lead) {
+                store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
+                __threadfence();  // this team's cells (all stored by this thread) before the CTA's count
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        if (vcta < p.n_tiles) {
+            // ---- the eight FFT warps of `team`
+            const int tt = t & 255;
+            float *red_f = s.red_f;
+            int *red_i = s.red_i;
+            const uint32_t e_taddr = tmem_base + (uint32_t)(team * 2 * kTwCols) + tmem_lane_base(tt) + (uint32_t)((tt >> 7) * kTwCols);  // [k2][16 complex]
+            {   // stage-B twiddle table into this team's shared memory
+                const float4 *src = reinterpret_cast<const float4 *>(p.tables);
+                float4 *dst = reinterpret_cast<float4 *>(s.T2);
+                for (int i = tt; i < kT2Elems / 2; i += 256) dst[i] = __ldg(src + i);
+            }
+            const float2 *bases = p.tables + kT2Elems + tt;  // [k2][256]: W16384^{4t+k2}
+            float2 bw = __ldg(bases);
+            int it = 0, par = 0;
+            const TileIdx t0(p, vcta);
+            int d = t0.d, dop = t0.dop;
+            st_fft_sync(team);   // the twiddle table is in place
+            for (long long tile = vcta; tile < p.n_tiles; tile += stride) {
+                float P[16];
+                float2 acc[16];
+                for (int b = 0; b < p.K; b++) {
+                    float2 x[16];
+#pragma unroll 1
+                    for (int k2 = 0; k2 < 4; k2++) {
+                        float2 *S1b = s.S1 + (it & 1) * kSub;
+                        const float2 *Dk = S1b + tt;
+                        if (b == 0) {   // E from the staged run; park this thread's 16 values for the blocks to come
+                            const int r = (k2 - dop) & 3;
+                            const int q = (k2 - dop - r) >> 2;
+                            const float2 *Ek = s.E + ((p.Q + q) & 1) + tt;
+                            mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+                            for (int a = 0; a < 16; a++) x[a] = Ek[256 * a];
+                            tmem_st16(e_taddr + 32 * k2, x);
+                            tmem_wait_st();
+                        } else {
+                            tmem_ld16(e_taddr + 32 * k2, x);
+                            mbar_wait(bar, (uint32_t)(it & 1));
+                            tmem_wait_ld();
+                        }
+                        // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471)
+#pragma unroll
+                        for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], x[a]);
+                        subfft4096_inv4s(x, k2, bw, S1b, tt, s.T2, BaseFromGlobal{bases}, [&] { st_fft_arrive(team); st_fft_sync(team); }, [] {});
+                        it++;
+                        if (k2 == 0) {
+#pragma unroll
+                            for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
+                        } else {
+#pragma unroll
+                            for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
+                        }
+                    }
+                    // block b was delayed by 16*b samples in the front end (k_front_end), so lag n lines up across blocks
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) P[n2] = (b == 0) ? cpower(acc[n2]) : (P[n2] + cpower(acc[n2]));
+                }
+                warp_reduce_peak(thread_peak_l1(P, tt), red_f + 16 * par, red_i + 8 * par, tt);
+                par ^= 1;
+                {   // the Doppler index of this team's next tile (the only tile coordinate an FFT warp needs)
+                    d += sd;
+                    if (d >= p.n_dop) d -= p.n_dop;
+                    const int h = p.dop_lo + d;
+                    const int v = p.half_bin ? (h & 1) : 0;
+                    dop = p.half_bin ? ((h - v) >> 1) : h;
+                }
+            }
+            st_fft_done(team);   // the last tile's warp partials are in place
+        }
+    }
+    __syncthreads();
+    if (t == 0 && p.ctas_total) atomicAdd(p.ctas_done, 1u);   // both teams' cells are stored and fenced (staging warps, above)
+    ACQ_TRACE_STAMP(kTrSearchL1, 2);
+    tmem_free_cta<4 * kTwCols>(tmem_base, t);
+}
+#endif  // ACQ_VARIANT_L1_MST

@@ -868,13 +868,17 @@ def test_code_resident_multi_kernel_equals_twiddle_resident_kernel(gpu_required,
              (dict(dop_lo=-7, dop_hi=30, k_noncoh=3, thr_l1=8.0), synth.make_capture(27, 3, table, scenarios.signals("cfg1", 7)), 3)]
     for kw, cap, reps in cases:
         out = {}
-        for kind, variant in (("code", None), ("tw", "l1_multi_tw")):
+        # product: k_search_l1_multi; l1_mst: its two-team form with staging warps (experiment, no gain); l1_multi_tw:
+        # k_search_l1<true>
+        for kind, variant in (("code", None), ("cta", "l1_mst"), ("tw", "l1_multi_tw")):
             with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
                 out[kind] = eng.search(np.concatenate([cap] * reps), want_grid=True)
-        (ra, ga), (rb, gb) = out["code"], out["tw"]
-        for f in ("peak", "lag", "noise", "snr"):
-            assert np.array_equal(ga[f], gb[f]), f
-        assert ra.tobytes() == rb.tobytes()
+        (ra, ga) = out["code"]
+        for other in ("cta", "tw"):
+            rb, gb = out[other]
+            for f in ("peak", "lag", "noise", "snr"):
+                assert np.array_equal(ga[f], gb[f]), (other, f)
+            assert ra.tobytes() == rb.tobytes(), other
         assert (ga[0] == ga[-1]).all()
 
 

@@ -26,7 +26,7 @@ with F.AcqEngine(table, F.default_params(**kw)) as eng:
     r4 = eng.search(cap2, sel=sel); f4 = eng.refine(r4)
 print("ok", r["snr"], r3["snr"], f["dop_hz"], r4["snr"], f4["dop_hz"], r6["snr"])
 P
-for tool in memcheck racecheck synccheck initcheck; do
+for tool in ${TOOLS:-memcheck racecheck synccheck initcheck}; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > $out/$tool.log 2>&1
   echo "$tool rc=$? $(grep -c 'ERROR SUMMARY' $out/$tool.log) $(grep 'ERROR SUMMARY\|RACECHECK SUMMARY' $out/$tool.log | tail -1)"
 done
