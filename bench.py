@@ -568,7 +568,11 @@ def main():
             e2 = T.wall(lambda: e.search_ptr(h_in.data_ptr(), 1, h_out.data_ptr()), steps_c, 3)
             ent["device_equals_host_path"] = bool(torch.equal(d_out.cpu(), h_out))
             ent["e2e"] = {"value": cells_c / (e2 * 1e-3), "unit": UNIT, "ms_per_step": e2, "h2d_bytes_per_step": int(cap.size),
-                          "d2h_bytes_per_step": len(tb) * 24, "api": "acq_search (C ABI, host buffers)"}
+                          "d2h_bytes_per_step": len(tb) * 24,
+                          "api": "acq_search (C ABI, host buffers)" + (
+                              ": the 8 KiB capture travels host -> device as the front-end kernel's argument, the records "
+                              "come back through mapped pinned memory" if cap.size == 8192 else
+                              ": pinned staging + H2D copy node, records through mapped pinned memory")}
             ent["sharding"] = "single GPU"
             e.set_profiling(True)
             km = []

@@ -57,6 +57,7 @@ VARIANTS = {
     "l1_multi_tw": ["ACQ_VARIANT_L1_MULTI_TW"],  # K > 1 C/A search with the twiddles (not the code run) in tensor memory
     "l1_mst": ["ACQ_VARIANT_L1_MST"],        # K > 1 C/A search in the two-team form with staging warps (measured: no gain)
     "l1_cta": ["ACQ_FORCE_L1_CTA=1"],        # K = 1 C/A search always by k_search_l1<false> (two CTAs per SM, thread 0 stages)
+    "l1_dr_all": ["ACQ_DR_MIN_TILES_PER_SM=0"],  # K = 1 full-bin C/A search by k_search_l1_dr at every size (the product: from 12 tiles per SM)
     "l1_sp": ["ACQ_VARIANT_L1_SP"],          # K = 1 C/A search software-pipelined across sub-FFTs, one CTA per SM (measured: -3.7 %)
     "l1_st": ["ACQ_VARIANT_L1_ST"],          # staging warps only (capture residue still staged per sub-FFT): +1.9 %
     "l1_ldg": ["ACQ_VARIANT_L1_LDG"],        # C/A search, operands straight from L2
@@ -69,6 +70,9 @@ VARIANTS = {
     "pdl0": ["ACQ_FORCE_PDL=0"],
     "pdl1": ["ACQ_FORCE_PDL=1"],
     "zcin": ["ACQ_ZC_INPUT=1"],              # front end reads small captures from mapped pinned memory (no H2D copy node)
+    "static_tiles": ["ACQ_DYN_MIN_ROUNDS=1000000000"],  # strided search kernels always on the static stride (the product: tiles claimed from a counter from 6 rounds up)
+    "dyn_tiles": ["ACQ_DYN_MIN_ROUNDS=0"],    # ... always claiming
+    "argin0": ["ACQ_ARG_INPUT=0"],           # single-block captures through the staging buffer + copy node (the product: kernel argument)
     "devrec": ["ACQ_HOST_RECORDS=0"],        # records through device memory + copy, stream wait (no mapped memory, no polling)
 }
 

@@ -114,6 +114,7 @@ struct acq_engine {
     float2 *d_x2 = nullptr, *d_Dp = nullptr;
     acq_cell *d_cells = nullptr;
     acq_record *d_records = nullptr;
+    unsigned *d_tile_ctr = nullptr;    // [2] claim counters of the C/A and the E1B search launch (SearchArgs::tile_ctr); zero between launches
     unsigned *d_ctas_done = nullptr;   // finished search CTAs of a small search (folded best-Doppler pick); zero between searches
     unsigned epoch = 0;                // search counter: value of the completion word
     // host path: pinned staging of small captures; records and the completion word in mapped pinned memory,
@@ -164,6 +165,11 @@ using namespace acq;
 #ifndef ACQ_ZC_INPUT
 #define ACQ_ZC_INPUT 0
 #endif
+//   ACQ_ARG_INPUT=1|0        a search of ONE 1-bit block: the capture travels as the front end's kernel argument (1) or by
+//                            the staging buffer and a copy node like every other search (0, variant "argin0")
+#ifndef ACQ_ARG_INPUT
+#define ACQ_ARG_INPUT 1
+#endif
 // Host path, small searches: the capture goes through an engine-owned pinned staging buffer (a pageable source would
 // make cudaMemcpyAsync synchronous), the kernels write the records straight into mapped pinned memory, and the host
 // polls a completion word there instead of waiting for the stream.  Above these sizes: plain copies and a stream wait.
@@ -192,6 +198,7 @@ int free_engine(acq_engine *e)
     cudaFree(e->d_cells);
     cudaFree(e->d_records);
     cudaFree(e->d_ctas_done);
+    cudaFree(e->d_tile_ctr);
     cudaFree(e->d_work_full);
     cudaFree(e->d_work_single);
     cudaFree(e->d_work);
@@ -363,7 +370,7 @@ int set_selection(acq_engine *e, const int32_t *sel, int n_sel)
 // device.  records_dev: where the kernels write the records (device memory, or the device alias of mapped host memory);
 // flag_dev: mapped completion word, or NULL.
 int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq_record *records_dev, unsigned *flag_dev,
-                   cudaStream_t st)
+                   cudaStream_t st, const uint8_t *packed_host_arg = nullptr)
 {
     const int K = e->prm.k_noncoh;
     const int blocks = n_captures * K;
@@ -377,7 +384,13 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const bool pdl = !prof && (ACQ_FORCE_PDL == 1 || (ACQ_FORCE_PDL < 0 && tiles_total <= 64LL * e->sm_count));
     if (++e->epoch >= 0xfffffffeu) e->epoch = 1;
     if (prof) CU(cudaEventRecord(e->prof[0], st));
-    e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st);
+    if (packed_host_arg) {   // one 1-bit block still in host memory: it rides in the front end's launch
+        if (!launch_front_end_arg(packed_host_arg, e->d_x2, e->d_rot, e->nvar, e->n_shift, e->smax, st))
+            return fail(ACQ_ERR_CUDA, "front-end launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        e->launches++;
+    } else {
+        e->launches += launch_front_end(packed_dev, e->d_x2, e->d_rot, blocks, e->nvar, K, e->sample_bits, e->n_shift, e->smax, st);
+    }
     if (prof) CU(cudaEventRecord(e->prof[1], st));
     e->launches += launch_fwd_fft(e->d_x2, e->d_Dp, e->d_tables, blocks * e->nvar * e->n_shift, true, e->sm_count, st, pdl);
     if (prof) CU(cudaEventRecord(e->prof[2], st));
@@ -405,7 +418,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     // one-CTA-per-tile forms (k_search_e1b, k_search_e1b_multi for non-coherent sums) have ~2.9x the throughput.
     const bool e1b_cluster = ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && tiles_e1b <= e->sm_count / 4);
     a.ctas_done = e->d_ctas_done;
-    a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, search_kind_l1(K, e->prm.half_bin), e->sm_count) +
+    a.ctas_total = fold ? (unsigned)(search_grid_ctas(tiles_l1, search_kind_l1(K, e->prm.half_bin, tiles_l1, e->sm_count), e->sm_count) +
                                      search_grid_ctas(tiles_e1b, e1b_cluster ? kSearchE1bCluster : kSearchE1b, e->sm_count))
                         : 0u;
     a.wait_prior = 1;
@@ -413,6 +426,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         a.work = e->cur_work;
         a.n_work = e->n_l1;
         a.n_tiles = tiles_l1;
+        a.tile_ctr = e->d_tile_ctr;
         e->launches += launch_search(a, false, e->sm_count, st, pdl);
         // The C/A kernel raises its launch-dependents trigger only after its own wait for the forward FFT, so an E1B
         // launch chained to it by programmatic dependent launch starts with the capture spectra complete: it does
@@ -424,6 +438,7 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
         a.work = e->cur_work + e->n_l1;
         a.n_work = e->n_e1b;
         a.n_tiles = tiles_e1b;
+        a.tile_ctr = e->d_tile_ctr + 1;
         if (e1b_cluster) e->launches += launch_search_e1b_cluster(a, e->sm_count, st, pdl);
         else e->launches += launch_search(a, true, e->sm_count, st, pdl);
     }
@@ -510,16 +525,22 @@ int search_host(acq_engine *e, const uint8_t *packed, int n_captures, const int3
     const bool host_records = ACQ_HOST_RECORDS && rows <= (size_t)kHostRecordRowsMax;
     const long long tiles_total = (long long)rows * e->n_dop * e->prm.k_noncoh;
     const bool poll = host_records && sync && !grid && !e->profiling && tiles_total <= 64LL * e->sm_count;
+    // The reference's own search -- one 1-bit block (gps/search.cpp:389-411) -- hands its 8 KiB to the front end as a
+    // kernel argument: the launch carries the bytes, nothing is staged or copied ahead of the first kernel.
+    const bool as_arg = ACQ_ARG_INPUT && n_captures == 1 && e->prm.k_noncoh == 1 && e->sample_bits == 1 &&
+                        bytes == (size_t)ACQ_BLOCK_BYTES;
     const uint8_t *src = packed;
-    if (bytes <= kStagePackedMax) {
-        memcpy(e->h_packed, packed, bytes);
-        src = e->h_packed;
-    }
     const uint8_t *packed_dev = e->d_packed;
-    if (ACQ_ZC_INPUT && src == e->h_packed && bytes <= kZeroCopyMax) packed_dev = e->dh_packed;
-    else CU(cudaMemcpyAsync(e->d_packed, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    if (!as_arg) {
+        if (bytes <= kStagePackedMax) {
+            memcpy(e->h_packed, packed, bytes);
+            src = e->h_packed;
+        }
+        if (ACQ_ZC_INPUT && src == e->h_packed && bytes <= kZeroCopyMax) packed_dev = e->dh_packed;
+        else CU(cudaMemcpyAsync(e->d_packed, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    }
     if ((rc = enqueue_search(e, packed_dev, n_captures, host_records ? e->dh_records : e->d_records,
-                             poll ? e->dh_flag : nullptr, e->stream)))
+                             poll ? e->dh_flag : nullptr, e->stream, as_arg ? packed : nullptr)))
         return rc;
     e->last_captures = n_captures;
     if (!host_records) CU(cudaMemcpyAsync(out, e->d_records, rows * sizeof(acq_record), cudaMemcpyDeviceToHost, e->stream));
@@ -674,6 +695,8 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     // completion counter of small searches, mapped completion word
     CUE(cudaMalloc(&e->d_ctas_done, sizeof(unsigned)));
     CUE(cudaMemset(e->d_ctas_done, 0, sizeof(unsigned)));
+    CUE(cudaMalloc(&e->d_tile_ctr, 2 * sizeof(unsigned)));
+    CUE(cudaMemset(e->d_tile_ctr, 0, 2 * sizeof(unsigned)));
     CUE(cudaHostAlloc(&e->h_flag, sizeof(unsigned), cudaHostAllocMapped));
     *e->h_flag = 0;
     CUE(cudaHostGetDevicePointer(&e->dh_flag, e->h_flag, 0));

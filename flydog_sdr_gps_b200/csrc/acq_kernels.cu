@@ -76,10 +76,15 @@ constexpr int kFeBytes = (kFeChunkBytes + 12 + 15) / 16 * 16 + 16;  // staged by
 // (+-1 | +-3) * c in the reference's summation order.
 // Code-Doppler compensation (n_shift > 1): every output row is written n_shift times, copy i delayed by a further
 // i - smax samples (row layout [block][variant][copy][16384]); the search kernels pick the copy per (block, Doppler).
-template <bool MAG>
-__global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ packed, float2 *__restrict__ x2,
-                                                   const float2 *__restrict__ rot, int nvar, int K, int row0,
-                                                   int n_shift, int smax)
+// A single 1-bit block can also ride in the launch itself (k_front_end_arg below: the capture is a kernel argument, so the
+// host path needs no copy node before the first kernel); the body is shared, only the staging of the packed bytes differs.
+struct FeBlockArg {
+    uint32_t w[ACQ_BLOCK_BYTES / 4];
+};
+template <bool MAG, bool FROM_ARG>
+__device__ __forceinline__ void front_end_body(const uint8_t *__restrict__ packed, const FeBlockArg *__restrict__ arg,
+                                               float2 *__restrict__ x2, const float2 *__restrict__ rot, int nvar, int K,
+                                               int row0, int n_shift, int smax)
 {
     __shared__ __align__(16) uint8_t sbits[kFeBytes + 16];
     __shared__ __align__(16) uint8_t mbits[MAG ? kFeBytes + 16 : 16];
@@ -89,33 +94,42 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
     ACQ_TRACE_STAMP(kTrFrontEnd, 0);
     pdl_launch_dependents();
     const int chunk = blockIdx.x;                      // kN / kFeOut chunks per block
-    const uint8_t *pk = packed + (size_t)blockIdx.y * (MAG ? 2 : 1) * ACQ_BLOCK_BYTES + kFeChunkBytes * chunk;
     const int avail = ACQ_BLOCK_BYTES - kFeChunkBytes * chunk;  // bytes of this block from the chunk start
     const int nbytes = avail < kFeBytes ? avail : kFeBytes;     // the last chunk(s): never read past the block
-    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
-    const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(sbits);
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = nbytes + t; i < kFeBytes + 16; i += 256) {  // zero tail (samples past the block)
-        sbits[i] = 0;
-        if (MAG) mbits[i] = 0;
-    }
-    __syncthreads();
-    if (t == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((MAG ? 2 : 1) * nbytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
-                     "l"(pk), "r"(nbytes), "r"(bar_a)
-                     : "memory");
-        if (MAG)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             (uint32_t)__cvta_generic_to_shared(mbits)),
-                         "l"(pk + ACQ_BLOCK_BYTES), "r"(nbytes), "r"(bar_a)
+    if (FROM_ARG) {
+        // the chunk's bytes straight from the argument (constant bank): word i of the staged window = word i of the chunk
+        static_assert(kFeChunkBytes % 4 == 0 && kFeBytes % 4 == 0 && (kFeBytes + 16) % 4 == 0, "word-wise staging");
+        uint32_t *sw = reinterpret_cast<uint32_t *>(sbits);
+        const int w0 = (kFeChunkBytes / 4) * chunk;
+        for (int i = t; i < (kFeBytes + 16) / 4; i += 256) sw[i] = (4 * i < nbytes) ? arg->w[w0 + i] : 0u;
+        __syncthreads();
+    } else {
+        const uint8_t *pk = packed + (size_t)blockIdx.y * (MAG ? 2 : 1) * ACQ_BLOCK_BYTES + kFeChunkBytes * chunk;
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+        const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(sbits);
+        if (t == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        for (int i = nbytes + t; i < kFeBytes + 16; i += 256) {  // zero tail (samples past the block)
+            sbits[i] = 0;
+            if (MAG) mbits[i] = 0;
+        }
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((MAG ? 2 : 1) * nbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                         "l"(pk), "r"(nbytes), "r"(bar_a)
                          : "memory");
-    }
-    {   // every thread waits for the bytes to land (phase 0)
-        mbar_wait(bar_a, 0);
+            if (MAG)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(mbits)),
+                             "l"(pk + ACQ_BLOCK_BYTES), "r"(nbytes), "r"(bar_a)
+                             : "memory");
+        }
+        {   // every thread waits for the bytes to land (phase 0)
+            mbar_wait(bar_a, 0);
+        }
     }
     // ---- first half-band stage into shared memory: x1s[m] = x1[2*o0 + m]
     const int i_base = 4 * kFeOut * chunk;  // first capture sample of this chunk (= bit 0 of sbits)
@@ -211,6 +225,22 @@ __global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ p
         }
     }
     ACQ_TRACE_STAMP(kTrFrontEnd, 2);
+}
+
+template <bool MAG>
+__global__ void __launch_bounds__(256) k_front_end(const uint8_t *__restrict__ packed, float2 *__restrict__ x2,
+                                                   const float2 *__restrict__ rot, int nvar, int K, int row0,
+                                                   int n_shift, int smax)
+{
+    front_end_body<MAG, false>(packed, nullptr, x2, rot, nvar, K, row0, n_shift, smax);
+}
+
+// One 1-bit block handed over as a kernel argument (8 KiB of the 32 KiB a launch may carry): a single-capture search
+// through acq_search then starts with this kernel -- no staging memcpy, no copy node, no copy-engine-to-SM hand-over.
+__global__ void __launch_bounds__(256) k_front_end_arg(const __grid_constant__ FeBlockArg block, float2 *__restrict__ x2,
+                                                       const float2 *__restrict__ rot, int nvar, int n_shift, int smax)
+{
+    front_end_body<false, true>(nullptr, &block, x2, rot, nvar, 1, 0, n_shift, smax);
 }
 
 // K6a.  Replica: sample i carries chip (i>>4) mod codelen (ca_rate = 1/16 exactly, search.cpp:205,254-258),
@@ -487,6 +517,7 @@ __device__ __forceinline__ Peak block_reduce_peak(Peak v, float *red_f, int *red
 
 struct TileIdx {
     int sat, slot, cap, d, dop, v, wi;
+    __device__ __forceinline__ TileIdx() {}
     // The host keeps a launch below 2^31 tiles (launch_search), so the decomposition runs on 32-bit unsigned
     // divisions: every warp pays it once per tile, and a K = 1 tile is only four sub-FFTs long.
     __device__ __forceinline__ TileIdx(const SearchArgs &p, long long tile)
@@ -523,6 +554,42 @@ struct TileIdx {
         dop = p.half_bin ? ((h - v) >> 1) : h;
     }
 };
+
+// Dynamic tile feed of the strided search kernels (k_search_l1, k_search_l1_multi, k_search_e1b, k_search_e1b_multi).
+// Two CTAs share an SM, and the SM does not share itself evenly: with a static stride the CTA that became resident first
+// ran its tiles 1.4-1.9x faster than its neighbour (%globaltimer stamps, trace variant: K = 20 C/A search, CTAs 0..147
+// done at 2.59 ms, CTAs 148..295 at 3.63 ms; E1B search 123 us against 171-179 us), and the late half then finished
+// alone on its SM at 1.3x, not 2x, the shared rate.  So a CTA takes tile blockIdx.x first and claims every further one
+// from a counter: thread 0 draws the claim during the tile's first sub-FFT (the atomic's latency is off every chain),
+// publishes the next tile's indices in shared memory after the barrier of the second-to-last sub-FFT, stages that tile's
+// first operands after the last barrier, and every thread picks the indices up behind that barrier.  Every CTA claims
+// once per tile it runs, so a launch makes exactly n_tiles claims; the CTA that draws the last one resets the counter.
+// Cells do not depend on which CTA computes them: results are bit-identical to the static stride.
+// `cur`: the tile the CTA is running.  tile_ctr == NULL: the static stride (successor cur + gridDim.x) -- searches of only
+// a few rounds, see search_claims_tiles().
+__device__ __forceinline__ unsigned claim_tile(const SearchArgs &p, unsigned cur)
+{
+    if (!p.tile_ctr) return cur + gridDim.x;
+    const unsigned c = atomicAdd(p.tile_ctr, 1u);
+    if (c == (unsigned)p.n_tiles - 1u) *(volatile unsigned *)p.tile_ctr = 0u;   // the launch's last claim: nobody draws after it
+    return gridDim.x + c;
+}
+__device__ __forceinline__ void publish_tile(int *feed, const SearchArgs &p, unsigned nxt)   // one thread
+{
+    if (nxt < (unsigned)p.n_tiles) {
+        const TileIdx tn(p, nxt);
+        feed[1] = tn.sat, feed[2] = tn.slot, feed[3] = tn.cap, feed[4] = tn.d, feed[5] = tn.dop, feed[6] = tn.v, feed[7] = tn.wi;
+        feed[0] = 1;
+    } else {
+        feed[0] = 0;
+    }
+}
+__device__ __forceinline__ bool next_tile(const int *feed, TileIdx &ti)
+{
+    if (!feed[0]) return false;
+    ti.sat = feed[1], ti.slot = feed[2], ti.cap = feed[3], ti.d = feed[4], ti.dop = feed[5], ti.v = feed[6], ti.wi = feed[7];
+    return true;
+}
 
 // Row of the capture-spectrum array for (capture, block b, variant) at this tile's Doppler index: with code-Doppler
 // compensation the copy delayed by s(b, h) more samples (SearchArgs::n_shift), otherwise the only one.
@@ -792,7 +859,10 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 #endif
         tma_load_1d(smem_u32(s.S1 + half * kS1pElems), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
     };
-    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+    TileIdx ti(p, blockIdx.x);   // the grid never exceeds the tile count: every CTA has a first tile
+    if (t == 0) issue(ti, 0, 0, 0);
+    int *feed = red_i + 20;      // dynamic tile feed (claim_tile / publish_tile / next_tile)
+    unsigned nxt = blockIdx.x;   // thread 0: the tile being run, then the claimed one
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
     // The cross-warp merge of a tile's peak is deferred to the next tile: the warp partials are left in a parity slot
@@ -802,16 +872,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
     };
 
-#if ACQ_L1_LEAN
-    // the launch stride gridDim.x as digits over (n_dop, n_work): tile indices advance without divisions
-    const int sd = (int)(gridDim.x % (unsigned)p.n_dop), sw = (int)((gridDim.x / (unsigned)p.n_dop) % (unsigned)p.n_work),
-              sc = (int)(gridDim.x / ((unsigned)p.n_dop * (unsigned)p.n_work));
-    TileIdx ti(p, blockIdx.x < p.n_tiles ? blockIdx.x : 0);
-#endif
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-#if !ACQ_L1_LEAN
-        const TileIdx ti(p, tile);
-#endif
+    for (;;) {
         float P[16];
         float2 acc[16];
         for (int b = 0; b < p.K; b++) {
@@ -840,16 +901,13 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
                 }
                 subfft4096_inv4<true>(x, k2, bw, S1b, t, tw_taddr, [&]() {
                     if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                        if (b == 0 && k2 == 0) nxt = claim_tile(p, nxt);
+                        if (b == p.K - 1 && k2 == 2) publish_tile(feed, p, nxt);
                         if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
                         else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
-                        else if (tile + gridDim.x < p.n_tiles) {
-#if ACQ_L1_LEAN
-                            TileIdx tn = ti;
-                            tn.step(p, sd, sw, sc);
-                            issue(tn, 0, 0, (it + 1) & 1);
-#else
-                            issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
-#endif
+                        else {
+                            TileIdx tn;
+                            if (next_tile(feed, tn)) issue(tn, 0, 0, (it + 1) & 1);
                         }
                     }
                 });
@@ -876,9 +934,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
         pend_slot = ti.slot;
         pend_d = ti.d;
         par ^= 1;
-#if ACQ_L1_LEAN
-        ti.step(p, sd, sw, sc);
-#endif
+        if (!next_tile(feed, ti)) break;   // published behind the barrier of sub-FFT 2, read behind that of sub-FFT 3
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
@@ -1043,6 +1099,13 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
             if (lead) {
                 store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
                 __threadfence();  // this team's cells (all stored by this thread) before the CTA's count
+#ifdef ACQ_TRACE
+                if (blockIdx.x < kTraceCtas) {   // slot 3: team 0 done; team 1 done goes to the second half of the CTA axis
+                    unsigned long long tm;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm));
+                    g_trace[kTrSearchL1][blockIdx.x + (team ? 512 : 0)][3] = tm;
+                }
+#endif
             }
         }
     } else {
@@ -1192,15 +1255,17 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
         }
         tma_load_1d(smem_u32(s.S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
     };
-    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+    TileIdx ti(p, blockIdx.x);   // the grid never exceeds the tile count: every CTA has a first tile
+    if (t == 0) issue(ti, 0, 0, 0);
+    int *feed = red_i + 20;      // dynamic tile feed (claim_tile / publish_tile / next_tile)
+    unsigned nxt = blockIdx.x;   // thread 0: the tile being run, then the claimed one
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
     auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge, see k_search_l1)
         store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
     };
 
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const TileIdx ti(p, tile);
+    for (;;) {
         float P[16];
         float2 acc[16];
         for (int b = 0; b < p.K; b++) {
@@ -1228,9 +1293,14 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
                 for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(Dk[256 * a], x[a]);
                 subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, BaseFromGlobal{bases}, [&]() {
                     if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                        if (b == 0 && k2 == 0) nxt = claim_tile(p, nxt);
+                        if (b == p.K - 1 && k2 == 2) publish_tile(feed, p, nxt);
                         if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
                         else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
-                        else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
+                        else {
+                            TileIdx tn;
+                            if (next_tile(feed, tn)) issue(tn, 0, 0, (it + 1) & 1);
+                        }
                     }
                 });
                 it++;
@@ -1252,6 +1322,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
         pend_slot = ti.slot;
         pend_d = ti.d;
         par ^= 1;
+        if (!next_tile(feed, ti)) break;   // published behind the barrier of the second-to-last sub-FFT, read behind the last
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
@@ -1347,15 +1418,17 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
         tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
         tma_load_1d(smem_u32(s.S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
     };
-    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0);
+    TileIdx ti(p, blockIdx.x);   // the grid never exceeds the tile count: every CTA has a first tile
+    if (t == 0) issue(ti, 0, 0);
+    int *feed = red_i + 20;      // dynamic tile feed (claim_tile / publish_tile / next_tile)
+    unsigned nxt = blockIdx.x;   // thread 0: the tile being run, then the claimed one
     int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
     auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge)
         store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
     };
 
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const TileIdx ti(p, tile);
+    for (;;) {
         float2 x[16];
 #pragma unroll kE1bK2Unroll
         for (int k2 = 0; k2 < 4; k2++) {
@@ -1371,8 +1444,13 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
             }
             subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, BaseFromTmem{zaddr + kE1bBaseCol}, [&]() {
                 if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                    if (k2 == 0) nxt = claim_tile(p, nxt);
+                    if (k2 == 2) publish_tile(feed, p, nxt);
                     if (k2 < 3) issue(ti, k2 + 1, (it + 1) & 1);
-                    else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, (it + 1) & 1);
+                    else {
+                        TileIdx tn;
+                        if (next_tile(feed, tn)) issue(tn, 0, (it + 1) & 1);
+                    }
                 }
             });
             it++;
@@ -1460,6 +1538,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
         pend_slot = ti.slot;
         pend_d = ti.d;
         par ^= 1;
+        if (!next_tile(feed, ti)) break;   // published behind the barrier of sub-FFT 2, read behind that of sub-FFT 3
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
@@ -1528,7 +1607,10 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_multi(const SearchArgs p)
         mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * kSub));
         tma_load_1d(smem_u32(s.S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
     };
-    if (t == 0 && blockIdx.x < p.n_tiles) issue(TileIdx(p, blockIdx.x), 0, 0, 0);
+    TileIdx ti(p, blockIdx.x);   // the grid never exceeds the tile count: every CTA has a first tile
+    if (t == 0) issue(ti, 0, 0, 0);
+    int *feed = red_i + 20;      // dynamic tile feed (claim_tile / publish_tile / next_tile)
+    unsigned nxt = blockIdx.x;   // thread 0: the tile being run, then the claimed one
     int it = 0;
     int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
     auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge)
@@ -1536,8 +1618,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_multi(const SearchArgs p)
     };
     const int lag0 = lag_of3(t, 0);
 
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const TileIdx ti(p, tile);
+    for (;;) {
         float bp[4] = {0.0f, 0.0f, 0.0f, 0.0f}, bsum = 0.0f;   // last block: running maximum per quarter, sum
         int bn2[4] = {0, 0, 0, 0};
         for (int b = 0; b < p.K; b++) {
@@ -1558,9 +1639,14 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_multi(const SearchArgs p)
                 }
                 subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, BaseFromGlobal{bases}, [&]() {
                     if (t == 0) {
+                        if (b == 0 && k2 == 0) nxt = claim_tile(p, nxt);
+                        if (b == p.K - 1 && k2 == 2) publish_tile(feed, p, nxt);
                         if (k2 < 3) issue(ti, b, k2 + 1, (it + 1) & 1);
                         else if (b + 1 < p.K) issue(ti, b + 1, 0, (it + 1) & 1);
-                        else if (tile + gridDim.x < p.n_tiles) issue(TileIdx(p, tile + gridDim.x), 0, 0, (it + 1) & 1);
+                        else {
+                            TileIdx tn;
+                            if (next_tile(feed, tn)) issue(tn, 0, 0, (it + 1) & 1);
+                        }
                     }
                 });
                 it++;
@@ -1646,6 +1732,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_multi(const SearchArgs p)
         pend_slot = ti.slot;
         pend_d = ti.d;
         par ^= 1;
+        if (!next_tile(feed, ti)) break;   // published behind the barrier of the second-to-last sub-FFT, read behind the last
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
@@ -2062,6 +2149,19 @@ int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n
     return launched;
 }
 
+// The same front end for ONE 1-bit block that still lies in host memory: the bytes travel as the kernel's argument.
+int launch_front_end_arg(const uint8_t *packed_host, float2 *x2, const float2 *rot, int nvar, int n_shift, int smax,
+                         cudaStream_t st)
+{
+    void *args[] = {const_cast<uint8_t *>(packed_host), &x2, &rot, &nvar, &n_shift, &smax};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kN / kFeOut, 1);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    if (cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(k_front_end_arg), args) != cudaSuccess) return 0;
+    return 1;
+}
+
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st)
 {
     k_hb1_code<<<dim3(128, n_sats), 256, 0, st>>>(chips, codelen_boc, x1);
@@ -2104,10 +2204,19 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
 // Which C/A search kernel a search runs: non-coherent sums -> k_search_l1_multi; K = 1 on full bins -> k_search_l1_dr
 // (the capture spectrum, the same for every Doppler index of a capture, stays in tensor memory); K = 1 on half-bins ->
 // k_search_l1<false> (odd and even half-bins read different capture spectra, so nothing could stay resident).
+// Short full-bin searches (fewer than kDrMinTilesPerSm tiles per SM: the reference's own one-capture search is 8.9) also
+// run k_search_l1<false>: its 296 strided CTAs spread a handful of rounds more evenly than 296 contiguous team ranges
+// (a team left with one tile more than its neighbour runs it alone on the SM at 1.3x, not 2x, the shared rate), and the
+// two-team CTA's longer prologue shows once the search is over in 50 us.  Measured through acq_search, hot caches
+// (tools/e2e_latency.py): 32 PRNs x 41 bins 76.0 us against 79.2 us, one satellite 34.1 against 35.8 us.
 #ifndef ACQ_FORCE_L1_CTA
 #define ACQ_FORCE_L1_CTA 0   // variant l1_cta: always k_search_l1<false> for K = 1 (the kernel-equivalence tests)
 #endif
-int search_kind_l1(int K, int half_bin)
+#ifndef ACQ_DR_MIN_TILES_PER_SM
+#define ACQ_DR_MIN_TILES_PER_SM 12   // variant l1_dr_all: 0
+#endif
+constexpr int kDrMinTilesPerSm = ACQ_DR_MIN_TILES_PER_SM;
+int search_kind_l1(int K, int half_bin, long long n_tiles, int sm_count)
 {
 #if defined(ACQ_VARIANT_L1_X3) || defined(ACQ_VARIANT_L1_LDG) || defined(ACQ_VARIANT_L1_MULTI_TW)
     return kSearchL1;   // these experiment builds run every C/A search on their own 256-thread kernels
@@ -2116,7 +2225,22 @@ int search_kind_l1(int K, int half_bin)
     if (K > 1) return kSearchL1Mst;
 #endif
     if (K > 1) return kSearchL1Multi;
-    return (half_bin || ACQ_FORCE_L1_CTA) ? kSearchL1 : kSearchL1Dr;
+    if (half_bin || ACQ_FORCE_L1_CTA) return kSearchL1;
+    return n_tiles < (long long)kDrMinTilesPerSm * sm_count ? kSearchL1 : kSearchL1Dr;
+}
+
+// Claimed tiles or the static stride?  Claiming evens out the two CTAs of an SM and the SMs among themselves, at the price
+// of a greedy tail: once the counter runs dry every CTA still finishes its tile, up to a whole tile time with the SM half
+// empty.  Over many rounds that is noise against what the balance wins (13.7 rounds of E1B tiles: 201.6 -> 190.5 us through
+// acq_search; K = 20: 3.65 -> 3.45 ms); the reference's own C/A search is 4.4 rounds, where the static stride's fixed
+// pattern (the early CTA of each SM runs five tiles, the late one four, the last of them alone) ends 3.6 us sooner
+// (75.4 against 79.0 us, hot caches).  ACQ_DYN_MIN_ROUNDS: rounds (tiles per CTA) from which a launch claims.
+#ifndef ACQ_DYN_MIN_ROUNDS
+#define ACQ_DYN_MIN_ROUNDS 6
+#endif
+bool search_claims_tiles(long long n_tiles, int grid)
+{
+    return grid > 0 && n_tiles >= (long long)ACQ_DYN_MIN_ROUNDS * grid;
 }
 
 int search_grid_ctas(long long n_tiles, int kind, int sm_count)
@@ -2131,11 +2255,13 @@ int search_grid_ctas(long long n_tiles, int kind, int sm_count)
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
 
-int launch_search(const SearchArgs &a, bool e1b, int sm_count, cudaStream_t st, bool pdl)
+int launch_search(const SearchArgs &a_in, bool e1b, int sm_count, cudaStream_t st, bool pdl)
 {
-    const int kind = e1b ? kSearchE1b : search_kind_l1(a.K, a.half_bin);
-    const int grid = search_grid_ctas(a.n_tiles, kind, sm_count);
+    const int kind = e1b ? kSearchE1b : search_kind_l1(a_in.K, a_in.half_bin, a_in.n_tiles, sm_count);
+    const int grid = search_grid_ctas(a_in.n_tiles, kind, sm_count);
     if (grid <= 0) return 0;
+    SearchArgs a = a_in;
+    if (!search_claims_tiles(a.n_tiles, grid)) a.tile_ctr = nullptr;   // few rounds: static stride
     if (e1b) {
 #ifdef ACQ_VARIANT_E1B_LDG
         launch_k(k_search_e1b_ldg, grid, 256, fft_smem3_bytes() + 64 * sizeof(float), st, pdl, a);

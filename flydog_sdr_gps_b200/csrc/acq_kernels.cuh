@@ -26,6 +26,10 @@ struct SearchArgs {
     // together); each bumps *ctas_done (zero between searches) after its last cell, and k_pick_small polls it.
     unsigned *ctas_done;
     unsigned ctas_total;
+    // Dynamic tile feed of the strided search kernels: a CTA's first tile is its block index, every further one is
+    // gridDim.x + atomicAdd(tile_ctr, 1).  *tile_ctr is zero between launches (the CTA that draws the launch's last
+    // claim, number n_tiles - 1, puts it back); the C/A and the E1B launch of one search use different words.
+    unsigned *tile_ctr;
     // 1: wait for the preceding grids of the stream (griddepcontrol.wait).  0: this launch directly follows another
     // search launch of the same search, which has already waited (see launch_search).
     int wait_prior;
@@ -48,6 +52,8 @@ cudaError_t launch_tables_init(const float2 *h_cC, const float *h_hb);
 // n_shift/smax: copies of each output row, copy i delayed by a further i - smax samples (code-Doppler compensation)
 int launch_front_end(const uint8_t *packed, float2 *x2, const float2 *rot, int n_blocks, int nvar, int K, int sample_bits,
                      int n_shift, int smax, cudaStream_t st);
+int launch_front_end_arg(const uint8_t *packed_host, float2 *x2, const float2 *rot, int nvar, int n_shift, int smax,
+                         cudaStream_t st);   // one 1-bit block passed as the kernel's argument (0: launch failed)
 int launch_hb1_code(const uint32_t *chips, const int *codelen_boc, float2 *x1, int n_sats, cudaStream_t st);
 int launch_hb2(const float2 *x1, float2 *x2, const float2 *rot, int n_rows, int nvar, int K, cudaStream_t st);
 // pdl: launch with programmatic stream serialization (the grid may become resident while the previous kernel of
@@ -67,7 +73,7 @@ int launch_pick_small(const acq_cell *cells, const int *slot_sat, acq_record *ou
                       bool pdl = false);
 // CTAs of a search launch that store cells (what SearchArgs::ctas_total sums over the launches of one search)
 enum { kSearchL1 = 0, kSearchE1b = 1, kSearchE1bCluster = 2, kSearchL1Multi = 3, kSearchL1Dr = 4, kSearchL1Mst = 5 };
-int search_kind_l1(int K, int half_bin);   // which C/A search kernel (and so which grid) a search uses
+int search_kind_l1(int K, int half_bin, long long n_tiles, int sm_count);   // which C/A search kernel (and so which grid) a search uses
 constexpr int kPickSmallRowsMax = 256;  // rows k_pick_small stages in shared memory
 // A record as k_pick_small hands it to a POLLING host (mapped pinned memory): two 16-byte halves, each carrying the
 // search's epoch in its last word.  Each half arrives by one 16-byte store, so a host that sees the epoch in a half has

@@ -827,7 +827,7 @@ def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle):
 
 
 def test_capture_resident_kernel_equals_cta_kernel(gpu_required, oracle):
-    """k_search_l1_dr (the K = 1 full-bin product kernel: one CTA per SM, two teams of FFT warps with a staging warp each,
+    """k_search_l1_dr (the K = 1 full-bin product kernel from 12 tiles per SM up: one CTA per SM, two teams of FFT warps with a staging warp each,
     contiguous tile ranges, the capture residue parked in tensor memory for all tiles of a capture) against
     k_search_l1<false> (two CTAs per SM striding over the tiles, both operands staged per sub-FFT; variant library l1_cta):
     the same arithmetic in the same order, so the whole per-Doppler table is bitwise equal.  Shapes: one capture (every team
@@ -844,13 +844,16 @@ def test_capture_resident_kernel_equals_cta_kernel(gpu_required, oracle):
              (dict(dop_lo=-20, dop_hi=20), [cap2, cap], np.array([2, 6, 10, 13, 18], np.int32))]
     for kw, caps, sel in cases:
         out = {}
-        for kind, variant in (("dr", None), ("cta", "l1_cta")):
+        # product: k_search_l1_dr from 12 tiles per SM, k_search_l1<false> below; l1_dr_all: k_search_l1_dr at every size
+        for kind, variant in (("product", None), ("dr", "l1_dr_all"), ("cta", "l1_cta")):
             with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
                 out[kind] = eng.search(np.concatenate(caps), sel=sel, want_grid=True)
-        (ra, ga), (rb, gb) = out["dr"], out["cta"]
-        for f in ("peak", "lag", "noise", "snr"):
-            assert np.array_equal(ga[f], gb[f]), (kw, len(caps), f)
-        assert ra.tobytes() == rb.tobytes()
+        rb, gb = out["cta"]
+        for kind in ("product", "dr"):
+            ra, ga = out[kind]
+            for f in ("peak", "lag", "noise", "snr"):
+                assert np.array_equal(ga[f], gb[f]), (kind, kw, len(caps), f)
+            assert ra.tobytes() == rb.tobytes(), kind
     # half-bin K = 1 searches stay on k_search_l1<false> (odd and even half-bins read different capture spectra)
     with F.AcqEngine(table, F.default_params(half_bin=1, dop_lo=-9, dop_hi=9)) as eng:
         rec, grid = eng.search(cap, want_grid=True)
@@ -912,3 +915,51 @@ def test_randomized_parameter_space(gpu_required, oracle, seed):
     for i in range(len(sel)):   # per-constellation thresholds: compare record by record
         compare_records(rec[0][i:i + 1], orec[i:i + 1], ogrid[i:i + 1], lo, float(thr[i]), ggrid=grid[0][i:i + 1], max_ties=1)
     assert np.array_equal(rec[0]["sat"], sel)
+
+
+def test_capture_as_kernel_argument_equals_copied_capture(gpu_required):
+    """acq_search of ONE 1-bit block hands the capture to the front end as a kernel argument (k_front_end_arg; no staging,
+    no copy node); every other search copies it to the device first.  Same bits in, same front-end arithmetic: the records
+    and the whole per-Doppler table are bytewise equal to the variant library that always copies (argin0), for a table
+    with C/A and E1B rows, and a two-capture search (copied in both builds) still matches its single-capture halves."""
+    table = scenarios.table("cfg4")
+    kw = scenarios.params_kw("cfg4")
+    caps = [synth.make_capture(s, 1, table, scenarios.signals("cfg4", s)) for s in (11, 12)]
+    out = {}
+    for kind, variant in (("arg", None), ("copy", "argin0")):
+        with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
+            out[kind] = [eng.search(c, want_grid=True) for c in caps] + [eng.search(np.concatenate(caps), want_grid=True)]
+    for (ra, ga), (rb, gb) in zip(out["arg"], out["copy"]):
+        assert ra.tobytes() == rb.tobytes()
+        assert ga.tobytes() == gb.tobytes()
+    both_r, both_g = out["arg"][2]
+    for i in range(2):
+        assert both_r[i].tobytes() == out["arg"][i][0][0].tobytes()
+        assert both_g[i].tobytes() == out["arg"][i][1][0].tobytes()
+
+
+def test_claimed_tiles_equal_static_stride(gpu_required):
+    """The strided search kernels (k_search_l1<false>, k_search_l1_multi, k_search_e1b, k_search_e1b_multi) claim their tiles
+    from a counter instead of striding by the grid size once a launch has six rounds of them (the two CTAs of an SM do not
+    progress at the same rate).  Which CTA
+    runs a tile cannot change its cell: records and the whole per-Doppler table are bytewise equal to the static stride
+    (variant static_tiles), over repeated searches on one engine (the counter must come back to zero by itself), for
+    searches of fewer tiles than CTAs, exactly one tile, and many rounds."""
+    cases = [("cfg4", {}, None, 3), ("cfg4", {}, np.array([3, 40], np.int32), 2), ("cfg1", dict(dop_lo=2, dop_hi=2), np.array([5], np.int32), 2),
+             ("cfg2", dict(dop_lo=-12, dop_hi=11), np.array([0, 9, 17], np.int32), 2), ("cfg3_k4", dict(dop_lo=-6, dop_hi=6), None, 2)]
+    for cfg, over, sel, reps in cases:
+        table = scenarios.table(cfg)
+        kw = dict(scenarios.params_kw(cfg))
+        kw.update(over)
+        K = kw.get("k_noncoh", 1)
+        caps = [synth.make_capture(70 + i, K, table, scenarios.signals(cfg, 70 + i)) for i in range(2)]
+        out = {}
+        # product: claims from six rounds of tiles up; dyn_tiles: always; static_tiles: never
+        for kind, variant in (("product", None), ("claimed", "dyn_tiles"), ("static", "static_tiles")):
+            with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
+                out[kind] = [eng.search(caps[i % 2], sel=sel, want_grid=True) for i in range(reps)]
+                out[kind].append(eng.search(np.concatenate(caps), sel=sel, want_grid=True))
+        for kind in ("product", "claimed"):
+            for (ra, ga), (rb, gb) in zip(out[kind], out["static"]):
+                assert ra.tobytes() == rb.tobytes(), (kind, cfg, over)
+                assert ga.tobytes() == gb.tobytes(), (kind, cfg, over)

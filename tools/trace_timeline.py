@@ -22,7 +22,8 @@ buf = np.zeros(total, np.uint64)
 for cfg in sys.argv[1:] or ["cfg1"]:
     table = scenarios.table(cfg)
     kw = scenarios.params_kw(cfg)
-    cap = synth.make_capture(1, kw.get("k_noncoh", 1), table, scenarios.signals(cfg, 1))
+    ncap = int(os.environ.get("TRACE_CAPS", "1"))
+    cap = np.concatenate([synth.make_capture(1 + i, kw.get("k_noncoh", 1), table, scenarios.signals(cfg, 1 + i)) for i in range(ncap)])
     with F.AcqEngine(table, F.default_params(**kw), variant=VARIANT) as eng:
         import time
         for _ in range(20):
@@ -45,5 +46,20 @@ for cfg in sys.argv[1:] or ["cfg1"]:
         extra = ""
         if (tr[k][used][:, 3] > 0).any():
             extra = "  mark3 %6.1f" % ((tr[k][used][:, 3].max() - start) / 1e3)
+        if os.environ.get("TRACE_DUMP") and name.startswith("search"):
+            xs = np.sort(x)
+            print("  %s exit deciles:" % name, " ".join("%.1f" % v for v in np.percentile(xs, range(0, 101, 10))))
+            ex_all = (tr[k][used][:, 2] - start) / 1e3
+            print("  %s exit by CTA index (every 8th):" % name, " ".join("%.0f" % v for v in ex_all[::8]))
+            if (tr[k][512:, 3] > 0).any():   # k_search_l1_dr: team 0 done at [cta][3], team 1 done at [512 + cta][3]
+                t0 = (tr[k][:512, 3][tr[k][:512, 3] > 0] - start) / 1e3
+                t1 = (tr[k][512:, 3][tr[k][512:, 3] > 0] - start) / 1e3
+                print("  %s team 0 done deciles:" % name, " ".join("%.0f" % v for v in np.percentile(t0, range(0, 101, 10))))
+                print("  %s team 1 done deciles:" % name, " ".join("%.0f" % v for v in np.percentile(t1, range(0, 101, 10))))
+                print("  %s team1 - team0 per CTA (every 8th):" % name, " ".join("%.0f" % v for v in (t1 - t0)[::8]))
+            m3 = (tr[k][used][:, 3] - start) / 1e3
+            if (tr[k][used][:, 3] > 0).any():
+                print("  %s mark3 by CTA index (every 8th):" % name, " ".join("%.0f" % v for v in m3[::8]))
+            print("  %s past-wait by CTA index (every 8th):" % name, " ".join("%.1f" % v for v in ((tr[k][used][:, 1] - start) / 1e3)[::8]))
         print("  %-12s ctas %4d  entry %6.1f..%6.1f  past-wait %6.1f..%6.1f  exit %6.1f..%6.1f (median %6.1f)%s" % (
             name, used.sum(), e.min(), e.max(), w.min(), w.max(), x.min(), x.max(), np.median(x), extra))
