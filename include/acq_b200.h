@@ -160,7 +160,8 @@ int acq_destroy(acq_engine *e);
  * Correlate() (gps/search.cpp:453-499) for n_sel satellites on n_captures captures in one call.
  *   packed : HOST memory, n_captures * k_noncoh * ACQ_CAPTURE_BLOCK_BYTES(sample_bits) bytes (ACQ_BLOCK_BYTES per
  *            block in the reference's 1-bit format); capture c occupies k_noncoh consecutive blocks.
- *            (Pinned memory avoids a staging copy.)
+ *            (Pinned memory avoids a staging copy.  The reference's own search -- ONE 1-bit block -- needs neither:
+ *            its 8 KiB travel as the first kernel's launch argument, read from `packed` before the call returns.)
  *   sel    : n_sel table indices to search, or NULL for the whole table (then n_sel is ignored).  Rows of type
  *            ACQ_SBAS carry an all-zero code spectrum, as in the reference (SearchInit builds replicas for Navstar,
  *            QZSS and E1B rows only, gps/search.cpp:244,306): their records are {lag 0, dop 0, snr 0}.
