@@ -114,7 +114,7 @@ struct acq_engine {
     float2 *d_x2 = nullptr, *d_Dp = nullptr;
     acq_cell *d_cells = nullptr;
     acq_record *d_records = nullptr;
-    unsigned *d_tile_ctr = nullptr;    // [2] claim counters of the C/A and the E1B search launch (SearchArgs::tile_ctr); zero between launches
+    unsigned *d_tile_ctr = nullptr;    // [4] claim counters [0,1] and done counters [2,3] of the C/A and the E1B search launch (SearchArgs::tile_ctr); zero between launches
     unsigned *d_ctas_done = nullptr;   // finished search CTAs of a small search (folded best-Doppler pick); zero between searches
     unsigned epoch = 0;                // search counter: value of the completion word
     // host path: pinned staging of small captures; records and the completion word in mapped pinned memory,
@@ -695,8 +695,8 @@ int acq_create(acq_engine **out, const acq_params *params, const acq_sat *sats, 
     // completion counter of small searches, mapped completion word
     CUE(cudaMalloc(&e->d_ctas_done, sizeof(unsigned)));
     CUE(cudaMemset(e->d_ctas_done, 0, sizeof(unsigned)));
-    CUE(cudaMalloc(&e->d_tile_ctr, 2 * sizeof(unsigned)));
-    CUE(cudaMemset(e->d_tile_ctr, 0, 2 * sizeof(unsigned)));
+    CUE(cudaMalloc(&e->d_tile_ctr, 4 * sizeof(unsigned)));
+    CUE(cudaMemset(e->d_tile_ctr, 0, 4 * sizeof(unsigned)));
     CUE(cudaHostAlloc(&e->h_flag, sizeof(unsigned), cudaHostAllocMapped));
     *e->h_flag = 0;
     CUE(cudaHostGetDevicePointer(&e->dh_flag, e->h_flag, 0));

@@ -562,17 +562,26 @@ struct TileIdx {
 // alone on its SM at 1.3x, not 2x, the shared rate.  So a CTA takes tile blockIdx.x first and claims every further one
 // from a counter: thread 0 draws the claim during the tile's first sub-FFT (the atomic's latency is off every chain),
 // publishes the next tile's indices in shared memory after the barrier of the second-to-last sub-FFT, stages that tile's
-// first operands after the last barrier, and every thread picks the indices up behind that barrier.  Every CTA claims
-// once per tile it runs, so a launch makes exactly n_tiles claims; the CTA that draws the last one resets the counter.
+// first operands after the last barrier, and every thread picks the indices up behind that barrier.  Every CTA counts
+// itself out after its last claim, and the last one out resets both counters (claims_done).
 // Cells do not depend on which CTA computes them: results are bit-identical to the static stride.
 // `cur`: the tile the CTA is running.  tile_ctr == NULL: the static stride (successor cur + gridDim.x) -- searches of only
 // a few rounds, see search_claims_tiles().
+// (Tried against the greedy tail and dropped: the late-resident CTA of each SM -- block index in the upper half of the
+// grid -- stops claiming once no more than one tile per SM is left, so that the last tiles run one per SM.  Slower
+// everywhere: 32 PRNs x 41 bins 80.1 us against 78.8 us through acq_search, the 82-PRN search 167.9 against 164.4 us.)
 __device__ __forceinline__ unsigned claim_tile(const SearchArgs &p, unsigned cur)
 {
     if (!p.tile_ctr) return cur + gridDim.x;
-    const unsigned c = atomicAdd(p.tile_ctr, 1u);
-    if (c == (unsigned)p.n_tiles - 1u) *(volatile unsigned *)p.tile_ctr = 0u;   // the launch's last claim: nobody draws after it
-    return gridDim.x + c;
+    return gridDim.x + atomicAdd(p.tile_ctr, 1u);
+}
+// End of a claiming CTA (after its last claim): the last one out puts both counters back to zero for the next launch.
+__device__ __forceinline__ void claims_done(const SearchArgs &p, int t)
+{
+    if (p.tile_ctr && t == 0 && atomicAdd(p.tile_ctr + 2, 1u) == gridDim.x - 1) {
+        *(volatile unsigned *)p.tile_ctr = 0u;
+        *(volatile unsigned *)(p.tile_ctr + 2) = 0u;
+    }
 }
 __device__ __forceinline__ void publish_tile(int *feed, const SearchArgs &p, unsigned nxt)   // one thread
 {
@@ -938,6 +947,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
+    claims_done(p, t);
     search_cta_epilogue(p, t);
     ACQ_TRACE_STAMP(kTrSearchL1, 2);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
@@ -1326,6 +1336,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
+    claims_done(p, t);
     search_cta_epilogue(p, t);
     ACQ_TRACE_STAMP(kTrSearchL1, 2);
     tmem_free_cta<2 * kTwCols>(tmem_base, t);
@@ -1542,6 +1553,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b(const SearchArgs p)
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
+    claims_done(p, t);
     search_cta_epilogue(p, t);
     ACQ_TRACE_STAMP(kTrSearchE1b, 2);
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);
@@ -1736,6 +1748,7 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_multi(const SearchArgs p)
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
+    claims_done(p, t);
     search_cta_epilogue(p, t);
     ACQ_TRACE_STAMP(kTrSearchE1b, 2);
     tmem_free_cta<kE1bTmemCols>(tmem_base, t);

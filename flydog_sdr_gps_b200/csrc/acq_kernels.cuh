@@ -27,8 +27,9 @@ struct SearchArgs {
     unsigned *ctas_done;
     unsigned ctas_total;
     // Dynamic tile feed of the strided search kernels: a CTA's first tile is its block index, every further one is
-    // gridDim.x + atomicAdd(tile_ctr, 1).  *tile_ctr is zero between launches (the CTA that draws the launch's last
-    // claim, number n_tiles - 1, puts it back); the C/A and the E1B launch of one search use different words.
+    // gridDim.x + atomicAdd(tile_ctr, 1); tile_ctr[2] counts the CTAs that are through with claiming, and the last of
+    // them zeroes both words for the next launch.  The C/A and the E1B launch of one search use different pairs
+    // (tile_ctr = base + 0 / base + 1).  NULL: static stride.
     unsigned *tile_ctr;
     // 1: wait for the preceding grids of the stream (griddepcontrol.wait).  0: this launch directly follows another
     // search launch of the same search, which has already waited (see launch_search).
