@@ -65,5 +65,10 @@ for cfg in sys.argv[1:] or ["cfg1"]:
             if (tr[k][used][:, 3] > 0).any():
                 print("  %s mark3 by CTA index (every 8th):" % name, " ".join("%.0f" % v for v in m3[::8]))
             print("  %s past-wait by CTA index (every 8th):" % name, " ".join("%.1f" % v for v in ((tr[k][used][:, 1] - start) / 1e3)[::8]))
+        if name == "fwd_fft" and (tr[k][64:320, 3] > 0).any():   # cluster forward FFT: inner stamps of thread 0
+            for lbl, off in (("loads arrived", 64), ("sub-FFT done", 128), ("cluster barrier passed", 192), ("combine + stores issued", 256)):
+                v = tr[k][off:off + 64, 3]
+                v = (v[v > 0] - start) / 1e3
+                print("  fwd_fft %-24s %6.2f..%6.2f" % (lbl, v.min(), v.max()))
         print("  %-12s ctas %4d  entry %6.1f..%6.1f  past-wait %6.1f..%6.1f  exit %6.1f..%6.1f (median %6.1f)%s" % (
             name, used.sum(), e.min(), e.max(), w.min(), w.max(), x.min(), x.max(), np.median(x), extra))
