@@ -72,6 +72,7 @@ VARIANTS = {
     "zcin": ["ACQ_ZC_INPUT=1"],              # front end reads small captures from mapped pinned memory (no H2D copy node)
     "static_tiles": ["ACQ_DYN_MIN_ROUNDS=1000000000"],  # strided search kernels always on the static stride (the product: tiles claimed from a counter from 6 rounds up)
     "dyn_tiles": ["ACQ_DYN_MIN_ROUNDS=0"],    # ... always claiming
+    "carve0": ["ACQ_CARVEOUT_MAX=0"],        # shared-memory carveout left to the driver per kernel (the product: max shared for the whole chain)
     "argin0": ["ACQ_ARG_INPUT=0"],           # single-block captures through the staging buffer + copy node (the product: kernel argument)
     "devrec": ["ACQ_HOST_RECORDS=0"],        # records through device memory + copy, stream wait (no mapped memory, no polling)
 }

@@ -2166,6 +2166,23 @@ cudaError_t search_kernels_configure()
     if ((e = cudaFuncSetAttribute(k_fwd_fft_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
     if ((e = cudaFuncSetAttribute(k_fwd_fft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw))) return e;
+    // One shared-memory carveout for every kernel of a search.  Left to the driver, the C/A kernel (2 x 96.3 KiB) runs
+    // its SMs at the 196 KiB split and the E1B kernel (2 x 103.8 KiB) at 228 KiB, and an SM changes its split only when
+    // it is empty: in a GPS + Galileo search the E1B CTAs -- launched to move in as the C/A CTAs retire -- entered no SM
+    // before BOTH its C/A CTAs had gone (trace: first E1B CTA at 54.8 us although half the C/A CTAs leave by 50 us).
+#ifndef ACQ_CARVEOUT_MAX
+#define ACQ_CARVEOUT_MAX 1   // 0 (variant carve0): the driver's choice per kernel
+#endif
+#if ACQ_CARVEOUT_MAX
+    const void *chain[] = {(const void *)k_front_end<false>, (const void *)k_front_end<true>, (const void *)k_front_end_arg,
+                           (const void *)k_fwd_fft<true>, (const void *)k_fwd_fft<false>, (const void *)k_fwd_fft_cluster<true>,
+                           (const void *)k_fwd_fft_cluster<false>, (const void *)k_search_l1<false>, (const void *)k_search_l1<true>,
+                           (const void *)k_search_l1_dr, (const void *)k_search_l1_multi, (const void *)k_search_e1b,
+                           (const void *)k_search_e1b_multi, (const void *)k_search_e1b_cluster<false>,
+                           (const void *)k_search_e1b_cluster<true>, (const void *)k_pick_small, (const void *)k_best_dop};
+    for (const void *f : chain)
+        if ((e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
+#endif
     return cudaSuccess;
 }
 
