@@ -148,7 +148,7 @@ using namespace acq;
 
 // Build-time switches of the experiment variants (tools/build_variants.py); the product library defines none of
 // them and reads no environment variable.
-//   ACQ_FORCE_PDL=0|1        programmatic dependent launch off / always (default: by search size)
+//   ACQ_FORCE_PDL=0|1        programmatic dependent launch off / on (default: on for every search)
 //   ACQ_FORCE_E1B_KERNEL=1|2 one-CTA / cluster form of the E1B search regardless of the tile count
 //   ACQ_HOST_RECORDS=0       records through device memory + copy even for small searches
 #ifndef ACQ_FORCE_PDL
@@ -377,11 +377,12 @@ int enqueue_search(acq_engine *e, const uint8_t *packed_dev, int n_captures, acq
     const bool prof = e->profiling;
     if (e->dev_pending) CU(cudaStreamWaitEvent(st, e->dev_done, 0));  // a no-op on the stream that recorded it
     // Programmatic dependent launch between the kernels of a search: a gain where the search is a few waves of tiles
-    // (single captures: 85 -> 77 us for the reference's 32-PRN cold start), a measured 3 % loss on long searches
-    // (the search CTAs are placed while the forward FFT still holds SMs), so by default only up to 64 tiles per SM.
-    // Event records between the kernels (profiling) would serialise them anyway.
-    const long long tiles_total = (long long)n_captures * e->n_slots * e->n_dop * K;
-    const bool pdl = !prof && (ACQ_FORCE_PDL == 1 || (ACQ_FORCE_PDL < 0 && tiles_total <= 64LL * e->sm_count));
+    // (single captures: 85 -> 77 us for the reference's 32-PRN cold start) and, since every kernel of the chain asks for
+    // the same shared-memory carveout (search_kernels_configure), a small one on long searches too (K = 20: 3.453 ->
+    // 3.437 ms, E1B with K = 4: 0.709 -> 0.702 ms, a 128-capture farm 5.97 -> 5.95 ms).  Before that it cost long searches
+    // 3 %: an SM had to empty before it could change its split, so the search CTAs of the early-launched grid were placed
+    // unevenly.  Event records between the kernels (profiling) would serialise them anyway.
+    const bool pdl = !prof && ACQ_FORCE_PDL != 0;
     if (++e->epoch >= 0xfffffffeu) e->epoch = 1;
     if (prof) CU(cudaEventRecord(e->prof[0], st));
     if (packed_host_arg) {   // one 1-bit block still in host memory: it rides in the front end's launch
