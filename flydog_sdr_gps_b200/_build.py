@@ -57,7 +57,9 @@ VARIANTS = {
     "l1_multi_tw": ["ACQ_VARIANT_L1_MULTI_TW"],  # K > 1 C/A search with the twiddles (not the code run) in tensor memory
     "l1_mst": ["ACQ_VARIANT_L1_MST"],        # K > 1 C/A search in the two-team form with staging warps (measured: no gain)
     "l1_cta": ["ACQ_FORCE_L1_CTA=1"],        # K = 1 C/A search always by k_search_l1<false> (two CTAs per SM, thread 0 stages)
-    "l1_dr_all": ["ACQ_DR_MIN_TILES_PER_SM=0"],  # K = 1 full-bin C/A search by k_search_l1_dr at every size (the product: from 12 tiles per SM)
+    "l1_dr_all": ["ACQ_DR_MIN_TILES_PER_SM=0"],  # K = 1 full-bin C/A search by k_search_l1_dr at every size (the product: never)
+    "l1_dr12": ["ACQ_DR_MIN_TILES_PER_SM=12"],   # ... from 12 tiles per SM (the product for most of round 2)
+    "l1_nocr": ["ACQ_L1_CR=0"],              # full-bin K = 1 searches on k_search_l1<false> at every size (the product: k_search_l1_cr where tiles are claimed)
     "l1_sp": ["ACQ_VARIANT_L1_SP"],          # K = 1 C/A search software-pipelined across sub-FFTs, one CTA per SM (measured: -3.7 %)
     "l1_st": ["ACQ_VARIANT_L1_ST"],          # staging warps only (capture residue still staged per sub-FFT): +1.9 %
     "l1_ldg": ["ACQ_VARIANT_L1_LDG"],        # C/A search, operands straight from L2

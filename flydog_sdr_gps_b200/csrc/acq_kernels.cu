@@ -595,6 +595,7 @@ struct TileIdx {
 // (Tried against the greedy tail and dropped: the late-resident CTA of each SM -- block index in the upper half of the
 // grid -- stops claiming once no more than one tile per SM is left, so that the last tiles run one per SM.  Slower
 // everywhere: 32 PRNs x 41 bins 80.1 us against 78.8 us through acq_search, the 82-PRN search 167.9 against 164.4 us.)
+constexpr unsigned kNoTile = 0xffffffffu;
 __device__ __forceinline__ unsigned claim_tile(const SearchArgs &p, unsigned cur)
 {
     if (!p.tile_ctr) return cur + gridDim.x;
@@ -1245,6 +1246,12 @@ __host__ __device__ constexpr size_t l1_multi_smem_bytes()
     return sizeof(float2) * (size_t)(2 * kSub + kEBufElems) + 16 + sizeof(float2) * kT2Elems + 64 * sizeof(float);
 }
 
+// Residue loop fully unrolled (24 bytes of spill): cfg2 3.53 ms rolled, 3.33 ms by two, 3.21 ms by four on one box, with
+// claimed tiles.  (On the static stride, earlier in round 2, the factor made no difference: the slower CTA of each SM
+// set the pace.)
+#ifndef ACQ_MULTI_UNROLL
+#define ACQ_MULTI_UNROLL 4
+#endif
 __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -1305,7 +1312,8 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
         float2 acc[16];
         for (int b = 0; b < p.K; b++) {
             float2 x[16];
-#pragma unroll 1
+            constexpr int kMultiUnroll = ACQ_MULTI_UNROLL;
+#pragma unroll kMultiUnroll
             for (int k2 = 0; k2 < 4; k2++) {
                 float2 *S1b = s.S1 + (it & 1) * kSub;
                 const float2 *Dk = S1b + t;
@@ -1358,6 +1366,174 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
         pend_d = ti.d;
         par ^= 1;
         if (!next_tile(feed, ti)) break;   // published behind the barrier of the second-to-last sub-FFT, read behind the last
+    }
+    __syncthreads();
+    if (t == 0 && pend_cap >= 0) flush();
+    claims_done(p, t);
+    search_cta_epilogue(p, t);
+    ACQ_TRACE_STAMP(kTrSearchL1, 2);
+    tmem_free_cta<2 * kTwCols>(tmem_base, t);
+}
+
+// k_search_l1_cr -- K = 1 on full bins with the CAPTURE operand resident in tensor memory and tiles claimed in CHUNKS.
+// The idea of k_search_l1_dr (a thread always reads the same 16 values of a capture residue: 4 residues x 16 complex = its
+// 128 TMEM columns, so D is staged and parked once and comes back by one tcgen05.ld per sub-FFT) in the two-CTAs-per-SM
+// form that claims its work: a CTA draws runs of consecutive tiles (same capture, bar the boundaries), 16 tiles long while
+// the launch is young, 4 and then single tiles towards its end (SearchArgs::ck_n16 / ck_n4, search_chunks()), so the
+// greedy tail stays one tile long while D is re-staged for ~1 tile in 14.  Stage-B twiddles: the 7.5 KiB shared table;
+// stage-A bases: the global table (as k_search_l1_multi, whose shared-memory layout this kernel uses).  Same arithmetic in
+// the same order as k_search_l1<false>: bitwise-equal cells (tested).
+__device__ __forceinline__ bool chunk_of(const SearchArgs &p, unsigned c, unsigned &start, unsigned &len)
+{
+    if (c < p.ck_n16) {
+        start = 16u * c, len = 16u;
+        return true;
+    }
+    c -= p.ck_n16;
+    if (c < p.ck_n4) {
+        start = 16u * p.ck_n16 + 4u * c, len = 4u;
+        return true;
+    }
+    c -= p.ck_n4;
+    start = 16u * p.ck_n16 + 4u * p.ck_n4 + c, len = 1u;
+    return start < (unsigned)p.n_tiles;
+}
+
+// Residue loop fully unrolled (126 registers, no spill): on a 128-capture farm 5.98 ms rolled, 5.49 ms by two, 5.24 ms by
+// four (28.1 / 30.6 / 32.1 M tiles/s; k_search_l1<false> with claimed tiles: 5.78 ms, k_search_l1_dr: 5.96 ms).
+#ifndef ACQ_CR_UNROLL
+#define ACQ_CR_UNROLL 4
+#endif
+__global__ void __launch_bounds__(256, 2) k_search_l1_cr(const SearchArgs p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    L1MultiSmem s;
+    s.S1 = reinterpret_cast<float2 *>(smem);
+    s.E = s.S1 + 2 * kSub;
+    s.bar = reinterpret_cast<unsigned long long *>(s.E + kEBufElems);
+    s.T2 = reinterpret_cast<float2 *>(s.bar + 2);
+    s.red_f = reinterpret_cast<float *>(s.T2 + kT2Elems);  // [2 parities][16], then the TMEM slot at [48]
+    s.red_i = reinterpret_cast<int *>(s.red_f + 32);        // [2 parities][8]
+    float *red_f = s.red_f;
+    int *red_i = s.red_i;
+    const int t = threadIdx.x;
+    ACQ_TRACE_STAMP(kTrSearchL1, 0);
+    constexpr int L = ACQ_LAGS_L1;
+    const uint32_t tmem_base = tmem_alloc_cta<2 * kTwCols>(reinterpret_cast<uint32_t *>(red_f + 48), t);
+    const uint32_t d_taddr = tmem_base + tmem_lane_base(t) + (uint32_t)((t >> 7) * kTwCols);  // [k2][16 complex]
+    {   // stage-B twiddle table into shared memory
+        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
+        float4 *dst = reinterpret_cast<float4 *>(s.T2);
+        for (int i = t; i < kT2Elems / 2; i += 256) dst[i] = __ldg(src + i);
+    }
+    const float2 *bases = p.tables + kT2Elems + t;  // [k2][256]: W16384^{4t+k2}
+    float2 bw = __ldg(bases);
+    const uint32_t bar = smem_u32(s.bar);
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (p.wait_prior) pdl_wait();
+    ACQ_TRACE_STAMP(kTrSearchL1, 1);
+    pdl_trigger_search();
+    // thread 0: stage the operands of sub-FFT (tn, k2n) -- E always, D (into S1 half `half`) only while the capture is new
+    auto issue = [&](const TileIdx &tn, bool fresh_n, int k2n, int half) {
+        const int r = (k2n - tn.dop) & 3;
+        const int q = (k2n - tn.dop - r) >> 2;
+        const float2 *Ek = p.Ep + (size_t)(tn.sat * 4 + r) * p.ext_len + ((p.Q + q) & ~1);
+        fence_proxy_async();  // generic-proxy reads of these buffers (ordered by the CTA barrier) before the async writes
+        mbar_expect_tx(bar, (uint32_t)(sizeof(float2) * (kEBufElems + (fresh_n ? kSub : 0))));
+        tma_load_1d(smem_u32(s.E), Ek, (uint32_t)(sizeof(float2) * kEBufElems), bar);
+        if (fresh_n) {
+            const float2 *Dk = p.Dp + d_row(p, tn, 0) * kN + k2n * kSub;
+            tma_load_1d(smem_u32(s.S1 + half * kSub), Dk, (uint32_t)(sizeof(float2) * kSub), bar);
+        }
+    };
+    // Chunk feed.  The CTA's first chunk is number blockIdx.x (the grid never exceeds the chunk count); thread 0 claims
+    // the next one during the first sub-FFT of a chunk's LAST tile, publishes the next tile (inside the chunk: the
+    // successor) behind the barrier of sub-FFT 2 and stages it behind that of sub-FFT 3.  feed[8]: the next tile belongs
+    // to another capture (D is staged and parked again), feed[9]: tiles left in its chunk behind it.
+    int *feed = red_i + 20;
+    unsigned cur, left;
+    chunk_of(p, blockIdx.x, cur, left);
+    left -= 1;
+    TileIdx ti(p, cur);
+    bool fresh = true;
+    unsigned nxt_chunk = blockIdx.x;   // thread 0: the chunk being run, then the claimed one
+    if (t == 0) issue(ti, true, 0, 0);
+    int it = 0;  // sub-FFT counter: S1 half and mbarrier phase parity = it & 1
+    int par = 0, pend_cap = -1, pend_slot = 0, pend_d = 0;
+    auto flush = [&]() {   // thread 0: the previous tile's peak (deferred cross-warp merge, see k_search_l1)
+        store_cell(p, pend_cap, pend_slot, pend_d, merge_warp_peaks(red_f + 16 * (par ^ 1), red_i + 8 * (par ^ 1)), L);
+    };
+
+    for (;;) {
+        float P[16];
+        float2 acc[16];
+        float2 x[16];
+        constexpr int kCrUnroll = ACQ_CR_UNROLL;
+#pragma unroll kCrUnroll
+        for (int k2 = 0; k2 < 4; k2++) {
+            float2 *S1b = s.S1 + (it & 1) * kSub;
+            const int r = (k2 - ti.dop) & 3;
+            const int q = (k2 - ti.dop - r) >> 2;
+            const float2 *Ek = s.E + ((p.Q + q) & 1) + t;
+            if (fresh) {   // D from the staged residue; park this thread's 16 values for the capture's other tiles
+                const float2 *Dk = S1b + t;
+                mbar_wait(bar, (uint32_t)(it & 1));
+#pragma unroll
+                for (int a = 0; a < 16; a++) x[a] = Dk[256 * a];
+                tmem_st16(d_taddr + 32 * k2, x);
+                tmem_wait_st();
+            } else {
+                tmem_ld16(d_taddr + 32 * k2, x);
+                mbar_wait(bar, (uint32_t)(it & 1));
+                tmem_wait_ld();
+            }
+            // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471)
+#pragma unroll
+            for (int a = 0; a < 16; a++) x[a] = cmul_conj_a(x[a], Ek[256 * a]);
+            subfft4096_inv4s(x, k2, bw, S1b, t, s.T2, BaseFromGlobal{bases}, [&]() {
+                if (t == 0) {  // every warp is past its operand reads of this sub-FFT and past stage C of the previous one
+                    if (k2 == 0 && left == 0) nxt_chunk = p.tile_ctr ? gridDim.x + atomicAdd(p.tile_ctr, 1u) : nxt_chunk + gridDim.x;
+                    if (k2 == 2) {
+                        unsigned ntile = cur + 1, nleft = left - 1;
+                        bool valid = true;
+                        if (left == 0) {
+                            valid = chunk_of(p, nxt_chunk, ntile, nleft);
+                            nleft -= 1;
+                        }
+                        publish_tile(feed, p, valid ? ntile : kNoTile);
+                        feed[8] = valid && feed[3] != ti.cap;
+                        feed[9] = (int)nleft;
+                        feed[10] = (int)ntile;
+                    }
+                    if (k2 < 3) issue(ti, fresh, k2 + 1, (it + 1) & 1);
+                    else {
+                        TileIdx tn;
+                        if (next_tile(feed, tn)) issue(tn, feed[8] != 0, 0, (it + 1) & 1);
+                    }
+                }
+            });
+            it++;
+            if (t == 0 && k2 == 0 && pend_cap >= 0) flush();
+            if (k2 == 0) {
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) acc[n2] = x[r16(n2)];
+            } else {
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) acc[n2] = cfma(x[r16(n2)], c_cC[k2][n2], acc[n2]);
+            }
+        }
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) P[n2] = cpower(acc[n2]);
+        warp_reduce_peak_redux(thread_peak_l1(P, t), red_f + 16 * par, red_i + 8 * par, t);
+        pend_cap = ti.cap;
+        pend_slot = ti.slot;
+        pend_d = ti.d;
+        par ^= 1;
+        if (!next_tile(feed, ti)) break;   // published behind the barrier of sub-FFT 2, read behind that of sub-FFT 3
+        fresh = feed[8] != 0;
+        left = (unsigned)feed[9];
+        cur = (unsigned)feed[10];
     }
     __syncthreads();
     if (t == 0 && pend_cap >= 0) flush();
@@ -1607,6 +1783,10 @@ __host__ __device__ constexpr size_t e1b_multi_smem_bytes()
 }
 constexpr int kE1bPowCol = 96;  // TMEM columns [96, 128): block powers of the lags with n2 >= 8, index 4 (n2 - 8) + m
 
+// Residue loop fully unrolled (16 bytes of spill): cfg3 with K = 4 0.721 ms rolled, 0.716 by two, 0.701 by four.
+#ifndef ACQ_E1B_MULTI_UNROLL
+#define ACQ_E1B_MULTI_UNROLL 4
+#endif
 __global__ void __launch_bounds__(256, 2) k_search_e1b_multi(const SearchArgs p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -1660,7 +1840,8 @@ __global__ void __launch_bounds__(256, 2) k_search_e1b_multi(const SearchArgs p)
         int bn2[4] = {0, 0, 0, 0};
         for (int b = 0; b < p.K; b++) {
             float2 x[16];
-#pragma unroll 1
+            constexpr int kE1bMultiUnroll = ACQ_E1B_MULTI_UNROLL;
+#pragma unroll kE1bMultiUnroll
             for (int k2 = 0; k2 < 4; k2++) {
                 float2 *S1b = s.S1 + (it & 1) * kSub;
                 {   // x[a] = conj(data[k]) * code[k - dop], k = 1024 a + 4 t + k2   (search.cpp:471); E straight from L2
@@ -2142,6 +2323,7 @@ cudaError_t search_kernels_configure()
     if ((e = cudaFuncSetAttribute(k_search_l1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
 #endif
     if ((e = cudaFuncSetAttribute(k_search_l1_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_multi_smem_bytes()))) return e;
+    if ((e = cudaFuncSetAttribute(k_search_l1_cr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_multi_smem_bytes()))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b, cudaFuncAttributeMaxDynamicSharedMemorySize, e1))) return e;
     if ((e = cudaFuncSetAttribute(k_search_e1b_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e1b_multi_smem_bytes()))) return e;
 #ifdef ACQ_VARIANT_L1_X3
@@ -2177,7 +2359,7 @@ cudaError_t search_kernels_configure()
     const void *chain[] = {(const void *)k_front_end<false>, (const void *)k_front_end<true>, (const void *)k_front_end_arg,
                            (const void *)k_fwd_fft<true>, (const void *)k_fwd_fft<false>, (const void *)k_fwd_fft_cluster<true>,
                            (const void *)k_fwd_fft_cluster<false>, (const void *)k_search_l1<false>, (const void *)k_search_l1<true>,
-                           (const void *)k_search_l1_dr, (const void *)k_search_l1_multi, (const void *)k_search_e1b,
+                           (const void *)k_search_l1_dr, (const void *)k_search_l1_cr, (const void *)k_search_l1_multi, (const void *)k_search_e1b,
                            (const void *)k_search_e1b_multi, (const void *)k_search_e1b_cluster<false>,
                            (const void *)k_search_e1b_cluster<true>, (const void *)k_pick_small, (const void *)k_best_dop};
     for (const void *f : chain)
@@ -2256,21 +2438,29 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
 
 // Grid of a search launch = the number of its CTAs that store cells (clusters: rank 0 stores for its cluster).
 // launch_search* and the host's SearchArgs::ctas_total both come from here.
-// Which C/A search kernel a search runs: non-coherent sums -> k_search_l1_multi; K = 1 on full bins -> k_search_l1_dr
-// (the capture spectrum, the same for every Doppler index of a capture, stays in tensor memory); K = 1 on half-bins ->
-// k_search_l1<false> (odd and even half-bins read different capture spectra, so nothing could stay resident).
-// Short full-bin searches (fewer than kDrMinTilesPerSm tiles per SM: the reference's own one-capture search is 8.9) also
-// run k_search_l1<false>: its 296 strided CTAs spread a handful of rounds more evenly than 296 contiguous team ranges
-// (a team left with one tile more than its neighbour runs it alone on the SM at 1.3x, not 2x, the shared rate), and the
-// two-team CTA's longer prologue shows once the search is over in 50 us.  Measured through acq_search, hot caches
-// (tools/e2e_latency.py): 32 PRNs x 41 bins 76.0 us against 79.2 us, one satellite 34.1 against 35.8 us.
+// Which C/A search kernel a search runs: non-coherent sums -> k_search_l1_multi (code run resident in tensor memory);
+// K = 1 on full bins -> k_search_l1_cr (capture residue resident in tensor memory, chunks of tiles claimed); K = 1 on
+// half-bins -> k_search_l1<false> (odd and even half-bins read different capture spectra: nothing could stay resident).
+// k_search_l1_dr (one CTA per SM, two teams with staging warps, capture residue resident, contiguous team ranges) was the
+// K = 1 full-bin kernel for most of round 2: +4.7 % over k_search_l1<false> ON THE STATIC STRIDE (6.30 -> 6.02 ms,
+// 128-capture farm).  Most of that turned out to be the static stride's own loss -- the two CTAs of an SM run at
+// different rates (see claim_tile) -- which the two-team CTA happened not to have: with claimed tiles k_search_l1<false>
+// does the same farm in 5.78 ms, k_search_l1_dr in 5.96 ms, and k_search_l1_cr -- the resident capture residue in the
+// two-CTA form, residue loop fully unrolled at 126 registers -- in 5.24 ms (32.1 M tiles/s).  On the reference's
+// one-capture search: 70.9 us through acq_search against 75.4 us (k_search_l1<false>) and 77.5 us (k_search_l1_dr).
+// k_search_l1_dr stays in the library for the equivalence tests and A/B runs: ACQ_DR_MIN_TILES_PER_SM >= 0 (variants
+// l1_dr_all = 0, l1_dr12 = 12) sends full-bin K = 1 searches of at least that many tiles per SM to it.
 #ifndef ACQ_FORCE_L1_CTA
 #define ACQ_FORCE_L1_CTA 0   // variant l1_cta: always k_search_l1<false> for K = 1 (the kernel-equivalence tests)
 #endif
 #ifndef ACQ_DR_MIN_TILES_PER_SM
-#define ACQ_DR_MIN_TILES_PER_SM 12   // variant l1_dr_all: 0
+#define ACQ_DR_MIN_TILES_PER_SM -1   // product: never
 #endif
 constexpr int kDrMinTilesPerSm = ACQ_DR_MIN_TILES_PER_SM;
+#ifndef ACQ_L1_CR
+#define ACQ_L1_CR 1   // 0 (variant l1_nocr): full-bin K = 1 searches on k_search_l1<false>
+#endif
+bool search_claims_tiles(long long n_tiles, int grid);
 int search_kind_l1(int K, int half_bin, long long n_tiles, int sm_count)
 {
 #if defined(ACQ_VARIANT_L1_X3) || defined(ACQ_VARIANT_L1_LDG) || defined(ACQ_VARIANT_L1_MULTI_TW)
@@ -2281,7 +2471,9 @@ int search_kind_l1(int K, int half_bin, long long n_tiles, int sm_count)
 #endif
     if (K > 1) return kSearchL1Multi;
     if (half_bin || ACQ_FORCE_L1_CTA) return kSearchL1;
-    return n_tiles < (long long)kDrMinTilesPerSm * sm_count ? kSearchL1 : kSearchL1Dr;
+    if (kDrMinTilesPerSm >= 0) return n_tiles < (long long)kDrMinTilesPerSm * sm_count ? kSearchL1 : kSearchL1Dr;
+    // full bins: the capture-resident kernel (chunks claimed from six rounds of tiles per CTA up, static stride below)
+    return ACQ_L1_CR ? kSearchL1Cr : kSearchL1;
 }
 
 // Claimed tiles or the static stride?  Claiming evens out the two CTAs of an SM and the SMs among themselves, at the price
@@ -2298,9 +2490,35 @@ bool search_claims_tiles(long long n_tiles, int grid)
     return grid > 0 && n_tiles >= (long long)ACQ_DYN_MIN_ROUNDS * grid;
 }
 
+// Chunk schedule of k_search_l1_cr: runs of 16 tiles, then of 4, then single tiles -- the last two rounds of the launch
+// (2 x grid tiles) go out one by one and the two rounds' worth before them in fours, so the tail stays one tile long.
+void search_chunks(long long n_tiles, int grid, unsigned *n16, unsigned *n4)
+{
+    *n16 = *n4 = 0;
+    if (!search_claims_tiles(n_tiles, grid)) return;   // static stride: single tiles, tile = blockIdx.x + i gridDim.x
+    const long long singles = 2LL * grid, fours = 8LL * grid;
+    long long t2 = n_tiles - singles;
+    if (t2 < 0) t2 = 0;
+    long long t1 = t2 - fours;
+    if (t1 < 0) t1 = 0;
+    t1 -= t1 % 16;
+    *n16 = (unsigned)(t1 / 16);
+    *n4 = (unsigned)((t2 - t1) / 4);
+}
+long long search_chunk_count(long long n_tiles, int grid)
+{
+    unsigned n16, n4;
+    search_chunks(n_tiles, grid, &n16, &n4);
+    return (long long)n16 + n4 + (n_tiles - 16LL * n16 - 4LL * n4);
+}
+
 int search_grid_ctas(long long n_tiles, int kind, int sm_count)
 {
     if (n_tiles <= 0 || n_tiles > kMaxTilesPerLaunch) return 0;
+    if (kind == kSearchL1Cr) {
+        const long long chunks = search_chunk_count(n_tiles, 2 * sm_count);
+        return (int)(chunks < 2LL * sm_count ? chunks : 2LL * sm_count);
+    }
     long long cap = (long long)sm_count * 2;  // two persistent CTAs per SM
     if (kind == kSearchE1bCluster) cap = sm_count / 4;
     if (kind == kSearchL1Dr || kind == kSearchL1Mst) cap = sm_count;   // one CTA per SM, two teams in it
@@ -2339,6 +2557,10 @@ int launch_search(const SearchArgs &a_in, bool e1b, int sm_count, cudaStream_t s
     else
 #endif
     if (a.K > 1) launch_k(k_search_l1_multi, grid, 256, l1_multi_smem_bytes(), st, pdl, a);
+    else if (kind == kSearchL1Cr) {
+        search_chunks(a.n_tiles, 2 * sm_count, &a.ck_n16, &a.ck_n4);
+        launch_k(k_search_l1_cr, grid, 256, l1_multi_smem_bytes(), st, pdl, a);
+    }
 #if defined(ACQ_VARIANT_L1_SP)
     else if (kind == kSearchL1Dr) launch_k(k_search_l1_sp, grid, kSpThreads, sp_smem_bytes(), st, pdl, a);
 #elif defined(ACQ_VARIANT_L1_ST)

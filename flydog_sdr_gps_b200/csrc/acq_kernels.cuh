@@ -31,6 +31,9 @@ struct SearchArgs {
     // them zeroes both words for the next launch.  The C/A and the E1B launch of one search use different pairs
     // (tile_ctr = base + 0 / base + 1).  NULL: static stride.
     unsigned *tile_ctr;
+    // k_search_l1_cr claims CHUNKS of consecutive tiles: ck_n16 chunks of 16 tiles, then ck_n4 of 4, then single tiles
+    // (filled in by launch_search).
+    unsigned ck_n16, ck_n4;
     // 1: wait for the preceding grids of the stream (griddepcontrol.wait).  0: this launch directly follows another
     // search launch of the same search, which has already waited (see launch_search).
     int wait_prior;
@@ -73,7 +76,7 @@ int launch_pick_small(const acq_cell *cells, const int *slot_sat, acq_record *ou
                       unsigned *host_flag, unsigned epoch, int n_rows, int n_slots, int n_dop, int dop_lo, cudaStream_t st,
                       bool pdl = false);
 // CTAs of a search launch that store cells (what SearchArgs::ctas_total sums over the launches of one search)
-enum { kSearchL1 = 0, kSearchE1b = 1, kSearchE1bCluster = 2, kSearchL1Multi = 3, kSearchL1Dr = 4, kSearchL1Mst = 5 };
+enum { kSearchL1 = 0, kSearchE1b = 1, kSearchE1bCluster = 2, kSearchL1Multi = 3, kSearchL1Dr = 4, kSearchL1Mst = 5, kSearchL1Cr = 6 };
 int search_kind_l1(int K, int half_bin, long long n_tiles, int sm_count);   // which C/A search kernel (and so which grid) a search uses
 constexpr int kPickSmallRowsMax = 256;  // rows k_pick_small stages in shared memory
 // A record as k_pick_small hands it to a POLLING host (mapped pinned memory): two 16-byte halves, each carrying the

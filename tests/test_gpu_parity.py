@@ -827,7 +827,8 @@ def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle):
 
 
 def test_capture_resident_kernel_equals_cta_kernel(gpu_required, oracle):
-    """k_search_l1_dr (the K = 1 full-bin product kernel from 12 tiles per SM up: one CTA per SM, two teams of FFT warps with a staging warp each,
+    """k_search_l1_cr (the K = 1 full-bin product kernel wherever tiles are claimed: two CTAs per SM, the capture residue
+    parked in tensor memory, chunks of 16 / 4 / 1 consecutive tiles claimed from a counter) and k_search_l1_dr (one CTA per SM, two teams of FFT warps with a staging warp each,
     contiguous tile ranges, the capture residue parked in tensor memory for all tiles of a capture) against
     k_search_l1<false> (two CTAs per SM striding over the tiles, both operands staged per sub-FFT; variant library l1_cta):
     the same arithmetic in the same order, so the whole per-Doppler table is bitwise equal.  Shapes: one capture (every team
@@ -844,12 +845,13 @@ def test_capture_resident_kernel_equals_cta_kernel(gpu_required, oracle):
              (dict(dop_lo=-20, dop_hi=20), [cap2, cap], np.array([2, 6, 10, 13, 18], np.int32))]
     for kw, caps, sel in cases:
         out = {}
-        # product: k_search_l1_dr from 12 tiles per SM, k_search_l1<false> below; l1_dr_all: k_search_l1_dr at every size
-        for kind, variant in (("product", None), ("dr", "l1_dr_all"), ("cta", "l1_cta")):
+        # product: k_search_l1_cr from six rounds of tiles, k_search_l1<false> below; l1_dr_all: k_search_l1_dr at every size
+        # cr: k_search_l1_cr (capture resident, chunks of tiles claimed) at every size -- the variant that always claims
+        for kind, variant in (("product", None), ("dr", "l1_dr_all"), ("cr", "dyn_tiles"), ("cta", "l1_cta")):
             with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
                 out[kind] = eng.search(np.concatenate(caps), sel=sel, want_grid=True)
         rb, gb = out["cta"]
-        for kind in ("product", "dr"):
+        for kind in ("product", "dr", "cr"):
             ra, ga = out[kind]
             for f in ("peak", "lag", "noise", "snr"):
                 assert np.array_equal(ga[f], gb[f]), (kind, kw, len(caps), f)
