@@ -430,6 +430,11 @@ def roofline_of(cfg, table, n_dop, k, n_cap, search_ms, step_kern_ms, mb, peaks)
                        "nominal 148 SM x 128 B/clk x SM clock",
         "algorithmic_bytes_per_launch": smem_b,
         "model": "SURVEY 8(d): %d B of shared-memory traffic per tile (4-pass model); the kernel itself moves fewer" % SMEM_BYTES_PER_TILE[max(lags)],
+        "frac_note": "frac = SURVEY's modelled bytes / kernel time / measured shared-memory peak. The kernels move fewer bytes "
+                     "than the model charges (three exchanges instead of four passes, pruned output, one operand and the "
+                     "parked values through tensor memory), so frac can exceed 1; frac_pipe_measured (ncu wavefronts of the "
+                     "committed profile x 128 B / live kernel time / peak) is the physical utilisation of the L1/shared pipe, "
+                     "fp32.frac that of the FP32 lanes",
         "kernel_ms": search_ms, "kernel_share_of_step": search_ms / step_kern_ms if step_kern_ms else None,
         "traffic": ctr.get("dram_bytes_per_tile") and ctr["dram_bytes_per_tile"] * tiles,
         "achieved_smem": smem_ach, "achieved_fp32": fp32_ach, "achieved_hbm": hbm_ach,

@@ -8,8 +8,8 @@ import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (config, summary file, tiles of the captured launch, what ran)
 CAPTURES = [
-    ("cfg5", "r2_ncu_l1_k1_cfg5.json", 128 * 32 * 41, "k_search_l1_dr, 128 captures x 32 PRNs x 41 bins (tools/ncu_driver.py cfg5 128)"),
-    ("cfg1", "r2_ncu_l1_k1_cfg1.json", 32 * 41, "k_search_l1<false> (short searches), one capture x 32 PRNs x 41 bins"),
+    ("cfg5", "r2_ncu_l1_k1_cfg5.json", 128 * 32 * 41, "k_search_l1_cr, 128 captures x 32 PRNs x 41 bins (tools/ncu_driver.py cfg5 128)"),
+    ("cfg1", "r2_ncu_l1_k1_cfg1.json", 32 * 41, "k_search_l1_cr on the static stride, one capture x 32 PRNs x 41 bins"),
     ("cfg2", "r2_ncu_l1_multi_cfg2.json", 32 * 161 * 20, "k_search_l1_multi, 32 PRNs x 161 half-bins x K = 20"),
     ("cfg3", "r2_ncu_e1b_cfg3.json", 50 * 81, "k_search_e1b, 50 PRNs x 81 bins"),
     ("cfg3_k4", "r2_ncu_e1b_multi_cfg3k4.json", 50 * 81 * 4, "k_search_e1b_multi, 50 PRNs x 81 bins x K = 4"),
