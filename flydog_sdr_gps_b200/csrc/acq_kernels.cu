@@ -1383,19 +1383,26 @@ __global__ void __launch_bounds__(256, 2) k_search_l1_multi(const SearchArgs p)
 // greedy tail stays one tile long while D is re-staged for ~1 tile in 14.  Stage-B twiddles: the 7.5 KiB shared table;
 // stage-A bases: the global table (as k_search_l1_multi, whose shared-memory layout this kernel uses).  Same arithmetic in
 // the same order as k_search_l1<false>: bitwise-equal cells (tested).
+#ifndef ACQ_CK_BIG
+#define ACQ_CK_BIG 16
+#endif
+#ifndef ACQ_CK_MID
+#define ACQ_CK_MID 4
+#endif
+constexpr unsigned kCkBig = ACQ_CK_BIG, kCkMid = ACQ_CK_MID;   // chunk lengths (SearchArgs::ck_n16 counts the big ones, ck_n4 the middle ones)
 __device__ __forceinline__ bool chunk_of(const SearchArgs &p, unsigned c, unsigned &start, unsigned &len)
 {
     if (c < p.ck_n16) {
-        start = 16u * c, len = 16u;
+        start = kCkBig * c, len = kCkBig;
         return true;
     }
     c -= p.ck_n16;
     if (c < p.ck_n4) {
-        start = 16u * p.ck_n16 + 4u * c, len = 4u;
+        start = kCkBig * p.ck_n16 + kCkMid * c, len = kCkMid;
         return true;
     }
     c -= p.ck_n4;
-    start = 16u * p.ck_n16 + 4u * p.ck_n4 + c, len = 1u;
+    start = kCkBig * p.ck_n16 + kCkMid * p.ck_n4 + c, len = 1u;
     return start < (unsigned)p.n_tiles;
 }
 
@@ -2496,20 +2503,20 @@ void search_chunks(long long n_tiles, int grid, unsigned *n16, unsigned *n4)
 {
     *n16 = *n4 = 0;
     if (!search_claims_tiles(n_tiles, grid)) return;   // static stride: single tiles, tile = blockIdx.x + i gridDim.x
-    const long long singles = 2LL * grid, fours = 8LL * grid;
+    const long long singles = 2LL * grid, mids = 2LL * kCkMid * grid;
     long long t2 = n_tiles - singles;
     if (t2 < 0) t2 = 0;
-    long long t1 = t2 - fours;
+    long long t1 = t2 - mids;
     if (t1 < 0) t1 = 0;
-    t1 -= t1 % 16;
-    *n16 = (unsigned)(t1 / 16);
-    *n4 = (unsigned)((t2 - t1) / 4);
+    t1 -= t1 % kCkBig;
+    *n16 = (unsigned)(t1 / kCkBig);
+    *n4 = (unsigned)((t2 - t1) / kCkMid);
 }
 long long search_chunk_count(long long n_tiles, int grid)
 {
     unsigned n16, n4;
     search_chunks(n_tiles, grid, &n16, &n4);
-    return (long long)n16 + n4 + (n_tiles - 16LL * n16 - 4LL * n4);
+    return (long long)n16 + n4 + (n_tiles - (long long)kCkBig * n16 - (long long)kCkMid * n4);
 }
 
 int search_grid_ctas(long long n_tiles, int kind, int sm_count)
