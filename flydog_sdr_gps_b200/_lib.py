@@ -43,8 +43,14 @@ _SIGNATURES = [
     ("acq_set_profiling", C.c_int, [_P, C.c_int]),
     ("acq_get_kernel_ms", C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     ("acq_device_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("acq_plan_launch", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
     ("acq_microbench", C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_int]),
 ]
+
+
+class AcqLaunchPlan(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("grid", C.c_int32), ("claims", C.c_int32), ("chunk_big", C.c_int32),
+                ("chunk_mid", C.c_int32), ("n_big", C.c_uint32), ("n_mid", C.c_uint32), ("n_chunks", C.c_int64)]
 
 
 def exported_symbols():

@@ -991,6 +991,26 @@ int acq_get_params(const acq_engine *e, acq_params *p)
 
 int64_t acq_launch_count(const acq_engine *e) { return e ? e->launches : 0; }
 
+int acq_plan_launch(int k_noncoh, int half_bin, int e1b, int64_t n_tiles, int sm_count, acq_launch_plan *out)
+{
+    if (!out || k_noncoh < 1 || sm_count < 1 || n_tiles < 1 || n_tiles > acq::kMaxTilesPerLaunch)
+        return fail(ACQ_ERR_ARG, "acq_plan_launch: bad argument");
+    memset(out, 0, sizeof *out);
+    int kind;
+    if (e1b) kind = (ACQ_FORCE_E1B_KERNEL == 2 || (ACQ_FORCE_E1B_KERNEL == 0 && n_tiles <= sm_count / 4)) ? acq::kSearchE1bCluster : acq::kSearchE1b;
+    else kind = acq::search_kind_l1(k_noncoh, half_bin, n_tiles, sm_count);
+    out->kernel = kind;
+    out->grid = acq::search_grid_ctas(n_tiles, kind, sm_count);
+    out->claims = kind != acq::kSearchE1bCluster && kind != acq::kSearchL1Dr && acq::search_claims_tiles(n_tiles, out->grid);
+    out->n_chunks = n_tiles;
+    acq::search_chunk_lengths(&out->chunk_big, &out->chunk_mid);
+    if (kind == acq::kSearchL1Cr) {
+        acq::search_chunks(n_tiles, 2 * sm_count, &out->n_big, &out->n_mid);
+        out->n_chunks = acq::search_chunk_count(n_tiles, 2 * sm_count);
+    }
+    return ACQ_OK;
+}
+
 int acq_set_profiling(acq_engine *e, int enable)
 {
     if (!e) return fail(ACQ_ERR_ARG, "engine is NULL");

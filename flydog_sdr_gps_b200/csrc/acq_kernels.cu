@@ -2519,6 +2519,12 @@ long long search_chunk_count(long long n_tiles, int grid)
     return (long long)n16 + n4 + (n_tiles - (long long)kCkBig * n16 - (long long)kCkMid * n4);
 }
 
+void search_chunk_lengths(int *big, int *mid)
+{
+    *big = (int)kCkBig;
+    *mid = (int)kCkMid;
+}
+
 int search_grid_ctas(long long n_tiles, int kind, int sm_count)
 {
     if (n_tiles <= 0 || n_tiles > kMaxTilesPerLaunch) return 0;

@@ -90,6 +90,11 @@ struct acq_record_tagged {
 };
 static_assert(sizeof(acq_record_tagged) == 32, "two 16-byte halves");
 int search_grid_ctas(long long n_tiles, int kind, int sm_count);
+bool search_claims_tiles(long long n_tiles, int grid);   // tiles claimed from a counter (true) or the static stride
+// chunk schedule of k_search_l1_cr (SearchArgs::ck_n16 / ck_n4) and the chunk lengths it was built with
+void search_chunks(long long n_tiles, int grid, unsigned *n_big, unsigned *n_mid);
+long long search_chunk_count(long long n_tiles, int grid);
+void search_chunk_lengths(int *big, int *mid);
 // refinement of the records of the most recent search (one CTA per record)
 int launch_refine(const float2 *Dp, const float2 *Ep, const acq_record *rec, const int *sat_type, acq_fine *out, int n_rows,
                   int n_slots, int K, int nvar, int half_bin, int ext_len, int Q, int n_shift, int smax, int cd_div,

@@ -233,6 +233,22 @@ int acq_get_kernel_ms(acq_engine *e, float *out, int n_out);
 /* Device ordinal and SM count of the engine's GPU. */
 int acq_device_info(const acq_engine *e, int *device, int *sm_count, int *sm_clock_khz);
 
+/* How a search launch of n_tiles tiles (captures x satellites of one family x Doppler indices) would be laid out on a GPU
+ * with sm_count SMs: pure host arithmetic, no device needed (tests, bring-up).  e1b: 0 = C/A family, 1 = Galileo E1B.
+ *   kernel    : 0 k_search_l1, 1 k_search_e1b, 2 k_search_e1b_cluster, 3 k_search_l1_multi, 6 k_search_l1_cr
+ *               (1 also stands for k_search_e1b_multi when k_noncoh > 1)
+ *   grid      : CTAs that store cells (clusters count once)
+ *   claims    : 1 = the CTAs claim their work from a counter, 0 = static stride blockIdx.x + i * grid
+ *   chunk_big / chunk_mid / n_big / n_mid / n_chunks : k_search_l1_cr claims runs of consecutive tiles -- n_big chunks of
+ *               chunk_big tiles, then n_mid of chunk_mid, then single tiles; n_chunks in all (other kernels: single
+ *               tiles, n_chunks = n_tiles). */
+typedef struct acq_launch_plan {
+    int32_t kernel, grid, claims, chunk_big, chunk_mid;
+    uint32_t n_big, n_mid;
+    int64_t n_chunks;
+} acq_launch_plan;
+int acq_plan_launch(int k_noncoh, int half_bin, int e1b, int64_t n_tiles, int sm_count, acq_launch_plan *out);
+
 /* On-device micro-benchmarks used as roofline denominators: fills
  *   out[0] = FP32 FFMA  throughput, TFLOP/s      out[1] = packed FFMA2 throughput, TFLOP/s
  *   out[2] = shared-memory read+write bandwidth, TB/s    out[3] = L2->SM read bandwidth, TB/s

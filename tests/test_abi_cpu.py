@@ -195,3 +195,46 @@ def test_bench_workload_descriptions():
     assert bench.farm_signals(5) == bench.farm_signals(5) and bench.farm_signals(5) != bench.farm_signals(6)
     a = bench.farm_captures_numpy([3])[0]
     assert a.shape == (8192,) and np.array_equal(a, bench.farm_captures_numpy([2, 3])[1])
+
+
+def test_launch_plan_covers_every_tile_once():
+    """acq_plan_launch (host arithmetic of launch_search, no device): which kernel, grid, claimed or strided, and the chunk
+    schedule of k_search_l1_cr.  The schedule must tile [0, n_tiles) exactly -- a hole or an overlap would be a silently
+    wrong or missing cell -- with single tiles over the last two rounds, and a launch claims from six rounds up."""
+    L = _lib.load()
+    plan = _lib.AcqLaunchPlan()
+
+    def ask(k, half, e1b, n_tiles, sms=148):
+        assert L.acq_plan_launch(k, half, e1b, n_tiles, sms, C.byref(plan)) == 0, L.acq_last_error()
+        return {f: getattr(plan, f) for f, _ in plan._fields_}
+
+    # the BASELINE shapes on a B200
+    assert ask(1, 0, 0, 1024 * 32 * 41)["kernel"] == 6 and plan.grid == 296 and plan.claims == 1   # cfg5: k_search_l1_cr, chunks claimed
+    assert ask(1, 0, 0, 32 * 41) == dict(kernel=6, grid=296, claims=0, chunk_big=16, chunk_mid=4, n_big=0, n_mid=0, n_chunks=1312)  # cfg1
+    assert ask(1, 0, 0, 41)["grid"] == 41 and plan.claims == 0                                      # one satellite
+    assert ask(20, 1, 0, 32 * 161)["kernel"] == 3 and plan.grid == 296 and plan.claims == 1         # cfg2: k_search_l1_multi
+    assert ask(1, 1, 0, 32 * 161)["kernel"] == 0                                                    # half-bin K = 1: k_search_l1
+    assert ask(1, 0, 1, 50 * 81)["kernel"] == 1 and plan.grid == 296 and plan.claims == 1           # cfg3: k_search_e1b
+    assert ask(1, 0, 1, 30)["kernel"] == 2 and plan.grid == 30 and plan.claims == 0                 # a cluster per tile
+    assert L.acq_plan_launch(1, 0, 0, 0, 148, C.byref(plan)) != 0 and L.acq_plan_launch(1, 0, 0, 2 ** 31, 148, C.byref(plan)) != 0
+
+    rng = np.random.default_rng(5)
+    sizes = [1, 2, 295, 296, 297, 1775, 1776, 1777, 2368, 4143, 4144, 4160, 5248, 167936, 2 ** 31 - 1]
+    sizes += [int(x) for x in rng.integers(1, 3_000_000, 300)]
+    for sms in (148, 132, 7):
+        for n in sizes:
+            d = ask(1, 0, 0, n, sms)
+            g2 = 2 * sms
+            big, mid = d["chunk_big"], d["chunk_mid"]
+            singles = n - big * d["n_big"] - mid * d["n_mid"]
+            assert singles >= 0 and d["n_chunks"] == d["n_big"] + d["n_mid"] + singles, (n, sms, d)
+            assert d["grid"] == min(d["n_chunks"], g2), (n, sms, d)
+            assert d["claims"] == (1 if n >= 6 * d["grid"] else 0), (n, sms, d)
+            if not d["claims"]:
+                assert d["n_big"] == 0 and d["n_mid"] == 0, (n, sms, d)     # static stride: single tiles
+            else:
+                assert singles >= 2 * g2 and singles < 2 * g2 + mid, (n, sms, d)        # the last two rounds go out one by one
+                assert mid * d["n_mid"] < 2 * mid * g2 + big, (n, sms, d)               # about two rounds' worth in middle chunks
+            # chunk c -> [start, start + len): consecutive, gap-free (the device's chunk_of, restated)
+            starts = [0, big * d["n_big"], big * d["n_big"] + mid * d["n_mid"], n]
+            assert starts == sorted(starts), (n, sms, d)
