@@ -827,8 +827,9 @@ def test_three_cta_kernel_equals_two_cta_kernel(gpu_required, oracle):
 
 
 def test_capture_resident_kernel_equals_cta_kernel(gpu_required, oracle):
-    """k_search_l1_cr (the K = 1 full-bin product kernel wherever tiles are claimed: two CTAs per SM, the capture residue
-    parked in tensor memory, chunks of 16 / 4 / 1 consecutive tiles claimed from a counter) and k_search_l1_dr (one CTA per SM, two teams of FFT warps with a staging warp each,
+    """k_search_l1_cr (the K = 1 full-bin product kernel: two CTAs per SM, the capture residue parked in tensor memory,
+    chunks of 16 / 4 / 1 consecutive tiles claimed from a counter once a launch has six rounds of tiles, the static stride
+    below) and k_search_l1_dr (one CTA per SM, two teams of FFT warps with a staging warp each,
     contiguous tile ranges, the capture residue parked in tensor memory for all tiles of a capture) against
     k_search_l1<false> (two CTAs per SM striding over the tiles, both operands staged per sub-FFT; variant library l1_cta):
     the same arithmetic in the same order, so the whole per-Doppler table is bitwise equal.  Shapes: one capture (every team
@@ -845,7 +846,7 @@ def test_capture_resident_kernel_equals_cta_kernel(gpu_required, oracle):
              (dict(dop_lo=-20, dop_hi=20), [cap2, cap], np.array([2, 6, 10, 13, 18], np.int32))]
     for kw, caps, sel in cases:
         out = {}
-        # product: k_search_l1_cr from six rounds of tiles, k_search_l1<false> below; l1_dr_all: k_search_l1_dr at every size
+        # product: k_search_l1_cr (claiming from six rounds of tiles); l1_dr_all: k_search_l1_dr at every size
         # cr: k_search_l1_cr (capture resident, chunks of tiles claimed) at every size -- the variant that always claims
         for kind, variant in (("product", None), ("dr", "l1_dr_all"), ("cr", "dyn_tiles"), ("cta", "l1_cta")):
             with F.AcqEngine(table, F.default_params(**kw), variant=variant) as eng:
