@@ -988,7 +988,7 @@ __global__ void __launch_bounds__(256, 2) k_search_l1(const SearchArgs p)
 // one staging warp per team that takes part in the team's barrier and does all of the above, so no FFT warp ever leaves
 // the common instruction stream.  Five warpgroups: the launch allocates 96 registers per thread, the staging warpgroup
 // drops to 32 (setmaxnreg.dec) and the four FFT warpgroups rise to 112 with exactly what it released.
-constexpr int kStThreads = 640, kStHandOver = 288;   // 2 x 256 FFT threads + a warpgroup of staging warps; hand-over = 8 + 1 warps
+[[maybe_unused]] constexpr int kStThreads = 640, kStHandOver = 288;   // 2 x 256 FFT threads + a warpgroup of staging warps; hand-over = 8 + 1 warps
 // Named barriers of a team (ids 1..3 for team 0, 4..6 for team 1):
 //   A (256 threads): the FFT warps' own barrier, one per sub-FFT;
 //   B (288): hand-over to the staging warp.  Every FFT warp ARRIVES (no wait) just before it waits on A, and the staging
@@ -1061,6 +1061,12 @@ __device__ __forceinline__ DrSmem dr_smem_carve(unsigned char *smem)
     return s;
 }
 
+// Compiled only into the variant libraries that route searches to it (l1_dr_all, l1_dr12): the product library holds no
+// A/B kernel.
+#ifndef ACQ_DR_MIN_TILES_PER_SM
+#define ACQ_DR_MIN_TILES_PER_SM -1   // product: never (see search_kind_l1)
+#endif
+#if ACQ_DR_MIN_TILES_PER_SM >= 0
 __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -1222,6 +1228,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_search_l1_dr(const SearchArgs
     ACQ_TRACE_STAMP(kTrSearchL1, 2);
     tmem_free_cta<4 * kTwCols>(tmem_base, t);
 }
+#endif  // ACQ_DR_MIN_TILES_PER_SM >= 0
 
 
 // k_search_l1_multi -- k_noncoh > 1 with the CODE operand resident in tensor memory.  The code run E of a tile depends on
@@ -2316,7 +2323,9 @@ cudaError_t search_kernels_configure()
     cudaError_t e;
     const int l1 = (int)search_l1_smem_bytes(), e1 = (int)search_e1b_smem_bytes(), fw = (int)fwd_smem_bytes();
     if ((e = cudaFuncSetAttribute(k_search_l1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l1))) return e;
+#if ACQ_DR_MIN_TILES_PER_SM >= 0
     if ((e = cudaFuncSetAttribute(k_search_l1_dr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dr_smem_bytes()))) return e;
+#endif
 #ifdef ACQ_VARIANT_L1_MST
     if ((e = cudaFuncSetAttribute(k_search_l1_mst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dr_smem_bytes()))) return e;
 #endif
@@ -2365,8 +2374,14 @@ cudaError_t search_kernels_configure()
 #if ACQ_CARVEOUT_MAX
     const void *chain[] = {(const void *)k_front_end<false>, (const void *)k_front_end<true>, (const void *)k_front_end_arg,
                            (const void *)k_fwd_fft<true>, (const void *)k_fwd_fft<false>, (const void *)k_fwd_fft_cluster<true>,
-                           (const void *)k_fwd_fft_cluster<false>, (const void *)k_search_l1<false>, (const void *)k_search_l1<true>,
-                           (const void *)k_search_l1_dr, (const void *)k_search_l1_cr, (const void *)k_search_l1_multi, (const void *)k_search_e1b,
+                           (const void *)k_fwd_fft_cluster<false>, (const void *)k_search_l1<false>,
+#ifdef ACQ_VARIANT_L1_MULTI_TW
+                           (const void *)k_search_l1<true>,
+#endif
+#if ACQ_DR_MIN_TILES_PER_SM >= 0
+                           (const void *)k_search_l1_dr,
+#endif
+                           (const void *)k_search_l1_cr, (const void *)k_search_l1_multi, (const void *)k_search_e1b,
                            (const void *)k_search_e1b_multi, (const void *)k_search_e1b_cluster<false>,
                            (const void *)k_search_e1b_cluster<true>, (const void *)k_pick_small, (const void *)k_best_dop};
     for (const void *f : chain)
@@ -2455,8 +2470,8 @@ int launch_build_ext(const float2 *C, float2 *Ep, int n_sats, int Q, int ext_len
 // does the same farm in 5.78 ms, k_search_l1_dr in 5.96 ms, and k_search_l1_cr -- the resident capture residue in the
 // two-CTA form, residue loop fully unrolled at 126 registers -- in 5.24 ms (32.1 M tiles/s).  On the reference's
 // one-capture search: 70.9 us through acq_search against 75.4 us (k_search_l1<false>) and 77.5 us (k_search_l1_dr).
-// k_search_l1_dr stays in the library for the equivalence tests and A/B runs: ACQ_DR_MIN_TILES_PER_SM >= 0 (variants
-// l1_dr_all = 0, l1_dr12 = 12) sends full-bin K = 1 searches of at least that many tiles per SM to it.
+// k_search_l1_dr is compiled only into variant libraries, for the equivalence tests and A/B runs: ACQ_DR_MIN_TILES_PER_SM
+// >= 0 (l1_dr_all = 0, l1_dr12 = 12) sends full-bin K = 1 searches of at least that many tiles per SM to it.
 #ifndef ACQ_FORCE_L1_CTA
 #define ACQ_FORCE_L1_CTA 0   // variant l1_cta: always k_search_l1<false> for K = 1 (the kernel-equivalence tests)
 #endif
@@ -2579,7 +2594,9 @@ int launch_search(const SearchArgs &a_in, bool e1b, int sm_count, cudaStream_t s
 #elif defined(ACQ_VARIANT_L1_ST)
     else if (kind == kSearchL1Dr) launch_k(k_search_l1_st, grid, kStThreads, st_smem_bytes(), st, pdl, a);
 #endif
+#if ACQ_DR_MIN_TILES_PER_SM >= 0
     else if (kind == kSearchL1Dr) launch_k(k_search_l1_dr, grid, kStThreads, dr_smem_bytes(), st, pdl, a);
+#endif
     else launch_k(k_search_l1<false>, grid, 256, search_l1_smem_bytes(), st, pdl, a);
 #endif
     return 1;
